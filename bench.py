@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Headline benchmark: `Flow.log_prob` samples/s on the MNIST-shape USFlow stack (BASELINE.json
+configs[1]: D=784 NonUSFlow, K=8 coupling blocks, conditioner MLP 784-256-256-1568, LU + Householder
+affine conjugation, Normal base), synthetic data, batch-sharded over N GPUs (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# ---- workload: BASELINE.json configs[1] / SURVEY.md section 8(d) "C2 MNIST" --------------------------------
+D, K_BLOCKS, HIDDEN = 784, 8, [256, 256]
+ROWS_PER_GPU = 65536
+ALG_FLOP_PER_SAMPLE = 26.84e6      # mask-pruned, conditioner counted once (SURVEY 8d / BASELINE.md section 4)
+ALG_BYTES_PER_SAMPLE = 4 * D + 4
+LAST_LAYER_GAIN = 0.25             # trained-flow-like activations (see DESIGN.md "Synthetic weights")
+CPU_SAMPLE_ROWS = 4096
+
+
+def build_flow(ns, device, dtype=torch.float32):
+    from _cases import build_flow as _bf, tame
+    torch.manual_seed(0)
+    flow = _bf(ns, "NonUSFlow", D, K_BLOCKS, ("mlp", HIDDEN), base="normal",
+               affine_conjugation=True, prior_scale=1.0)
+    tame(flow, LAST_LAYER_GAIN)
+    return flow.to(device).eval()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+def cpu_reference_run(steps, warmup, rows):
+    """The reference's CPU PyTorch path for the same workload: the oracle's restatement of
+    `nf4ad.flows.NonUSFlow` + `MaskedAffineCoupling` on the `src.usflows` shim (the genuine USFlows /
+    pyro packages are not installable), fp32, eval() + no_grad() as `adbench_wrapper.py:422-424`,
+    all host threads."""
+    import oracle
+    O = oracle.load()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    flow = build_flow(O, "cpu")
+    x = torch.randn(rows, D, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        for _ in range(warmup):
+            flow.log_prob(x)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            flow.log_prob(x)
+            ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return rows * steps / total, cores, total / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "C2 MNIST-shape NonUSFlow log_prob scoring: D=784, K=8, MLP 784-256-256-1568, "
+                          "LU+Householder conjugation, Normal base",
+              "rows_per_gpu": args.rows, "global_rows": args.rows * max(world, 1), "parallelism": f"batch-shard x{world}",
+              "l2_policy": "inputs larger than L2 (205 MB fp32 per GPU), no flush needed",
+              "weights": "seeded init (seed 0), last conditioner layer x0.25"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rows = CPU_SAMPLE_ROWS
+        v, cores, ms = cpu_reference_run(args.steps, args.warmup, rows)
+        line = {"impl": "reference", "metric": "log_prob samples/sec", "value": v, "unit": "samples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config, rows_per_step=rows),
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": f"{rows} rows x {args.steps} steps of the same stack (oracle port of the "
+                                           "reference's PyTorch path; real USFlows/pyro not installable)"},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import nf4ad_b200
+    from nf4ad_b200 import _lib
+    from nf4ad_b200.parallel import ShardedScorer
+    P = nf4ad_b200.namespace()
+    flow = build_flow(P, dev)
+    flow.precision = args.precision
+    B = args.rows
+    gen = torch.Generator().manual_seed(42 + rank)
+    x_host = torch.randn(B, D, generator=gen).pin_memory()
+    x = x_host.to(dev)
+    scorer = ShardedScorer(flow)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K steps of the fused launch chain -----------------------------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            lp = scorer.score_local(x)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            lp = scorer.score_local(x)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches_per_step = flow.last_launches
+        assert launches_per_step > 0, "fused CUDA path did not run"
+        assert bool(torch.isfinite(lp).all())
+
+        # ---- end to end through the public API: pinned host rows -> H2D -> log_prob -> scores D2H, every step
+        # (the call sequence of ADBenchFlow.predict_score, adbench_wrapper.py:419-433) + score gather to rank 0
+        for _ in range(2):
+            scorer.predict_score_host(x_host)
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            scores = scorer.predict_score_host(x_host, gather=True)
+        f1.record()
+        barrier()
+        e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0)
+
+        # ---- per-launch device time of every kernel of one step (CUDA events on the launching stream)
+        n_prof = launches_per_step * 3
+        _lib.check(_lib.lib().usf_profile_begin(n_prof + 8))
+        for _ in range(3):
+            scorer.score_local(x)
+        ms = (ctypes.c_float * (n_prof + 8))()
+        tags = (ctypes.c_int * (n_prof + 8))()
+        n = ctypes.c_int(0)
+        _lib.check(_lib.lib().usf_profile_end(ms, tags, ctypes.byref(n)))
+        per_tag = {}
+        for i in range(n.value):
+            per_tag.setdefault(tags[i], []).append(ms[i])
+    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        n_gemm = sum(len(v) for k, v in per_tag.items() if k != 0)
+        gemm_ms = sum(sum(v) for k, v in per_tag.items() if k != 0)
+        steps_prof = 3
+        gemm_ms_per_step = gemm_ms / steps_prof
+        avg_launch_ms = gemm_ms / max(n_gemm, 1)
+        flop_per_launch = ALG_FLOP_PER_SAMPLE * B / (n_gemm / steps_prof)
+        achieved = flop_per_launch / (avg_launch_ms * 1e-3) / 1e12
+        peak, peak_src = measured_peak_tflops()
+        value = B * world * args.steps / (ms_total * 1e-3)
+        e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+        names = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base"}
+        line = {
+            "metric": "log_prob samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "kernel": _lib.lib().usf_gemm_kernel_name(
+                             _lib.USF_PREC_BF16 if args.precision == "bf16" else _lib.USF_PREC_FP32).decode(),
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "alg_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_ms,
+                         "gemm_share_of_step": gemm_ms_per_step / (ms_total / args.steps),
+                         "launch_ms_by_kind": {names[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},
+                         "launches_by_kind": {names[k]: len(v) // steps_prof for k, v in sorted(per_tag.items())}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, cms = cpu_reference_run(3, 1, CPU_SAMPLE_ROWS)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_ROWS} rows x 3 steps of the same stack, fp32, "
+                                              f"{cores} threads ({cms:.0f} ms/step)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

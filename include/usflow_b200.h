@@ -1,0 +1,250 @@
+/*
+ * usflow_b200.h -- C ABI of the B200-native USFlows density path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (libusflow_b200.so,
+ * sm_100a only) that the Python mirror of the USFlows module API
+ * (nf4ad_b200/, import names `src.usflows.*`) binds with ctypes.  There are no
+ * torch types in any signature: raw device pointers, int64 sizes / leading
+ * dimensions (in elements), a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - every matrix is row-major; `(B, D)` activations are fp32 with leading
+ *     dimension `ld*` (elements); bf16 buffers are `uint16_t*`.
+ *   - the CALLER allocates every output and workspace; the library never
+ *     allocates device memory, frees, or keeps a pointer past the call.
+ *   - all entry points return 0 on success, or a negative USF_E_* code;
+ *     `usf_last_error()` gives the thread-local message.
+ *   - every call only enqueues work on `stream` (no host sync), so the chain is
+ *     CUDA-graph capturable; re-entrant across streams/threads.
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points
+ *     return USF_E_CUDA.
+ *
+ * "Reference interface" citations are file:line in /root/reference (nf4ad) or,
+ * where the arithmetic lives in the un-vendored USFlows package, the nf4ad call
+ * site that fixes the contract.
+ */
+#ifndef USFLOW_B200_H
+#define USFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USF_VERSION 100 /* 0.1.0 */
+
+#define USF_OK 0
+#define USF_E_ARG (-1)       /* bad argument (null pointer, negative size, unsupported combination) */
+#define USF_E_CUDA (-2)      /* CUDA runtime / launch error (message has cudaGetErrorString) */
+#define USF_E_WORKSPACE (-3) /* caller workspace too small */
+#define USF_E_UNSUPPORTED (-4)
+
+typedef void* usf_stream_t; /* cudaStream_t */
+
+int usf_version(void);
+const char* usf_last_error(void);
+/* 1 if a CUDA device with compute capability 10.x is usable by this process, else 0. */
+int usf_device_ok(void);
+
+/* ------------------------------------------------------------------------- */
+/* Layer kernels (fp32).  One entry point per bijector of the BaseTransform   */
+/* protocol `forward / backward / log_abs_det_jacobian`                       */
+/* (/root/reference/src/nf4ad/transforms.py:66-140).                          */
+/* ------------------------------------------------------------------------- */
+
+/* LUTransform parameter packing: W = (tril(L_raw,-1)+I) * triu(U_raw)  (D x D),
+ * logabsdet[0] = sum_i log|U_ii|  (data-independent log-det folded into a constant).
+ * Replaces USFlows LUTransform weight build; call site nf4ad/flows.py:85,110. */
+int usf_lu_pack(const float* L_raw, const float* U_raw, int64_t D, float* W, float* logabsdet,
+                float* scratch /* 2*D*D floats */, usf_stream_t stream);
+
+/* y = x W^T + bias : LUTransform.forward / any dense affine map / nn.Linear.
+ * relu != 0 applies max(0, .) (conditioner hidden layers, tests/conftest.py:114-118).
+ * x:(B,K) ldx, W:(N,K) ldw, y:(B,N) ldy. */
+int usf_linear(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, int relu,
+               float* y, int64_t ldy, int64_t B, int64_t N, int64_t K, usf_stream_t stream);
+
+/* x = U^{-1} L^{-1} (y - bias): LUTransform.backward as a blocked triangular solve
+ * (forward substitution with unit-lower L, back substitution with U).  In place
+ * (x == y) is allowed.  bias may be NULL.  transpose != 0 solves with (L U)^T instead
+ * (the input-gradient of the same layer).  nf4ad/flows.py:85 -> Flow.log_prob inverse direction. */
+int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, const float* U_raw, const float* bias,
+                 int transpose, float* x, int64_t ldx, int64_t B, int64_t D, usf_stream_t stream);
+
+/* Product of nvs Householder reflections H_v = I - 2 v v^T/|v|^2, applied in storage
+ * order (reverse != 0: last first = the inverse map).  V:(nvs,D).  nf4ad/flows.py:90. */
+int usf_householder(const float* x, int64_t ldx, const float* V, int64_t nvs, int reverse, float* y,
+                    int64_t ldy, int64_t B, int64_t D, usf_stream_t stream);
+
+/* y = x * scale (inverse != 0: x / scale).  ScaleTransform, nf4ad/flows.py:113. */
+int usf_scale(const float* x, int64_t ldx, const float* scale, int inverse, float* y, int64_t ldy,
+              int64_t B, int64_t D, usf_stream_t stream);
+
+/* out[0] = sum_i log|v_i| : the constant log-det of Scale / diag(U). */
+int usf_sum_log_abs(const float* v, int64_t n, int64_t stride, float* out, usf_stream_t stream);
+
+/* Masked coupling epilogue given conditioner outputs s,t:(B,D) (s == NULL: additive,
+ * USFlows MaskedCoupling).  log_s = clamp*tanh(s).
+ *   inverse == 0: y = m*x + (1-m)*(x*exp(log_s) + t)      nf4ad/transforms.py:66-90
+ *   inverse != 0: y = m*x + (1-m)*((x - t)*exp(-log_s))   nf4ad/transforms.py:92-113
+ * ladj (optional, (B,)): ladj[b] += ladj_coef * sum_d (1-m_d) log_s[b,d]   (:115-140)
+ * In place (y == x) allowed. */
+int usf_coupling(const float* x, int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
+                 const float* mask, float clamp, int inverse, float* y, int64_t ldy, float* ladj,
+                 float ladj_coef, int64_t B, int64_t D, usf_stream_t stream);
+
+/* Base log-density summed over the event dim (Independent(base,1).log_prob):
+ *   kind 0 Normal : -0.5*((z-loc)/scale)^2 - log scale - 0.5 log 2pi
+ *   kind 1 Laplace: -|z-loc|/scale - log(2 scale)
+ * loc:(D), scale:(scale_numel in {1,D}).  out[b] = sum_d(...) + (add ? add_coef*add[b] : 0).
+ * tests/conftest.py:105-108, experiments/fashion/fashion.yaml:55-60. */
+int usf_base_logprob(int kind, const float* z, int64_t ldz, const float* loc, const float* scale,
+                     int64_t scale_numel, const float* add, float add_coef, float* out, int64_t B,
+                     int64_t D, usf_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Training backward of the layer kernels (autograd of                        */
+/* `loss = -log_prob.mean(); loss.backward()`, adbench_wrapper.py:383-386).   */
+/* ------------------------------------------------------------------------- */
+
+/* Backward of y = x W^T + b (optionally through relu, given y):
+ *   dx = dy W (dx may be NULL), dW (+)= dy^T x, db (+)= colsum(dy).  accumulate != 0 adds. */
+int usf_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* W,
+                   int64_t ldw, const float* y_relu, int64_t ldyr, float* dx, int64_t lddx, float* dW,
+                   int64_t lddw, float* db, int accumulate, float* scratch, int64_t B, int64_t N,
+                   int64_t K, usf_stream_t stream);
+/* bytes of `scratch` needed by usf_linear_bwd (masked dy copy when y_relu != NULL). */
+size_t usf_linear_bwd_scratch_bytes(int64_t B, int64_t N);
+
+/* Chain rule from W = L*U to the raw factors: dL_raw += strict_lower(dW U^T),
+ * dU_raw += upper(L^T dW); dU_raw_ii += dlogdet / U_ii. */
+int usf_lu_pack_bwd(const float* dW, const float* L_raw, const float* U_raw, float dlogdet, int64_t D,
+                    float* dL_raw, float* dU_raw, float* scratch /* 3*D*D floats */,
+                    usf_stream_t stream);
+
+/* Backward of usf_scale.  `xy` is the layer INPUT x (inverse == 0) or OUTPUT y (inverse != 0);
+ * dx = dy*scale (or dy/scale), dscale[d] += sum_b ... (atomic accumulate, may be NULL). */
+int usf_scale_bwd(const float* dy, int64_t lddy, const float* xy, int64_t ldxy, const float* scale,
+                  int inverse, float* dx, int64_t lddx, float* dscale, int64_t B, int64_t D,
+                  usf_stream_t stream);
+
+/* out[c] (+)= coef * sum_b a[b,c]  (bias gradients). */
+int usf_colsum(const float* a, int64_t lda, float coef, int accumulate, float* out, int64_t B, int64_t N,
+               usf_stream_t stream);
+
+/* Plain fp32 GEMM C[M,N] (+)= opA(A) * opB(B)^T used by the backward pass:
+ * a_trans == 0: A[m*lda+k], 1: A[k*lda+m];  b_trans == 0: B[n*ldb+k], 1: B[k*ldb+n]. */
+int usf_gemm(const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb, int b_trans, float* C,
+             int64_t ldc, int accumulate, int64_t M, int64_t N, int64_t K, usf_stream_t stream);
+
+/* Backward of usf_coupling in the direction that was run (needs the layer INPUT x, s, t):
+ * produces dx, ds (NULL if additive), dt from dy and dladj (scalar per row, may be NULL). */
+int usf_coupling_bwd(const float* dy, int64_t lddy, const float* dladj, float ladj_coef, const float* x,
+                     int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
+                     const float* mask, float clamp, int inverse, float* dx, int64_t lddx, float* ds,
+                     int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D, usf_stream_t stream);
+
+/* Backward of usf_householder: dx and dV (+=) from dy, given the layer input x. scratch: B*D floats * (nvs+1). */
+int usf_householder_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* V,
+                        int64_t nvs, int reverse, float* dx, int64_t lddx, float* dV, float* scratch,
+                        int64_t B, int64_t D, usf_stream_t stream);
+
+/* Backward of usf_base_logprob w.r.t. z (dz = dout[b] * d logp/dz) and the per-dim sums needed for
+ * loc / scale gradients: dloc[d] += ..., dscale[d or 0] += ... (either may be NULL). */
+int usf_base_logprob_bwd(int kind, const float* dout, const float* z, int64_t ldz, const float* loc,
+                         const float* scale, int64_t scale_numel, float* dz, int64_t lddz, float* dloc,
+                         float* dscale, int64_t B, int64_t D, usf_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Weight packing for the fused stack (runs once per weight version).         */
+/* ------------------------------------------------------------------------- */
+
+/* Generic gather/pack:  out[r, c] = src[row_idx[r], col_idx[c]] - (sub_row0 ? src[0, col_idx[c]] : 0)
+ * (transpose_src != 0: out[r, c] = src[col_idx[c], row_idx[r]] - (sub_row0 ? src[0, row_idx[r]] : 0));
+ * any index < 0 -> 0; idx == NULL -> identity.  Writes fp32 `out` (may be NULL) and/or bf16
+ * `out_bf16` (may be NULL), both with leading dimension ldo; columns [n_cols, ldo) are zeroed. */
+int usf_pack_matrix(const float* src, int64_t lds, const int32_t* row_idx, const int32_t* col_idx,
+                    int sub_row0, int transpose_src, int64_t n_rows, int64_t n_cols, float* out,
+                    uint16_t* out_bf16, int64_t ldo, usf_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Fused stack: Flow.log_prob / Flow.backward / Flow.forward(sample) as ONE    */
+/* call over a packed layer-descriptor array                                   */
+/* (USFlows Flow.log_prob = TransformedDistribution.log_prob; callers          */
+/*  adbench_wrapper.py:383,424, vaeflow.py:201,240).                           */
+/* ------------------------------------------------------------------------- */
+
+#define USF_PREC_FP32 0 /* SIMT FFMA GEMMs, fp32 activations: log_prob rel. err <= 1e-4 tier */
+#define USF_PREC_BF16 1 /* tcgen05 bf16 GEMMs (fp32 accumulate in TMEM), bf16 activations: <= 1e-2 tier */
+
+#define USF_MAX_MLP 8
+
+typedef struct {
+  const float* W;      /* (N, ldw) fp32, K-major rows (used by USF_PREC_FP32) */
+  const uint16_t* Wb;  /* same matrix in bf16 (used by USF_PREC_BF16), may be NULL */
+  const float* bias;   /* (N) */
+  int32_t N, K, ldw;
+} usf_linear_desc;
+
+typedef struct {
+  usf_linear_desc G;   /* dense affine map applied BEFORE the coupling: u = G x + g; output columns are
+                          [a-part (Da) | zero pad | b-part (Db) starting at column b_off] */
+  int32_t b_off;       /* first column of the transformed (b) coordinates in the activation row */
+  int32_t n_mlp;       /* conditioner Linear layers; all but the last are followed by ReLU */
+  usf_linear_desc mlp[USF_MAX_MLP]; /* first: K = Da (conditioning coords); last: rows packed per tile [s(C)|t(C)] or [t(C)] */
+  int32_t Da, Db;      /* |mask==1| conditioning coords, |mask==0| transformed coords; Da + Db = D */
+  int32_t C;           /* coords per output tile of the last layer */
+  int32_t affine;      /* 1: (s,t) affine coupling (nf4ad MaskedAffineCoupling); 0: additive (USFlows MaskedCoupling) */
+  float clamp;         /* log_s = clamp * tanh(s) */
+} usf_block_desc;
+
+typedef struct {
+  int32_t D;
+  int32_t n_blocks;
+  const usf_block_desc* blocks; /* HOST pointer to n_blocks descriptors, in execution order */
+  usf_linear_desc G_final;      /* last affine map (outputs in natural coordinate order) */
+  int32_t inverse;              /* 1: data -> latent direction (couplings inverted; log_prob/backward); 0: generative */
+  int32_t base_kind;            /* -1: none (transform only), 0: Normal, 1: Laplace */
+  const float* loc;             /* (D) */
+  const float* inv_scale;       /* (D) 1/scale */
+  float const_term;             /* sum of all data-independent terms (affine log-dets, -sum log scale, -D/2 log 2pi ...) */
+} usf_stack_desc;
+
+/* Workspace bytes needed to push up to B rows through the stack at the given precision. */
+size_t usf_stack_workspace_bytes(const usf_stack_desc* st, int64_t B, int precision);
+
+/* Runs the whole stack on x:(B,D) fp32.
+ *   out_logprob (B) : log p(x) (requires st->inverse==1 and base_kind >= 0); may be NULL
+ *   out_y (B,D) ldy : transformed points (latent z if inverse, data x if generative); may be NULL
+ *   out_ladj (B)    : accumulated log|det| of the applied direction (optional)
+ * gpu_launches (optional host int) receives the number of kernels enqueued. */
+int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                  float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                  int precision, int* gpu_launches, usf_stream_t stream);
+
+/* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
+ * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
+ * synchronises and returns per-launch device milliseconds and a tag per launch
+ * (0 input pack, 1 affine GEMM, 2 conditioner hidden GEMM, 3 last conditioner GEMM + coupling
+ * epilogue, 4 final GEMM + base density).  ms/tags must hold max_launches entries. */
+int usf_profile_begin(int max_launches);
+int usf_profile_end(float* ms, int* tags, int* n_out);
+
+/* Debug: reads (and optionally clears) the flag raised when a bounded mbarrier wait of the tcgen05
+ * GEMM expired (a pipeline protocol bug); synchronises the device. */
+int usf_debug_tc_timeout(int* flag, int reset);
+
+/* Standalone bf16 tensor-core GEMM y = act(x W^T + bias) (testing / conditioner layers):
+ * x:(B,K) bf16 ldx, W:(N,K) bf16 ldw (ld multiples of 8, N multiple of 16), y:(B,N) bf16 or fp32. */
+int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias, int relu,
+                    void* y, int64_t ldy, int y_is_bf16, int64_t B, int64_t N, int64_t K, usf_stream_t stream);
+
+/* Name of the dominant GEMM kernel of the given precision (for profiler filters). */
+const char* usf_gemm_kernel_name(int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USFLOW_B200_H */

@@ -1,0 +1,124 @@
+"""ctypes binding of libusflow_b200.so (the C ABI in include/usflow_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or a compute entry point is
+called without a CUDA (sm_100) device / on a non-CUDA tensor, this module raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libusflow_b200.so")
+
+USF_PREC_FP32 = 0
+USF_PREC_BF16 = 1
+USF_MAX_MLP = 8
+
+_i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
+_int = C.c_int
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("W", _vp), ("Wb", _vp), ("bias", _vp), ("N", _i32), ("K", _i32), ("ldw", _i32)]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("G", LinearDesc), ("b_off", _i32), ("n_mlp", _i32), ("mlp", LinearDesc * USF_MAX_MLP),
+                ("Da", _i32), ("Db", _i32), ("C", _i32), ("affine", _i32), ("clamp", _f32)]
+
+
+class StackDesc(C.Structure):
+    _fields_ = [("D", _i32), ("n_blocks", _i32), ("blocks", C.POINTER(BlockDesc)), ("G_final", LinearDesc),
+                ("inverse", _i32), ("base_kind", _i32), ("loc", _vp), ("inv_scale", _vp), ("const_term", _f32)]
+
+
+# name -> (restype, argtypes); mirrors include/usflow_b200.h one to one
+_PROTOS = {
+    "usf_version": (_int, []),
+    "usf_last_error": (C.c_char_p, []),
+    "usf_device_ok": (_int, []),
+    "usf_lu_pack": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "usf_linear": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "usf_lu_solve": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
+    "usf_householder": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
+    "usf_scale": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
+    "usf_sum_log_abs": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "usf_coupling": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _vp, _i64, _vp, _f32, _i64, _i64, _vp]),
+    "usf_base_logprob": (_int, [_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _vp, _i64, _i64, _vp]),
+    "usf_linear_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _int, _vp,
+                              _i64, _i64, _i64, _vp]),
+    "usf_linear_bwd_scratch_bytes": (_sz, [_i64, _i64]),
+    "usf_lu_pack_bwd": (_int, [_vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp]),
+    "usf_scale_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _vp, _i64, _i64, _vp]),
+    "usf_colsum": (_int, [_vp, _i64, _f32, _int, _vp, _i64, _i64, _vp]),
+    "usf_gemm": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp]),
+    "usf_coupling_bwd": (_int, [_vp, _i64, _vp, _f32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _vp, _i64,
+                                _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "usf_householder_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "usf_base_logprob_bwd": (_int, [_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "usf_pack_matrix": (_int, [_vp, _i64, _vp, _vp, _int, _int, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "usf_stack_workspace_bytes": (_sz, [C.POINTER(StackDesc), _i64, _int]),
+    "usf_stack_run": (_int, [C.POINTER(StackDesc), _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _sz, _int,
+                             C.POINTER(_int), _vp]),
+    "usf_profile_begin": (_int, [_int]),
+    "usf_profile_end": (_int, [C.POINTER(_f32), C.POINTER(_int), C.POINTER(_int)]),
+    "usf_debug_tc_timeout": (_int, [C.POINTER(_int), _int]),
+    "usf_linear_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp]),
+    "usf_gemm_kernel_name": (C.c_char_p, [_int]),
+}
+
+EXPORTED = tuple(_PROTOS)
+_lib = None
+
+
+class USFError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise USFError(
+                f"{LIB_PATH} is missing: build it with `python -m nf4ad_b200.build` "
+                "(the B200 path has no CPU/PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().usf_last_error().decode("utf-8", "replace")
+        raise USFError(f"{what or 'usflow_b200'} failed (code {rc}): {msg}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise USFError(
+                "nf4ad_b200 runs on CUDA (sm_100a) tensors only and has no CPU fallback; got a "
+                f"{t.device} tensor. Move the flow and its inputs to a B200 (`flow.to('cuda')`).")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32c(t):
+    """fp32, last-dim-contiguous 2-D view (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    return t

@@ -1,0 +1,314 @@
+// Host side of the C ABI: error plumbing, device probe, and the fused-stack runner that turns a packed
+// layer-descriptor array into one launch chain (Flow.log_prob / Flow.backward / Flow.forward).
+#include <stdarg.h>
+
+#include "usf_common.cuh"
+
+namespace usf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return USF_E_CUDA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+namespace {
+
+// Measurement-only, thread-local: when enabled, usf_stack_run brackets every kernel it enqueues with
+// CUDA events on the launching stream so bench.py can report the per-launch device time of each kernel.
+struct Profile {
+  bool on = false;
+  int cap = 0;
+  int n = 0;
+  cudaEvent_t* ev = nullptr;  // 2 events per launch
+  int* tag = nullptr;
+};
+thread_local Profile g_prof;
+
+struct ProfScope {
+  cudaStream_t s;
+  int idx;
+  ProfScope(cudaStream_t st, int tag) : s(st), idx(-1) {
+    if (g_prof.on && g_prof.n < g_prof.cap) {
+      idx = g_prof.n++;
+      g_prof.tag[idx] = tag;
+      cudaEventRecord(g_prof.ev[2 * idx], s);
+    }
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.ev[2 * idx + 1], s);
+  }
+};
+
+struct StackPlan {
+  int64_t ld_act;     // activation leading dimension (elements)
+  int64_t ld_hid;     // hidden leading dimension (elements)
+  size_t act_bytes;   // one activation buffer for `rows` rows
+  size_t hid_bytes;
+  size_t acc_bytes;
+  size_t total;
+};
+
+constexpr int64_t kChunkRows = 131072;  // rows pushed through the stack per pass (bounds the workspace)
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan* p) {
+  USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0, "stack: bad descriptor");
+  USF_CHECK_ARG(st->n_blocks == 0 || st->blocks != nullptr, "stack: blocks pointer is null");
+  USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16, "stack: unknown precision %d", precision);
+  int64_t wmax = st->D, hmax = 16;
+  for (int b = 0; b < st->n_blocks; ++b) {
+    const usf_block_desc& blk = st->blocks[b];
+    USF_CHECK_ARG(blk.n_mlp >= 1 && blk.n_mlp <= USF_MAX_MLP, "stack: block %d has %d conditioner layers", b, blk.n_mlp);
+    if (blk.G.N > wmax) wmax = blk.G.N;
+    if (blk.G.K > wmax) wmax = blk.G.K;
+    for (int l = 0; l + 1 < blk.n_mlp; ++l)
+      if (blk.mlp[l].N > hmax) hmax = blk.mlp[l].N;
+  }
+  if (st->G_final.K > wmax) wmax = st->G_final.K;
+  const size_t esz = precision == USF_PREC_BF16 ? 2 : 4;
+  p->ld_act = round_up(wmax, 16);
+  p->ld_hid = round_up(hmax, 16);
+  p->act_bytes = align256((size_t)rows * p->ld_act * esz);
+  p->hid_bytes = align256((size_t)rows * p->ld_hid * esz);
+  p->acc_bytes = align256((size_t)rows * sizeof(float));
+  p->total = 2 * p->act_bytes + 2 * p->hid_bytes + p->acc_bytes + 256;
+  return USF_OK;
+}
+
+}  // namespace
+}  // namespace usf
+
+using namespace usf;
+
+extern "C" int usf_version(void) { return USF_VERSION; }
+extern "C" const char* usf_last_error(void) { return g_err; }
+
+extern "C" int usf_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" const char* usf_gemm_kernel_name(int precision) {
+  return precision == USF_PREC_BF16 ? kTcGemmKernelName : kSimtGemmKernelName;
+}
+
+extern "C" int usf_debug_tc_timeout(int* flag, int reset) { return tc_timeout_flag(flag, reset); }
+
+extern "C" int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias,
+                               int relu, void* y, int64_t ldy, int y_is_bf16, int64_t B, int64_t N, int64_t K,
+                               usf_stream_t stream) {
+  USF_CHECK_ARG(x && W && y && bias, "usf_linear_bf16: null pointer");
+  EpiParams ep{};
+  ep.mode = relu ? EPI_BIAS_RELU : EPI_BIAS;
+  ep.bias = bias;
+  ep.out = y;
+  ep.ldo = ldy;
+  ep.out_bf16 = y_is_bf16;
+  return tc_gemm(x, ldx, W, ldw, B, N, K, tc_pick_bn(N), ep, as_stream(stream));
+}
+
+extern "C" int usf_profile_begin(int max_launches) {
+  USF_CHECK_ARG(max_launches > 0 && !g_prof.on, "usf_profile_begin: bad state");
+  g_prof.ev = new cudaEvent_t[2 * (size_t)max_launches];
+  g_prof.tag = new int[max_launches];
+  for (int i = 0; i < 2 * max_launches; ++i) USF_CUDA(cudaEventCreate(&g_prof.ev[i]));
+  g_prof.cap = max_launches;
+  g_prof.n = 0;
+  g_prof.on = true;
+  return USF_OK;
+}
+
+extern "C" int usf_profile_end(float* ms, int* tags, int* n_out) {
+  USF_CHECK_ARG(g_prof.on, "usf_profile_end: profiling is not active");
+  g_prof.on = false;
+  int rc = USF_OK;
+  for (int i = 0; i < g_prof.n; ++i) {
+    if (cudaEventSynchronize(g_prof.ev[2 * i + 1]) != cudaSuccess) rc = USF_E_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) != cudaSuccess) rc = USF_E_CUDA;
+    if (ms) ms[i] = t;
+    if (tags) tags[i] = g_prof.tag[i];
+  }
+  if (n_out) *n_out = g_prof.n;
+  for (int i = 0; i < 2 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
+  delete[] g_prof.ev;
+  delete[] g_prof.tag;
+  g_prof = Profile();
+  if (rc) set_error("usf_profile_end: event query failed");
+  return rc;
+}
+
+extern "C" size_t usf_stack_workspace_bytes(const usf_stack_desc* st, int64_t B, int precision) {
+  StackPlan p;
+  const int64_t rows = B < kChunkRows ? (B > 0 ? B : 1) : kChunkRows;
+  if (plan_stack(st, rows, precision, &p) != USF_OK) return 0;
+  return p.total;
+}
+
+extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                             float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                             int precision, int* gpu_launches, usf_stream_t stream) {
+  USF_CHECK_ARG(st != nullptr && x != nullptr && B >= 0, "usf_stack_run: bad arguments");
+  USF_CHECK_ARG(!(out_logprob && (st->base_kind < 0 || !st->inverse)),
+                "usf_stack_run: log_prob needs the inverse direction and a base distribution");
+  USF_CHECK_ARG(!(out_logprob && out_ladj), "usf_stack_run: request log_prob or ladj, not both");
+  USF_CHECK_ARG(ldx >= st->D && (out_y == nullptr || ldy >= st->D), "usf_stack_run: leading dimension < D");
+  if (gpu_launches) *gpu_launches = 0;
+  if (B == 0) return USF_OK;
+  const int64_t rows_max = B < kChunkRows ? B : kChunkRows;
+  StackPlan p;
+  int rc = plan_stack(st, rows_max, precision, &p);
+  if (rc) return rc;
+  if (workspace == nullptr || workspace_bytes < p.total) {
+    set_error("usf_stack_run: workspace too small (%zu < %zu bytes)", workspace_bytes, p.total);
+    return USF_E_WORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream);
+  const bool bf16 = precision == USF_PREC_BF16;
+  const size_t esz = bf16 ? 2 : 4;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  uint8_t* act[2] = {base, base + p.act_bytes};
+  uint8_t* hid[2] = {base + 2 * p.act_bytes, base + 2 * p.act_bytes + p.hid_bytes};
+
+  int launches = 0;
+
+  // One GEMM of the chain at the chosen precision.
+  auto gemm = [&](const void* A, int64_t lda, const usf_linear_desc& L, int bn, EpiParams& ep, int64_t rows) -> int {
+    if (bf16) {
+      USF_CHECK_ARG(L.Wb != nullptr, "usf_stack_run: bf16 weights missing in descriptor");
+      return tc_gemm(reinterpret_cast<const uint16_t*>(A), lda, L.Wb, L.ldw, rows, L.N, L.K, bn, ep, s);
+    }
+    USF_CHECK_ARG(L.W != nullptr, "usf_stack_run: fp32 weights missing in descriptor");
+    return simt_gemm(reinterpret_cast<const float*>(A), lda, 0, L.W, L.ldw, 0, rows, L.N, L.K, ep, s);
+  };
+
+  for (int64_t r0 = 0; r0 < B; r0 += kChunkRows) {
+    const int64_t rows = (B - r0) < kChunkRows ? (B - r0) : kChunkRows;
+    float* row_acc = out_logprob ? out_logprob + r0 : (out_ladj ? out_ladj + r0 : nullptr);
+    const float acc_init = out_logprob ? st->const_term : 0.f;
+
+
+    // stage 0: bring x into the activation layout (bf16, or padded fp32) and seed the per-row accumulator
+    int cur = 0;
+    {
+      ProfScope ps(s, 0);
+      rc = launch_convert_rows(x + r0 * ldx, ldx, bf16 ? reinterpret_cast<uint16_t*>(act[0]) : nullptr,
+                               bf16 ? nullptr : reinterpret_cast<float*>(act[0]), p.ld_act, rows, st->D, row_acc,
+                               acc_init, s);
+    }
+    if (rc) return rc;
+    ++launches;
+
+    for (int b = 0; b < st->n_blocks; ++b) {
+      const usf_block_desc& blk = st->blocks[b];
+      // (1) dense affine map u = G x + g, written in [a | pad | b] column order
+      {
+        EpiParams ep{};
+        ep.mode = EPI_BIAS;
+        ep.bias = blk.G.bias;
+        ep.out = act[cur ^ 1];
+        ep.ldo = p.ld_act;
+        ep.out_bf16 = bf16;
+        {
+          ProfScope ps(s, 1);
+          rc = gemm(act[cur], p.ld_act, blk.G, bf16 ? tc_pick_bn(blk.G.N) : 0, ep, rows);
+        }
+        if (rc) return rc;
+        ++launches;
+        cur ^= 1;
+      }
+      // (2) conditioner MLP on the a-part, last layer fused with the coupling update of the b-part
+      const void* in = act[cur];
+      int64_t ld_in = p.ld_act;
+      for (int l = 0; l < blk.n_mlp; ++l) {
+        const usf_linear_desc& L = blk.mlp[l];
+        EpiParams ep{};
+        ep.bias = L.bias;
+        int bn = 0;
+        if (l + 1 < blk.n_mlp) {
+          ep.mode = EPI_BIAS_RELU;
+          ep.out = hid[l & 1];
+          ep.ldo = p.ld_hid;
+          ep.out_bf16 = bf16;
+          if (bf16) bn = tc_pick_bn(L.N);
+        } else {
+          if (blk.affine) ep.mode = st->inverse ? EPI_COUPLING_INV : EPI_COUPLING_FWD;
+          else ep.mode = st->inverse ? EPI_ADD_INV : EPI_ADD_FWD;
+          ep.ub = act[cur] + (size_t)blk.b_off * esz;
+          ep.ldub = p.ld_act;
+          ep.ub_bf16 = bf16;
+          ep.Db = blk.Db;
+          ep.C = blk.C;
+          ep.clamp = blk.clamp;
+          ep.row_acc = row_acc;
+          if (bf16) bn = blk.affine ? 2 * blk.C : blk.C;
+        }
+        {
+          ProfScope ps(s, l + 1 < blk.n_mlp ? 2 : 3);
+          rc = gemm(in, ld_in, L, bn, ep, rows);
+        }
+        if (rc) return rc;
+        ++launches;
+        in = hid[l & 1];
+        ld_in = p.ld_hid;
+      }
+    }
+    // (3) last affine map, fused with the base log-density when a density is requested
+    {
+      EpiParams ep{};
+      ep.bias = st->G_final.bias;
+      ep.n_valid = st->D;
+      ep.out = out_y ? out_y + r0 * ldy : nullptr;
+      ep.ldo = ldy;
+      ep.out_bf16 = 0;
+      if (out_logprob) {
+        ep.mode = st->base_kind == 0 ? EPI_BASE_NORMAL : EPI_BASE_LAPLACE;
+        ep.loc = st->loc;
+        ep.inv_scale = st->inv_scale;
+        ep.row_acc = row_acc;
+      } else {
+        USF_CHECK_ARG(out_y != nullptr, "usf_stack_run: nothing to compute (no output requested)");
+        ep.mode = EPI_BIAS;
+      }
+      // fp32 path: the SIMT kernel stores exactly N = D columns
+      usf_linear_desc Lf = st->G_final;
+      if (!bf16) Lf.N = st->D;
+      {
+        ProfScope ps(s, 4);
+        rc = gemm(act[cur], p.ld_act, Lf, bf16 ? tc_pick_bn(Lf.N) : 0, ep, rows);
+      }
+      if (rc) return rc;
+      ++launches;
+    }
+  }
+  if (gpu_launches) *gpu_launches = launches;
+  return USF_OK;
+}

@@ -1,0 +1,1083 @@
+// fp32 SIMT kernels of the usflow_b200 library (sm_100a).
+//
+//  * simt_gemm: 128x128x16 register-tiled FFMA GEMM with the fused layer epilogues (EpiParams): the
+//    fp32-accuracy path of every dense contraction (LU apply, conditioner MLP) and of the fused stack.
+//  * trsm_rows: blocked triangular solve over batch rows (LUTransform.backward).
+//  * row kernels (one warp per sample row): Householder, scale, coupling, base log-density and their
+//    backward counterparts; small reductions.
+//
+// Roofline notes: the GEMM is FFMA-bound (fp32 pipe); all row kernels are HBM-bound (one read + one
+// write of the (B,D) activation, coalesced, one warp per row, warp-shuffle reductions).
+#include "usf_common.cuh"
+
+namespace usf {
+
+// ================================================================================================
+// SIMT GEMM
+// ================================================================================================
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NTHREADS = 256, PAD = 4;
+
+__device__ __forceinline__ float warp16_sum(float v) {
+  // reduce over the 16 lanes that share ty (lanes differ in tx = lane & 15)
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float ld_act(const void* p, int64_t idx, int is_bf16) {
+  if (is_bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+  return reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st_act(void* p, int64_t idx, int is_bf16, float v) {
+  if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+// Loads an (ROWS=128) x (BK=16) operand tile into registers (8 floats / thread).
+// trans == 0: element(r,k) = P[r*ld + k]  (k contiguous)  -> thread: r = tid/2, k = (tid%2)*8 + i
+// trans == 1: element(r,k) = P[k*ld + r]  (r contiguous)  -> thread: k = tid/16, r = (tid%16)*8 + i
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t ld, int trans, int64_t r0,
+                                          int64_t k0, int64_t R, int64_t K, int tid, float (&v)[8]) {
+  if (!trans) {
+    const int64_t r = r0 + (tid >> 1);
+    const int64_t k = k0 + (tid & 1) * 8;
+    const float* src = P + r * ld + k;
+    if (r < R && k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (r < R && k + i < K) ? src[i] : 0.f;
+    }
+  } else {
+    const int64_t k = k0 + (tid >> 4);
+    const int64_t r = r0 + (tid & 15) * 8;
+    const float* src = P + k * ld + r;
+    if (k < K && r + 8 <= R && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (k < K && r + i < R) ? src[i] : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int trans, int tid, const float (&v)[8]) {
+  if (!trans) {
+    const int r = tid >> 1, k = (tid & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[k + i][r] = v[i];
+  } else {
+    const int k = tid >> 4, r = (tid & 15) * 8;
+    *reinterpret_cast<float4*>(&S[k][r]) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(&S[k][r + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+struct PlainOut {
+  float* C;
+  int64_t ldc;
+  int accumulate;  // 0: store, 1: += (non-atomic when split_k == 1, atomic otherwise)
+  int split_k;
+};
+
+// One kernel body; FUSED selects the layer epilogues (EpiParams) vs the plain C output (backward).
+template <bool FUSED>
+__global__ void __launch_bounds__(NTHREADS)
+usf_simt_gemm_kernel(const float* __restrict__ A, int64_t lda, int a_trans, const float* __restrict__ W,
+                     int64_t ldw, int w_trans, int64_t M, int64_t N, int64_t K, EpiParams ep, PlainOut po) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+
+  // split-K range (plain variant only)
+  int64_t kb = 0, ke = K;
+  if (!FUSED && po.split_k > 1) {
+    const int64_t chunk = round_up(ceil_div(K, po.split_k), BK);
+    kb = (int64_t)blockIdx.z * chunk;
+    ke = kb + chunk < K ? kb + chunk : K;
+    if (kb >= ke) return;
+  }
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  load_tile(A, lda, a_trans, m0, kb, M, ke, tid, ra);
+  load_tile(W, ldw, w_trans, n0, kb, N, ke, tid, rb);
+  store_tile(As[0], a_trans, tid, ra);
+  store_tile(Bs[0], w_trans, tid, rb);
+  __syncthreads();
+
+  int buf = 0;
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const bool has_next = k0 + BK < ke;
+    if (has_next) {
+      load_tile(A, lda, a_trans, m0, k0 + BK, M, ke, tid, ra);
+      load_tile(W, ldw, w_trans, n0, k0 + BK, N, ke, tid, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_tile(As[buf ^ 1], a_trans, tid, ra);
+      store_tile(Bs[buf ^ 1], w_trans, tid, rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // ------------------------------------------------------------------ epilogue
+  if (!FUSED) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (r >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (c >= N) continue;
+        float* dst = po.C + r * po.ldc + c;
+        if (po.split_k > 1) atomicAdd(dst, acc[i][j]);
+        else if (po.accumulate) *dst += acc[i][j];
+        else *dst = acc[i][j];
+      }
+    }
+    return;
+  }
+
+  const int mode = ep.mode;
+  if (mode == EPI_BIAS || mode == EPI_BIAS_RELU) {
+    float bj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      bj[j] = (ep.bias != nullptr && c < N) ? ep.bias[c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (r >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (c >= N) continue;
+        float v = acc[i][j] + bj[j];
+        if (mode == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+        st_act(ep.out, r * ep.ldo + c, ep.out_bf16, v);
+      }
+    }
+  } else if (mode == EPI_COUPLING_INV || mode == EPI_COUPLING_FWD) {
+    // tile columns [0,64) = s of coords blockIdx.y*64 + [0,64); columns [64,128) = t of the same coords
+    float bs[4], bt[4];
+    int coord[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      coord[j] = (int)blockIdx.y * 64 + tx * 4 + j;
+      bs[j] = ep.bias[n0 + tx * 4 + j];
+      bt[j] = ep.bias[n0 + 64 + tx * 4 + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      float lsum = 0.f;
+      if (r < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (coord[j] >= ep.Db) continue;
+          const float s = acc[i][j] + bs[j];
+          const float t = acc[i][4 + j] + bt[j];
+          const float ls = ep.clamp * tanhf(s);
+          const int64_t idx = r * ep.ldub + coord[j];
+          const float u = ld_act(ep.ub, idx, ep.ub_bf16);
+          const float y = (mode == EPI_COUPLING_INV) ? (u - t) * expf(-ls) : fmaf(u, expf(ls), t);
+          st_act(ep.ub, idx, ep.ub_bf16, y);
+          lsum += ls;
+        }
+      }
+      lsum = warp16_sum(lsum);
+      if (tx == 0 && r < M && ep.row_acc != nullptr)
+        atomicAdd(ep.row_acc + r, mode == EPI_COUPLING_INV ? -lsum : lsum);
+    }
+  } else if (mode == EPI_ADD_INV || mode == EPI_ADD_FWD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (r >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (c >= ep.Db) continue;
+        const float t = acc[i][j] + ep.bias[c];
+        const int64_t idx = r * ep.ldub + c;
+        const float u = ld_act(ep.ub, idx, ep.ub_bf16);
+        st_act(ep.ub, idx, ep.ub_bf16, mode == EPI_ADD_INV ? u - t : u + t);
+      }
+    }
+  } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      float lsum = 0.f;
+      if (r < M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+          if (c >= N) continue;
+          const float z = acc[i][j] + ep.bias[c];
+          if (ep.out != nullptr) st_act(ep.out, r * ep.ldo + c, ep.out_bf16, z);
+          if (ep.loc != nullptr) {
+            const float d = (z - ep.loc[c]) * ep.inv_scale[c];
+            lsum += (mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+          }
+        }
+      }
+      lsum = warp16_sum(lsum);
+      if (tx == 0 && r < M && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + r, lsum);
+    }
+  }
+}
+
+}  // namespace
+
+const char* const kSimtGemmKernelName = "usf_simt_gemm_kernel";
+
+int simt_gemm(const float* A, int64_t lda, int a_trans, const float* W, int64_t ldw, int w_trans,
+              int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return USF_OK;
+  if ((ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD) && ep.C != 64) {
+    set_error("simt_gemm: coupling epilogue needs C == 64 (got %d)", ep.C);
+    return USF_E_ARG;
+  }
+  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN), 1);
+  PlainOut po{nullptr, 0, 0, 1};
+  usf_simt_gemm_kernel<true><<<grid, NTHREADS, 0, stream>>>(A, lda, a_trans, W, ldw, w_trans, M, N, K, ep, po);
+  USF_LAUNCH_CHECK("usf_simt_gemm_kernel");
+  return USF_OK;
+}
+
+int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, int64_t ldw, int w_trans,
+                    int64_t M, int64_t N, int64_t K, float* Cout, int64_t ldc, int accumulate,
+                    cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return USF_OK;
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  int split = 1;
+  if (K >= 1024 && tiles < num_sms()) {
+    split = (int)((2 * num_sms()) / tiles);
+    const int64_t max_split = ceil_div(K, 256);
+    if (split > max_split) split = (int)max_split;
+    if (split < 1) split = 1;
+  }
+  if (split > 1 && !accumulate) {
+    // split-K accumulates atomically: clear the output first
+    if (ldc == N) {
+      USF_CUDA(cudaMemsetAsync(Cout, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
+    } else {
+      USF_CUDA(cudaMemset2DAsync(Cout, sizeof(float) * ldc, 0, sizeof(float) * N, (size_t)M, stream));
+    }
+  }
+  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN), (unsigned)split);
+  EpiParams ep{};
+  PlainOut po{Cout, ldc, accumulate, split};
+  usf_simt_gemm_kernel<false><<<grid, NTHREADS, 0, stream>>>(A, lda, a_trans, W, ldw, w_trans, M, N, K, ep, po);
+  USF_LAUNCH_CHECK("usf_simt_gemm_kernel<plain>");
+  return USF_OK;
+}
+
+// ================================================================================================
+// Triangular solve over batch rows:  X E^T = R  (each row r: E x_r = rhs_r), E triangular D x D.
+//   element E(i,j) = TRANS ? T[j*D+i] : T[i*D+j], used only inside the triangle; UNIT: implicit 1 diagonal.
+// One CTA owns 64 batch rows and walks the 32-wide column blocks in dependency order, accumulating the
+// already-solved part with an smem-tiled product and finishing each block by substitution.
+// ================================================================================================
+namespace {
+
+constexpr int TR = 64, TB = 32;
+
+template <bool LOWER, bool UNIT, bool TRANS>
+__global__ void __launch_bounds__(256)
+usf_trsm_rows_kernel(const float* __restrict__ T, int64_t D, const float* rhs, int64_t ldr,
+                     const float* __restrict__ bias, float* X, int64_t ldx, int64_t B) {
+  __shared__ float Xs[TR][TB + 1];
+  __shared__ float Es[TB][TB + 1];
+  __shared__ float Ts[TR][TB + 1];
+  const int tid = threadIdx.x;
+  const int c = tid & 31, rg = tid >> 5;  // accumulate mapping: column c, rows rg*8 + i
+  const int64_t r0 = (int64_t)blockIdx.x * TR;
+  const int nblk = (int)ceil_div(D, TB);
+
+  for (int step = 0; step < nblk; ++step) {
+    const int jb = LOWER ? step : nblk - 1 - step;
+    const int64_t j0 = (int64_t)jb * TB;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // already-solved column blocks: k-blocks before jb (LOWER) or after jb (UPPER)
+    for (int s2 = 0; s2 < step; ++s2) {
+      const int kbk = LOWER ? s2 : nblk - 1 - s2;
+      const int64_t k0 = (int64_t)kbk * TB;
+      // Xs[r][kk] = X[r0+r][k0+kk]
+      for (int e = tid; e < TR * TB; e += 256) {
+        const int r = e >> 5, kk = e & 31;
+        const int64_t gr = r0 + r, gk = k0 + kk;
+        Xs[r][kk] = (gr < B && gk < D) ? X[gr * ldx + gk] : 0.f;
+      }
+      // Es[cc][kk] = E(j0+cc, k0+kk)
+      for (int e = tid; e < TB * TB; e += 256) {
+        int cc, kk;
+        if (TRANS) { kk = e >> 5; cc = e & 31; } else { cc = e >> 5; kk = e & 31; }
+        const int64_t gi = j0 + cc, gk = k0 + kk;
+        float v = 0.f;
+        if (gi < D && gk < D) v = TRANS ? T[gk * D + gi] : T[gi * D + gk];
+        Es[cc][kk] = v;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < TB; ++kk) {
+        const float ev = Es[c][kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(Xs[rg * 8 + i][kk], ev, acc[i]);
+      }
+      __syncthreads();
+    }
+    // Ts = rhs - bias - acc ; Es = diagonal block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rg * 8 + i;
+      const int64_t gr = r0 + r, gc = j0 + c;
+      float v = 0.f;
+      if (gr < B && gc < D) {
+        v = rhs[gr * ldr + gc] - acc[i];
+        if (bias != nullptr) v -= bias[gc];
+      }
+      Ts[r][c] = v;
+    }
+    for (int e = tid; e < TB * TB; e += 256) {
+      int cc, kk;
+      if (TRANS) { kk = e >> 5; cc = e & 31; } else { cc = e >> 5; kk = e & 31; }
+      const int64_t gi = j0 + cc, gk = j0 + kk;
+      float v = (cc == kk) ? 1.f : 0.f;  // padding keeps the block non-singular
+      if (gi < D && gk < D) {
+        v = TRANS ? T[gk * D + gi] : T[gi * D + gk];
+        if (UNIT && cc == kk) v = 1.f;
+      }
+      Es[cc][kk] = v;
+    }
+    __syncthreads();
+    if (tid < TR) {
+      const int r = tid;
+      if (LOWER) {
+        for (int cc = 0; cc < TB; ++cc) {
+          float xv = Ts[r][cc];
+          if (!UNIT) xv /= Es[cc][cc];
+          Ts[r][cc] = xv;
+          for (int c2 = cc + 1; c2 < TB; ++c2) Ts[r][c2] = fmaf(-xv, Es[c2][cc], Ts[r][c2]);
+        }
+      } else {
+        for (int cc = TB - 1; cc >= 0; --cc) {
+          float xv = Ts[r][cc];
+          if (!UNIT) xv /= Es[cc][cc];
+          Ts[r][cc] = xv;
+          for (int c2 = 0; c2 < cc; ++c2) Ts[r][c2] = fmaf(-xv, Es[c2][cc], Ts[r][c2]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rg * 8 + i;
+      const int64_t gr = r0 + r, gc = j0 + c;
+      if (gr < B && gc < D) X[gr * ldx + gc] = Ts[r][c];
+    }
+    __syncthreads();  // X writes visible to this CTA's next accumulation pass
+  }
+}
+
+}  // namespace
+
+int trsm_rows(const float* T, int64_t D, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr,
+              const float* bias, float* X, int64_t ldx, int64_t B, cudaStream_t stream) {
+  if (B <= 0 || D <= 0) return USF_OK;
+  dim3 grid((unsigned)ceil_div(B, TR));
+#define USF_TRSM(L, U, TT) usf_trsm_rows_kernel<L, U, TT><<<grid, 256, 0, stream>>>(T, D, rhs, ldr, bias, X, ldx, B)
+  if (lower) {
+    if (unit) { if (trans) USF_TRSM(true, true, true); else USF_TRSM(true, true, false); }
+    else      { if (trans) USF_TRSM(true, false, true); else USF_TRSM(true, false, false); }
+  } else {
+    if (unit) { if (trans) USF_TRSM(false, true, true); else USF_TRSM(false, true, false); }
+    else      { if (trans) USF_TRSM(false, false, true); else USF_TRSM(false, false, false); }
+  }
+#undef USF_TRSM
+  USF_LAUNCH_CHECK("usf_trsm_rows_kernel");
+  return USF_OK;
+}
+
+// ================================================================================================
+// Row kernels: one warp per sample row, 8 rows per CTA.
+// ================================================================================================
+namespace {
+
+constexpr int ROWS_PER_CTA = 8;
+
+__global__ void usf_householder_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ V,
+                                       int nvs, int reverse, float* y, int64_t ldy, int64_t B, int64_t D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (r >= B) return;
+  const float* src = x + r * ldx;
+  float* dst = y + r * ldy;
+  for (int it = 0; it < nvs; ++it) {
+    const float* v = V + (int64_t)(reverse ? nvs - 1 - it : it) * D;
+    float dot = 0.f, nrm = 0.f;
+    for (int64_t d = lane; d < D; d += 32) {
+      const float vv = v[d];
+      dot = fmaf(src[d], vv, dot);
+      nrm = fmaf(vv, vv, nrm);
+    }
+    dot = warp_sum(dot);
+    nrm = warp_sum(nrm);
+    const float coef = 2.f * dot / nrm;
+    for (int64_t d = lane; d < D; d += 32) dst[d] = fmaf(-coef, v[d], src[d]);
+    __syncwarp();
+    src = dst;
+  }
+  if (nvs == 0 && src != dst)
+    for (int64_t d = lane; d < D; d += 32) dst[d] = src[d];
+}
+
+__global__ void usf_scale_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
+                                 int inverse, float* y, int64_t ldy, int64_t B, int64_t D) {
+  const int64_t total = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, d = i - r * D;
+    const float v = x[r * ldx + d];
+    y[r * ldy + d] = inverse ? v / scale[d] : v * scale[d];
+  }
+}
+
+__global__ void usf_sum_log_abs_kernel(const float* __restrict__ v, int64_t n, int64_t stride, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += logf(fabsf(v[i * stride]));
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s;
+  }
+}
+
+// y = m*x + (1-m)*(x*exp(ls)+t)  /  y = m*x + (1-m)*((x-t)*exp(-ls)), ls = clamp*tanh(s)
+__global__ void usf_coupling_kernel(const float* x, int64_t ldx, const float* __restrict__ s, int64_t lds,
+                                    const float* __restrict__ t, int64_t ldt, const float* __restrict__ mask,
+                                    float clamp, int inverse, float* y, int64_t ldy, float* ladj, float ladj_coef,
+                                    int64_t B, int64_t D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float lsum = 0.f;
+  for (int64_t d = lane; d < D; d += 32) {
+    const float m = mask[d];
+    const float xv = x[r * ldx + d];
+    const float tv = t[r * ldt + d];
+    float ls = 0.f;
+    if (s != nullptr) ls = clamp * tanhf(s[r * lds + d]);
+    const float inner = inverse ? (xv - tv) * expf(-ls) : fmaf(xv, expf(ls), tv);
+    y[r * ldy + d] = xv * m + (1.f - m) * inner;
+    lsum = fmaf(1.f - m, ls, lsum);
+  }
+  if (ladj != nullptr) {
+    lsum = warp_sum(lsum);
+    if (lane == 0) ladj[r] += ladj_coef * lsum;
+  }
+}
+
+__global__ void usf_coupling_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ dladj,
+                                        float ladj_coef, const float* __restrict__ x, int64_t ldx,
+                                        const float* __restrict__ s, int64_t lds, const float* __restrict__ t,
+                                        int64_t ldt, const float* __restrict__ mask, float clamp, int inverse,
+                                        float* dx, int64_t lddx, float* ds, int64_t ldds, float* dt, int64_t lddt,
+                                        int64_t B, int64_t D) {
+  const int64_t total = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, d = i - r * D;
+    const float m = mask[d], om = 1.f - m;
+    const float g = dy[r * lddy + d];
+    const float xv = x[r * ldx + d];
+    const float tv = t[r * ldt + d];
+    float th = 0.f, ls = 0.f;
+    if (s != nullptr) { th = tanhf(s[r * lds + d]); ls = clamp * th; }
+    const float gl = dladj != nullptr ? dladj[r] * ladj_coef : 0.f;
+    float gx, gt, gls;
+    if (!inverse) {
+      const float e = expf(ls);
+      gx = g * (m + om * e);
+      gt = g * om;
+      gls = g * om * xv * e + gl * om;
+    } else {
+      const float e = expf(-ls);
+      gx = g * (m + om * e);
+      gt = -g * om * e;
+      gls = -g * om * (xv - tv) * e + gl * om;
+    }
+    dx[r * lddx + d] = gx;
+    dt[r * lddt + d] = gt;
+    if (ds != nullptr) ds[r * ldds + d] = gls * clamp * (1.f - th * th);
+  }
+}
+
+__global__ void usf_base_logprob_kernel(int kind, const float* __restrict__ z, int64_t ldz,
+                                        const float* __restrict__ loc, const float* __restrict__ scale,
+                                        int64_t scale_numel, const float* __restrict__ add, float add_coef,
+                                        float* out, int64_t B, int64_t D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float acc = 0.f;
+  for (int64_t d = lane; d < D; d += 32) {
+    const float sc = scale[scale_numel == 1 ? 0 : d];
+    const float u = (z[r * ldz + d] - loc[d]) / sc;
+    if (kind == 0) acc += -0.5f * u * u - logf(sc) - 0.91893853320467274178f;
+    else acc += -fabsf(u) - logf(2.f * sc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + (add != nullptr ? add_coef * add[r] : 0.f);
+}
+
+// dz = dout * dlogp/dz ; column sums for loc / scale grads via atomics (one partial per warp-row).
+__global__ void usf_base_logprob_bwd_kernel(int kind, const float* __restrict__ dout, const float* __restrict__ z,
+                                            int64_t ldz, const float* __restrict__ loc, const float* __restrict__ scale,
+                                            int64_t scale_numel, float* dz, int64_t lddz, float* dloc, float* dscale,
+                                            int64_t B, int64_t D) {
+  // thread per column chunk: block handles 32 columns x all rows strided by gridDim.y
+  const int64_t d = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;  // 0..7
+  float gl = 0.f, gs = 0.f;
+  if (d < D) {
+    const float sc = scale[scale_numel == 1 ? 0 : d];
+    const float lc = loc[d];
+    for (int64_t r = (int64_t)blockIdx.y * 8 + rl; r < B; r += (int64_t)gridDim.y * 8) {
+      const float g = dout[r];
+      const float u = (z[r * ldz + d] - lc) / sc;
+      float dzv, dsc;
+      if (kind == 0) { dzv = -u / sc; dsc = (u * u - 1.f) / sc; }
+      else { const float sg = (u > 0.f) - (u < 0.f); dzv = -sg / sc; dsc = (fabsf(u) - 1.f) / sc; }
+      if (dz != nullptr) dz[r * lddz + d] = g * dzv;
+      gl += -g * dzv;
+      gs += g * dsc;
+    }
+  }
+  __shared__ float sl[8][33], ss[8][33];
+  sl[rl][threadIdx.x & 31] = gl;
+  ss[rl][threadIdx.x & 31] = gs;
+  __syncthreads();
+  if (rl == 0 && d < D) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sl[i][threadIdx.x]; b += ss[i][threadIdx.x]; }
+    if (dloc != nullptr) atomicAdd(dloc + d, a);
+    if (dscale != nullptr) atomicAdd(dscale + (scale_numel == 1 ? 0 : d), b);
+  }
+}
+
+// Householder backward for ONE reflection: given input x (before this reflection), dy -> dx, dv +=.
+//   y = x - c v, c = 2 (x.v)/(v.v);  dx = dy - (2 (dy.v)/(v.v)) v
+//   dv += -c dy - (2 (dy.v)/(v.v)) x + (4 (x.v)(dy.v)/(v.v)^2) v     (per row, reduced over rows)
+__global__ void usf_householder_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x,
+                                           int64_t ldx, const float* __restrict__ v, float* dx, int64_t lddx,
+                                           float* dv, int64_t B, int64_t D) {
+  extern __shared__ float dv_s[];  // D floats, CTA-local accumulation of dv
+  for (int64_t d = threadIdx.x; d < D; d += blockDim.x) dv_s[d] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * nw + wid; r < B; r += (int64_t)gridDim.x * nw) {
+    float xv = 0.f, gv = 0.f, vv = 0.f;
+    for (int64_t d = lane; d < D; d += 32) {
+      const float ve = v[d];
+      xv = fmaf(x[r * ldx + d], ve, xv);
+      gv = fmaf(dy[r * lddy + d], ve, gv);
+      vv = fmaf(ve, ve, vv);
+    }
+    xv = warp_sum(xv); gv = warp_sum(gv); vv = warp_sum(vv);
+    const float c = 2.f * xv / vv, e = 2.f * gv / vv, f = 4.f * xv * gv / (vv * vv);
+    for (int64_t d = lane; d < D; d += 32) {
+      const float g = dy[r * lddy + d], ve = v[d], xe = x[r * ldx + d];
+      dx[r * lddx + d] = fmaf(-e, ve, g);
+      atomicAdd(&dv_s[d], -c * g - e * xe + f * ve);
+    }
+  }
+  __syncthreads();
+  for (int64_t d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(dv + d, dv_s[d]);
+}
+
+// Backward of y = x*scale (inverse: y = x/scale). `xy` is the layer input x (forward) or OUTPUT y (inverse).
+//   forward: dx = dy*scale, dscale[d] += sum_b dy*x ;  inverse: dx = dy/scale, dscale[d] += -sum_b dy*y/scale
+__global__ void usf_scale_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ xy,
+                                     int64_t ldxy, const float* __restrict__ scale, int inverse, float* dx,
+                                     int64_t lddx, float* dscale, int64_t B, int64_t D) {
+  const int64_t d = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  float gs = 0.f;
+  if (d < D) {
+    const float sc = scale[d];
+    for (int64_t r = (int64_t)blockIdx.y * 8 + rl; r < B; r += (int64_t)gridDim.y * 8) {
+      const float g = dy[r * lddy + d];
+      const float v = xy[r * ldxy + d];
+      if (!inverse) { dx[r * lddx + d] = g * sc; gs += g * v; }
+      else { dx[r * lddx + d] = g / sc; gs -= g * v / sc; }
+    }
+  }
+  __shared__ float sm[8][33];
+  sm[rl][threadIdx.x & 31] = gs;
+  __syncthreads();
+  if (rl == 0 && d < D && dscale != nullptr) {
+    float a = 0.f;
+    for (int i = 0; i < 8; ++i) a += sm[i][threadIdx.x];
+    atomicAdd(dscale + d, a);
+  }
+}
+
+__global__ void usf_colsum_kernel(const float* __restrict__ a, int64_t lda, float* out, float coef, int accumulate,
+                                  int64_t B, int64_t N) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < N)
+    for (int64_t r = rl; r < B; r += 8) s += a[r * lda + c];
+  __shared__ float sm[8][33];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    out[c] = (accumulate ? out[c] : 0.f) + coef * t;
+  }
+}
+
+__global__ void usf_relu_mask_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y,
+                                     int64_t ldy, float* out, int64_t B, int64_t N) {
+  const int64_t total = B * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / N, c = i - r * N;
+    out[i] = y[r * ldy + c] > 0.f ? dy[r * lddy + c] : 0.f;
+  }
+}
+
+// mode 0: out = tril(src,-1) + I ; mode 1: out = triu(src)
+__global__ void usf_tri_copy_kernel(const float* __restrict__ src, float* out, int64_t D, int mode) {
+  const int64_t total = D * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, c = i - r * D;
+    float v;
+    if (mode == 0) v = c < r ? src[i] : (c == r ? 1.f : 0.f);
+    else v = c >= r ? src[i] : 0.f;
+    out[i] = v;
+  }
+}
+
+// mode 0: dst += strict_lower(src) ; mode 1: dst += upper(src) (+ dlogdet / U_ii on the diagonal)
+__global__ void usf_tri_add_kernel(const float* __restrict__ src, float* dst, int64_t D, int mode,
+                                   const float* __restrict__ U_raw, float dlogdet) {
+  const int64_t total = D * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, c = i - r * D;
+    if (mode == 0) { if (c < r) dst[i] += src[i]; }
+    else {
+      if (c >= r) dst[i] += src[i];
+      if (c == r && dlogdet != 0.f) dst[i] += dlogdet / U_raw[i];
+    }
+  }
+}
+
+__global__ void usf_pack_matrix_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ row_idx,
+                                       const int32_t* __restrict__ col_idx, int sub_row0, int transpose_src,
+                                       int64_t n_rows, int64_t n_cols, float* out, __nv_bfloat16* out_bf16,
+                                       int64_t ldo) {
+  const int64_t total = n_rows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldo, c = i - r * ldo;
+    float v = 0.f;
+    if (c < n_cols) {
+      const int64_t sr = row_idx ? row_idx[r] : r;
+      const int64_t sc = col_idx ? col_idx[c] : c;
+      if (sr >= 0 && sc >= 0) {
+        if (!transpose_src) {
+          v = src[sr * lds + sc];
+          if (sub_row0) v -= src[sc];
+        } else {  // out[r,c] = src[col_idx[c], row_idx[r]] - src[0, row_idx[r]]
+          v = src[sc * lds + sr];
+          if (sub_row0) v -= src[sr];
+        }
+      }
+    }
+    if (out) out[i] = v;
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// fp32 (B,D) -> bf16 and/or fp32 copy with padded leading dimension (pad columns zeroed); optional row_init.
+__global__ void usf_convert_rows_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* yb, float* yf,
+                                        int64_t ldy, int64_t B, int64_t D, float* row_init, float init_value) {
+  const int64_t total = B * ldy;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldy, c = i - r * ldy;
+    const float v = c < D ? x[r * ldx + c] : 0.f;
+    if (yb) yb[i] = __float2bfloat16_rn(v);
+    if (yf) yf[i] = v;
+    if (c == 0 && row_init) row_init[r] = init_value;
+  }
+}
+
+__global__ void usf_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* y, int64_t ldy,
+                                       int64_t B, int64_t D) {
+  const int64_t total = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, c = i - r * D;
+    y[r * ldy + c] = __bfloat162float(x[r * ldx + c]);
+  }
+}
+
+inline unsigned ew_grid(int64_t total, int threads = 256) {
+  int64_t g = ceil_div(total, threads);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace
+
+int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_f32, int64_t ldy, int64_t B,
+                        int64_t D, float* row_init, float init_value, cudaStream_t stream) {
+  if (B <= 0) return USF_OK;
+  usf_convert_rows_kernel<<<ew_grid(B * ldy), 256, 0, stream>>>(
+      x, ldx, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy, B, D, row_init, init_value);
+  USF_LAUNCH_CHECK("usf_convert_rows_kernel");
+  return USF_OK;
+}
+
+int launch_bf16_to_f32(const uint16_t* x, int64_t ldx, float* y, int64_t ldy, int64_t B, int64_t D,
+                       cudaStream_t stream) {
+  if (B <= 0) return USF_OK;
+  usf_bf16_to_f32_kernel<<<ew_grid(B * D), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, y, ldy, B, D);
+  USF_LAUNCH_CHECK("usf_bf16_to_f32_kernel");
+  return USF_OK;
+}
+
+}  // namespace usf
+
+// ================================================================================================
+// extern "C" layer entry points
+// ================================================================================================
+using namespace usf;
+
+extern "C" int usf_lu_pack(const float* L_raw, const float* U_raw, int64_t D, float* W, float* logabsdet,
+                           float* scratch, usf_stream_t stream) {
+  USF_CHECK_ARG(L_raw && U_raw && W && scratch && D > 0, "usf_lu_pack: null pointer or D <= 0");
+  cudaStream_t st = as_stream(stream);
+  float* Lm = scratch;
+  float* Um = scratch + D * D;
+  usf_tri_copy_kernel<<<ew_grid(D * D), 256, 0, st>>>(L_raw, Lm, D, 0);
+  usf_tri_copy_kernel<<<ew_grid(D * D), 256, 0, st>>>(U_raw, Um, D, 1);
+  USF_LAUNCH_CHECK("usf_tri_copy_kernel");
+  // W[i,j] = sum_k Lm[i,k] Um[k,j] : A = Lm (k contiguous), operand "W"(n=j,k) = Um[k*D+j] -> w_trans
+  int rc = simt_gemm_plain(Lm, D, 0, Um, D, 1, D, D, D, W, D, 0, st);
+  if (rc) return rc;
+  if (logabsdet) {
+    usf_sum_log_abs_kernel<<<1, 256, 0, st>>>(U_raw, D, D + 1, logabsdet);
+    USF_LAUNCH_CHECK("usf_sum_log_abs_kernel");
+  }
+  return USF_OK;
+}
+
+extern "C" int usf_linear(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, int relu,
+                          float* y, int64_t ldy, int64_t B, int64_t N, int64_t K, usf_stream_t stream) {
+  USF_CHECK_ARG(x && W && y, "usf_linear: null pointer");
+  USF_CHECK_ARG(B >= 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N, "usf_linear: bad sizes");
+  EpiParams ep{};
+  ep.mode = relu ? EPI_BIAS_RELU : EPI_BIAS;
+  ep.bias = bias;
+  ep.out = y;
+  ep.ldo = ldy;
+  return simt_gemm(x, ldx, 0, W, ldw, 0, B, N, K, ep, as_stream(stream));
+}
+
+extern "C" int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, const float* U_raw, const float* bias,
+                            int transpose, float* x, int64_t ldx, int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(y && L_raw && U_raw && x && D > 0 && B >= 0, "usf_lu_solve: null pointer or bad size");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (!transpose) {
+    // L z = y - b (unit lower), U x = z (upper)
+    rc = trsm_rows(L_raw, D, true, true, false, y, ldy, bias, x, ldx, B, st);
+    if (rc) return rc;
+    return trsm_rows(U_raw, D, false, false, false, x, ldx, nullptr, x, ldx, B, st);
+  }
+  // (LU)^T x = y : U^T z = y (lower, non-unit), L^T x = z (upper, unit)
+  rc = trsm_rows(U_raw, D, true, false, true, y, ldy, bias, x, ldx, B, st);
+  if (rc) return rc;
+  return trsm_rows(L_raw, D, false, true, true, x, ldx, nullptr, x, ldx, B, st);
+}
+
+extern "C" int usf_householder(const float* x, int64_t ldx, const float* V, int64_t nvs, int reverse, float* y,
+                               int64_t ldy, int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(x && y && (V || nvs == 0) && D > 0 && B >= 0 && nvs >= 0, "usf_householder: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_householder_kernel<<<(unsigned)ceil_div(B, ROWS_PER_CTA), ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(
+      x, ldx, V, (int)nvs, reverse, y, ldy, B, D);
+  USF_LAUNCH_CHECK("usf_householder_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_scale(const float* x, int64_t ldx, const float* scale, int inverse, float* y, int64_t ldy,
+                         int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(x && y && scale && D > 0 && B >= 0, "usf_scale: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_scale_kernel<<<ew_grid(B * D), 256, 0, as_stream(stream)>>>(x, ldx, scale, inverse, y, ldy, B, D);
+  USF_LAUNCH_CHECK("usf_scale_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_sum_log_abs(const float* v, int64_t n, int64_t stride, float* out, usf_stream_t stream) {
+  USF_CHECK_ARG(v && out && n >= 0 && stride > 0, "usf_sum_log_abs: bad arguments");
+  usf_sum_log_abs_kernel<<<1, 256, 0, as_stream(stream)>>>(v, n, stride, out);
+  USF_LAUNCH_CHECK("usf_sum_log_abs_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_coupling(const float* x, int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
+                            const float* mask, float clamp, int inverse, float* y, int64_t ldy, float* ladj,
+                            float ladj_coef, int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(x && t && mask && y && D > 0 && B >= 0, "usf_coupling: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_coupling_kernel<<<(unsigned)ceil_div(B, ROWS_PER_CTA), ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(
+      x, ldx, s, lds, t, ldt, mask, clamp, inverse, y, ldy, ladj, ladj_coef, B, D);
+  USF_LAUNCH_CHECK("usf_coupling_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_base_logprob(int kind, const float* z, int64_t ldz, const float* loc, const float* scale,
+                                int64_t scale_numel, const float* add, float add_coef, float* out, int64_t B,
+                                int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(z && loc && scale && out && D > 0 && B >= 0, "usf_base_logprob: bad arguments");
+  USF_CHECK_ARG(kind == 0 || kind == 1, "usf_base_logprob: kind must be 0 (Normal) or 1 (Laplace)");
+  USF_CHECK_ARG(scale_numel == 1 || scale_numel == D, "usf_base_logprob: scale_numel must be 1 or D");
+  if (B == 0) return USF_OK;
+  usf_base_logprob_kernel<<<(unsigned)ceil_div(B, ROWS_PER_CTA), ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(
+      kind, z, ldz, loc, scale, scale_numel, add, add_coef, out, B, D);
+  USF_LAUNCH_CHECK("usf_base_logprob_kernel");
+  return USF_OK;
+}
+
+extern "C" size_t usf_linear_bwd_scratch_bytes(int64_t B, int64_t N) {
+  return sizeof(float) * (size_t)(B > 0 ? B : 0) * (size_t)(N > 0 ? N : 0);
+}
+
+extern "C" int usf_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* W,
+                              int64_t ldw, const float* y_relu, int64_t ldyr, float* dx, int64_t lddx, float* dW,
+                              int64_t lddw, float* db, int accumulate, float* scratch, int64_t B, int64_t N,
+                              int64_t K, usf_stream_t stream) {
+  USF_CHECK_ARG(dy && B >= 0 && N > 0 && K > 0, "usf_linear_bwd: bad arguments");
+  USF_CHECK_ARG(!(dx && !W) && !(dW && !x), "usf_linear_bwd: dx needs W, dW needs x");
+  USF_CHECK_ARG(!(y_relu && !scratch), "usf_linear_bwd: relu backward needs scratch");
+  if (B == 0) return USF_OK;
+  cudaStream_t st = as_stream(stream);
+  const float* g = dy;
+  int64_t ldg = lddy;
+  if (y_relu) {
+    usf_relu_mask_kernel<<<ew_grid(B * N), 256, 0, st>>>(dy, lddy, y_relu, ldyr, scratch, B, N);
+    USF_LAUNCH_CHECK("usf_relu_mask_kernel");
+    g = scratch;
+    ldg = N;
+  }
+  int rc;
+  if (dx) {  // dx[b,k] = sum_n g[b,n] W[n,k]
+    rc = simt_gemm_plain(g, ldg, 0, W, ldw, 1, B, K, N, dx, lddx, 0, st);
+    if (rc) return rc;
+  }
+  if (dW) {  // dW[n,k] = sum_b g[b,n] x[b,k]
+    rc = simt_gemm_plain(g, ldg, 1, x, ldx, 1, N, K, B, dW, lddw, accumulate, st);
+    if (rc) return rc;
+  }
+  if (db) {
+    usf_colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(g, ldg, db, 1.f, accumulate, B, N);
+    USF_LAUNCH_CHECK("usf_colsum_kernel");
+  }
+  return USF_OK;
+}
+
+extern "C" int usf_lu_pack_bwd(const float* dW, const float* L_raw, const float* U_raw, float dlogdet, int64_t D,
+                               float* dL_raw, float* dU_raw, float* scratch, usf_stream_t stream) {
+  USF_CHECK_ARG(L_raw && U_raw && dL_raw && dU_raw && scratch && D > 0, "usf_lu_pack_bwd: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  float* Lm = scratch;
+  float* Um = scratch + D * D;
+  float* T1 = scratch + 2 * D * D;
+  if (dW) {
+    usf_tri_copy_kernel<<<ew_grid(D * D), 256, 0, st>>>(L_raw, Lm, D, 0);
+    usf_tri_copy_kernel<<<ew_grid(D * D), 256, 0, st>>>(U_raw, Um, D, 1);
+    USF_LAUNCH_CHECK("usf_tri_copy_kernel");
+    // dL = strict_lower(dW U^T): [i,k] = sum_j dW[i,j] Um[k,j]
+    int rc = simt_gemm_plain(dW, D, 0, Um, D, 0, D, D, D, T1, D, 0, st);
+    if (rc) return rc;
+    usf_tri_add_kernel<<<ew_grid(D * D), 256, 0, st>>>(T1, dL_raw, D, 0, nullptr, 0.f);
+    USF_LAUNCH_CHECK("usf_tri_add_kernel");
+    // dU = upper(L^T dW): [k,j] = sum_i Lm[i,k] dW[i,j]
+    rc = simt_gemm_plain(Lm, D, 1, dW, D, 1, D, D, D, T1, D, 0, st);
+    if (rc) return rc;
+    usf_tri_add_kernel<<<ew_grid(D * D), 256, 0, st>>>(T1, dU_raw, D, 1, U_raw, dlogdet);
+    USF_LAUNCH_CHECK("usf_tri_add_kernel");
+  } else if (dlogdet != 0.f) {
+    USF_CUDA(cudaMemsetAsync(T1, 0, sizeof(float) * D * D, st));
+    usf_tri_add_kernel<<<ew_grid(D * D), 256, 0, st>>>(T1, dU_raw, D, 1, U_raw, dlogdet);
+    USF_LAUNCH_CHECK("usf_tri_add_kernel");
+  }
+  return USF_OK;
+}
+
+extern "C" int usf_coupling_bwd(const float* dy, int64_t lddy, const float* dladj, float ladj_coef, const float* x,
+                                int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
+                                const float* mask, float clamp, int inverse, float* dx, int64_t lddx, float* ds,
+                                int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(dy && x && t && mask && dx && dt && D > 0 && B >= 0, "usf_coupling_bwd: bad arguments");
+  USF_CHECK_ARG((s == nullptr) == (ds == nullptr), "usf_coupling_bwd: s and ds must both be given or both NULL");
+  if (B == 0) return USF_OK;
+  usf_coupling_bwd_kernel<<<ew_grid(B * D), 256, 0, as_stream(stream)>>>(
+      dy, lddy, dladj, ladj_coef, x, ldx, s, lds, t, ldt, mask, clamp, inverse, dx, lddx, ds, ldds, dt, lddt, B, D);
+  USF_LAUNCH_CHECK("usf_coupling_bwd_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_householder_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* V,
+                                   int64_t nvs, int reverse, float* dx, int64_t lddx, float* dV, float* scratch,
+                                   int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(dy && x && dx && dV && (V || nvs == 0) && D > 0 && B >= 0, "usf_householder_bwd: bad arguments");
+  USF_CHECK_ARG(nvs <= 1 || scratch, "usf_householder_bwd: scratch needed for nvs > 1");
+  USF_CHECK_ARG(D * sizeof(float) <= 200 * 1024, "usf_householder_bwd: D too large");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) return USF_OK;
+  if (nvs == 0) {
+    USF_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * lddx, dy, sizeof(float) * lddy, sizeof(float) * D, B,
+                               cudaMemcpyDeviceToDevice, st));
+    return USF_OK;
+  }
+  // recompute the inputs of every reflection: xs[0] = x, xs[i+1] = reflect_i(xs[i]); scratch holds xs[1..nvs-1]
+  // and one gradient ping buffer.
+  const size_t smem = sizeof(float) * (size_t)D;
+  if (smem > 48 * 1024)
+    USF_CUDA(cudaFuncSetAttribute(usf_householder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned rows_grid = (unsigned)ceil_div(B, ROWS_PER_CTA);
+  for (int64_t i = 0; i + 1 < nvs; ++i) {
+    const float* src = i == 0 ? x : scratch + (i - 1) * B * D;
+    const int64_t lds_ = i == 0 ? ldx : D;
+    const float* v = V + (reverse ? nvs - 1 - i : i) * D;
+    usf_householder_kernel<<<rows_grid, ROWS_PER_CTA * 32, 0, st>>>(src, lds_, v, 1, 0, scratch + i * B * D, D, B, D);
+    USF_LAUNCH_CHECK("usf_householder_kernel");
+  }
+  float* gbuf = scratch ? scratch + (nvs - 1) * B * D : nullptr;
+  const float* g = dy;
+  int64_t ldg = lddy;
+  int nblocks = num_sms() * 2;
+  if ((int64_t)nblocks * 8 > B) nblocks = (int)ceil_div(B, 8);
+  for (int64_t i = nvs - 1; i >= 0; --i) {
+    const float* xin = i == 0 ? x : scratch + (i - 1) * B * D;
+    const int64_t ldxin = i == 0 ? ldx : D;
+    const int64_t vi = reverse ? nvs - 1 - i : i;
+    float* gout = (i == 0) ? dx : gbuf;
+    const int64_t ldgout = (i == 0) ? lddx : D;
+    // in-place on gbuf is safe: each element is read then written by the same thread
+    usf_householder_bwd_kernel<<<nblocks, 256, smem, st>>>(g, ldg, xin, ldxin, V + vi * D, gout, ldgout,
+                                                           dV + vi * D, B, D);
+    USF_LAUNCH_CHECK("usf_householder_bwd_kernel");
+    g = gout;
+    ldg = ldgout;
+  }
+  return USF_OK;
+}
+
+extern "C" int usf_base_logprob_bwd(int kind, const float* dout, const float* z, int64_t ldz, const float* loc,
+                                    const float* scale, int64_t scale_numel, float* dz, int64_t lddz, float* dloc,
+                                    float* dscale, int64_t B, int64_t D, usf_stream_t stream) {
+  USF_CHECK_ARG(dout && z && loc && scale && D > 0 && B >= 0, "usf_base_logprob_bwd: bad arguments");
+  USF_CHECK_ARG(kind == 0 || kind == 1, "usf_base_logprob_bwd: kind must be 0 or 1");
+  if (B == 0) return USF_OK;
+  int gy = (int)ceil_div(B, 8 * 64);
+  if (gy < 1) gy = 1;
+  if (gy > 256) gy = 256;
+  dim3 grid((unsigned)ceil_div(D, 32), (unsigned)gy);
+  usf_base_logprob_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, dout, z, ldz, loc, scale, scale_numel, dz,
+                                                                  lddz, dloc, dscale, B, D);
+  USF_LAUNCH_CHECK("usf_base_logprob_bwd_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_scale_bwd(const float* dy, int64_t lddy, const float* xy, int64_t ldxy, const float* scale,
+                             int inverse, float* dx, int64_t lddx, float* dscale, int64_t B, int64_t D,
+                             usf_stream_t stream) {
+  USF_CHECK_ARG(dy && xy && scale && dx && D > 0 && B >= 0, "usf_scale_bwd: bad arguments");
+  if (B == 0) return USF_OK;
+  int gy = (int)ceil_div(B, 8 * 64);
+  if (gy < 1) gy = 1;
+  if (gy > 256) gy = 256;
+  dim3 grid((unsigned)ceil_div(D, 32), (unsigned)gy);
+  usf_scale_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, lddy, xy, ldxy, scale, inverse, dx, lddx, dscale, B, D);
+  USF_LAUNCH_CHECK("usf_scale_bwd_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_colsum(const float* a, int64_t lda, float coef, int accumulate, float* out, int64_t B, int64_t N,
+                          usf_stream_t stream) {
+  USF_CHECK_ARG(a && out && N > 0 && B >= 0, "usf_colsum: bad arguments");
+  usf_colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, as_stream(stream)>>>(a, lda, out, coef, accumulate, B, N);
+  USF_LAUNCH_CHECK("usf_colsum_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_gemm(const float* A, int64_t lda, int a_trans, const float* Bm, int64_t ldb, int b_trans,
+                        float* C, int64_t ldc, int accumulate, int64_t M, int64_t N, int64_t K,
+                        usf_stream_t stream) {
+  USF_CHECK_ARG(A && Bm && C && M >= 0 && N >= 0 && K >= 0, "usf_gemm: bad arguments");
+  return simt_gemm_plain(A, lda, a_trans, Bm, ldb, b_trans, M, N, K, C, ldc, accumulate, as_stream(stream));
+}
+
+extern "C" int usf_pack_matrix(const float* src, int64_t lds, const int32_t* row_idx, const int32_t* col_idx,
+                               int sub_row0, int transpose_src, int64_t n_rows, int64_t n_cols, float* out,
+                               uint16_t* out_bf16, int64_t ldo, usf_stream_t stream) {
+  USF_CHECK_ARG(src && (out || out_bf16) && n_rows >= 0 && n_cols >= 0 && ldo >= n_cols, "usf_pack_matrix: bad arguments");
+  if (n_rows == 0) return USF_OK;
+  usf_pack_matrix_kernel<<<ew_grid(n_rows * ldo), 256, 0, as_stream(stream)>>>(
+      src, lds, row_idx, col_idx, sub_row0, transpose_src, n_rows, n_cols, out, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo);
+  USF_LAUNCH_CHECK("usf_pack_matrix_kernel");
+  return USF_OK;
+}

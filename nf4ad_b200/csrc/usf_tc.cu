@@ -1,0 +1,523 @@
+// tcgen05 / TMEM / TMA bf16 GEMM with fused USFlow layer epilogues (sm_100a only).
+//
+//   acc[m, n] = sum_k A[m, k] * W[n, k]        A: activations (M x K, bf16), W: packed weights (N x K, bf16)
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into a 4-stage smem ring
+//   warp 1   : MMA issuer    -- one lane issues tcgen05.mma (M=128, N=bn<=256, K=16) into TMEM;
+//                               tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-5: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM, 2 x 256 cols)
+//                               and apply the layer epilogue (bias / ReLU / coupling / base density)
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+// Every mbarrier wait is bounded (g_tc_timeout flag) so a protocol bug cannot hang the GPU.
+//
+// Roofline: tensor-pipe bound for K >= 256 (4096 bf16 MAC/clk/SM); smem operand traffic per MMA is
+// (128 + bn) * 32 B per 128*bn/256... cycles, below the 128 B/clk smem port for bn >= 128.
+#include <cuda.h>
+
+#include "usf_common.cuh"
+
+namespace usf {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // bf16 elements per k-block: 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_BN = 256;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_MAX_BN * TC_BK * 2;  // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_BAR_BYTES = 256;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + 1024;  // + alignment slack
+constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr long long TC_WAIT_LIMIT_CYCLES = 400000000LL;  // ~0.2 s
+
+__device__ int g_tc_timeout = 0;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: returns false (and raises the global flag) if the barrier never completes.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*reinterpret_cast<volatile int*>(&g_tc_timeout) != 0) return false;
+    if (clock64() - t0 > TC_WAIT_LIMIT_CYCLES) {
+      atomicExch(&g_tc_timeout, 1);
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows at a 128-byte pitch, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address
+  d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+struct TcArgs {
+  int64_t M, N, K;
+  int bn;        // N-tile width (multiple of 16, <= 256)
+  int n_tiles;   // ceil(N / bn)
+  int m_tiles;
+  int n_valid;   // valid output columns for fp32 stores / base density (<= N)
+  EpiParams ep;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  const int total_tiles = args.m_tiles * args.n_tiles;
+  const int num_kb = (int)((args.K + TC_BK - 1) / TC_BK);
+  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)args.bn * TC_BK * 2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ok = mbar_wait(empty_bar(s), ph ^ 1u);
+          if (!ok) break;
+          mbar_expect_tx(full_bar(s), stage_tx);
+          const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, mt * TC_BM);
+          tma_load_2d(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, nt * args.bn);
+          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+        (void)mt;
+        int width = (int)(args.N - (int64_t)nt * args.bn);
+        if (width > args.bn) width = args.bn;
+        const uint32_t idesc = make_idesc((uint32_t)width);
+        ok = mbar_wait(tempty_bar(a), aph ^ 1u);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ok = mbar_wait(full_bar(s), ph);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * TC_STAGE_BYTES;
+          const uint32_t b_addr = a_addr + TC_A_BYTES;
+          int64_t krem = args.K - (int64_t)kb * TC_BK;
+          if (krem > TC_BK) krem = TC_BK;
+          const int ksteps = (int)((krem + TC_UMMA_K - 1) / TC_UMMA_K);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * TC_UMMA_K * 2);
+            const uint64_t bd = make_smem_desc(b_addr + k * TC_UMMA_K * 2);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // smem stage reusable once these MMAs retire
+          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(a));    // accumulator ready for the epilogue
+        a ^= 1;
+        if (a == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2..5)
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const EpiParams& ep = args.ep;
+    int a = 0;
+    uint32_t aph = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      const int64_t row = (int64_t)mt * TC_BM + lane_grp * 32 + lane;
+      const bool rvalid = row < args.M;
+      const int64_t n0 = (int64_t)nt * args.bn;
+      int width = (int)(args.N - n0);
+      if (width > args.bn) width = args.bn;
+      ok = mbar_wait(tfull_bar(a), aph);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+
+      if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
+        for (int c = 0; c < width; c += 16) {
+          float v[16];
+          tmem_ld16(t_base + c, v);
+          tmem_ld_wait();
+          if (rvalid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] += ep.bias[n0 + c + j];
+              if (ep.mode == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ep.out_bf16) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c);
+              dst[0] = q0;
+              dst[1] = q1;
+            } else {
+              float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c + j < args.n_valid) dst[j] = v[j];
+            }
+          }
+        }
+      } else if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD) {
+        const int C = ep.C;
+        float lsum = 0.f;
+        for (int c = 0; c < C; c += 16) {
+          float sv[16], tv[16];
+          tmem_ld16(t_base + c, sv);
+          tmem_ld16(t_base + C + c, tv);
+          tmem_ld_wait();
+          const int coord0 = nt * C + c;
+          if (rvalid && coord0 < ep.Db) {
+            uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+            float u[16];
+            const bool full = coord0 + 16 <= ep.Db;
+            if (full) {
+              const uint4 q0 = reinterpret_cast<const uint4*>(up)[0];
+              const uint4 q1 = reinterpret_cast<const uint4*>(up)[1];
+              unpack_bf16x8(q0, u);
+              unpack_bf16x8(q1, u + 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
+            }
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float s = sv[j] + ep.bias[n0 + c + j];
+              const float tt = tv[j] + ep.bias[n0 + C + c + j];
+              const float ls = ep.clamp * fast_tanh(s);
+              y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
+              if (coord0 + j < ep.Db) lsum += ls;
+            }
+            if (full) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
+              q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
+              q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
+              q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
+              reinterpret_cast<uint4*>(up)[0] = q0;
+              reinterpret_cast<uint4*>(up)[1] = q1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
+            }
+          }
+        }
+        if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
+      } else if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) {
+        const int C = ep.C;
+        for (int c = 0; c < C; c += 16) {
+          float tv[16];
+          tmem_ld16(t_base + c, tv);
+          tmem_ld_wait();
+          const int coord0 = nt * C + c;
+          if (rvalid && coord0 < ep.Db) {
+            uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (coord0 + j < ep.Db) {
+                const float u = __uint_as_float((uint32_t)up[j] << 16);
+                const float tt = tv[j] + ep.bias[n0 + c + j];
+                up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
+              }
+            }
+          }
+        }
+      } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE
+        float lsum = 0.f;
+        for (int c = 0; c < width; c += 16) {
+          float v[16];
+          tmem_ld16(t_base + c, v);
+          tmem_ld_wait();
+          if (rvalid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int64_t col = n0 + c + j;
+              if (col < args.n_valid) {
+                const float z = v[j] + ep.bias[col];
+                if (ep.out != nullptr) reinterpret_cast<float*>(ep.out)[row * ep.ldo + col] = z;
+                if (ep.loc != nullptr) {
+                  const float d = (z - ep.loc[col]) * ep.inv_scale[col];
+                  lsum += (ep.mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+                }
+              }
+            }
+          }
+        }
+        if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+      }
+
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));
+      a ^= 1;
+      if (a == 0) aph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor (rows x cols, leading dimension ld elements), box = box_rows x 64 cols, 128B swizzle.
+int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return USF_E_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+              (const void*)base, (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return USF_E_CUDA;
+  }
+  return USF_OK;
+}
+
+}  // namespace
+
+const char* const kTcGemmKernelName = "usf_tc_gemm_kernel";
+
+int tc_pick_bn(int64_t N) {
+  // balanced N tiles: as few tiles as possible, equal width, multiple of 16, <= 256
+  const int64_t nt = ceil_div(N, TC_MAX_BN);
+  return (int)round_up(ceil_div(N, nt), 16);
+}
+
+int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int64_t M, int64_t N, int64_t K, int bn,
+            const EpiParams& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return USF_OK;
+  USF_CHECK_ARG(A && W, "tc_gemm: null operand");
+  USF_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "tc_gemm: leading dimensions must be multiples of 8 (got %lld, %lld)",
+                (long long)lda, (long long)ldw);
+  USF_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                "tc_gemm: operands must be 16-byte aligned");
+  USF_CHECK_ARG(bn >= 16 && bn <= TC_MAX_BN && (bn % 16) == 0 && (N % 16) == 0 && K > 0,
+                "tc_gemm: bad tile/shape (bn=%d N=%lld K=%lld)", bn, (long long)N, (long long)K);
+  if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD)
+    USF_CHECK_ARG(bn == 2 * ep.C && (ep.C % 16) == 0 && (N % bn) == 0, "tc_gemm: coupling tile must be [s(C)|t(C)]");
+  if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD)
+    USF_CHECK_ARG(bn == ep.C && (N % bn) == 0, "tc_gemm: additive tile must be [t(C)]");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap(&tmA, A, M, K, lda, TC_BM);
+  if (rc) return rc;
+  rc = make_tmap(&tmW, W, N, K, ldw, bn);
+  if (rc) return rc;
+
+  TcArgs args;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.bn = bn;
+  args.n_tiles = (int)ceil_div(N, bn);
+  args.m_tiles = (int)ceil_div(M, TC_BM);
+  args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
+  args.ep = ep;
+  const int64_t total = (int64_t)args.m_tiles * args.n_tiles;
+  int grid = num_sms();
+  if (grid > total) grid = (int)total;
+  usf_tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
+  USF_LAUNCH_CHECK("usf_tc_gemm_kernel");
+  return USF_OK;
+}
+
+int tc_timeout_flag(int* out, int reset) {
+  int v = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_timeout, sizeof(int));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyFromSymbol(g_tc_timeout)");
+  if (out) *out = v;
+  if (reset && v) {
+    const int z = 0;
+    e = cudaMemcpyToSymbol(g_tc_timeout, &z, sizeof(int));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyToSymbol(g_tc_timeout)");
+  }
+  return USF_OK;
+}
+
+}  // namespace usf

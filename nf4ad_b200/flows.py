@@ -1,0 +1,352 @@
+"""`Flow`, `USFlow` (the `src.usflows.flows` names) and a `NonUSFlow` mirror on the B200 path.
+
+`Flow.log_prob / sample / forward / backward` keep the surface nf4ad's wrappers use
+(`/root/reference/src/nf4ad/adbench_wrapper.py:345,369,383,424`, `vaeflow.py:201,240`,
+`flows.py:117-125`) and the semantics of `TransformedDistribution.log_prob / sample`
+(torch `transformed_distribution.py:143-190`), but execute as:
+
+  * inference (no autograd): ONE fused launch chain over a packed layer-descriptor array
+    (`nf4ad_b200.stack` -> `usf_stack_run`), fp32 SIMT or bf16 tcgen05 GEMMs (`flow.precision`);
+  * training (autograd): the layer-wise fp32 kernels with their hand-written backward kernels
+    (`nf4ad_b200.ops` autograd Functions).
+
+CUDA tensors only -- a CPU tensor raises (`USFError`); the CPU restatement lives in `oracle/`.
+"""
+import os
+from typing import Any, Dict, List, Optional, Type
+
+import torch
+
+from . import _lib, ops, stack
+from .transforms import (
+    BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform, MaskedAffineCoupling,
+    MaskedCoupling, ScaleTransform, SequentialAffineTransform, run_conditioner, split_params,
+)
+
+_PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16}
+
+
+def _default_precision():
+    p = os.environ.get("USF_PRECISION", "fp32").lower()
+    if p not in _PRECISIONS:
+        raise ValueError(f"USF_PRECISION must be one of {sorted(_PRECISIONS)}, got {p!r}")
+    return p
+
+
+class Flow(torch.nn.Module):
+    """Normalising flow = base distribution pushed through `layers` (generative order)."""
+
+    export = "log_prob"
+
+    def __init__(self, base_distribution, layers, soft_training: bool = False,
+                 training_noise_prior=None, device="cpu", *args, **kwargs):
+        preset = dict(self.__dict__)          # subclasses assign attributes first (flows.py:54-61)
+        super().__init__()
+        for k, v in preset.items():
+            self.__dict__.setdefault(k, v)
+        self.soft_training = soft_training
+        self.training_noise_prior = training_noise_prior
+        self.layers = list(layers)
+        self.trainable_layers = torch.nn.ModuleList(
+            [l for l in self.layers if isinstance(l, torch.nn.Module)])
+        self.base_distribution = base_distribution
+        self.device = device
+        self.precision = _default_precision()   # "fp32" (<=1e-4 tier) or "bf16" (tcgen05, <=1e-2 tier)
+        self.last_launches = 0                  # kernels enqueued by the last fused call
+        self._compiled = {}
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def event_dim(self):
+        return int(self.in_dims[0]) if hasattr(self, "in_dims") else int(self._infer_dim())
+
+    def _infer_dim(self):
+        for l in self.layers:
+            if hasattr(l, "dim"):
+                d = l.dim
+                return d[0] if isinstance(d, (tuple, list)) else d
+            if hasattr(l, "mask"):
+                return l.mask.numel()
+        raise ValueError("cannot infer the event dimension")
+
+    def _weights_key(self):
+        key = [(p.data_ptr(), p._version) for p in self.parameters()]
+        key += [(b.data_ptr(), b._version) for b in self.buffers()]
+        base = self.base_distribution
+        for v in getattr(base, "__dict__", {}).values():
+            if isinstance(v, torch.Tensor):
+                key.append((v.data_ptr(), v._version))
+        return tuple(key)
+
+    def _stack(self, inverse, device):
+        """Compiled (packed) stack for this direction / precision / weight version, or None."""
+        prec = _PRECISIONS[self.precision]
+        slot = (bool(inverse), prec)
+        key = (self._weights_key(), str(device))
+        hit = self._compiled.get(slot)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        try:
+            cs = stack.CompiledStack(self.layers, self.base_distribution, self.event_dim, device, inverse, prec)
+        except stack.Unsupported as e:
+            cs = None
+            self._unsupported_reason = str(e)
+        self._compiled[slot] = (key, cs)
+        return cs
+
+    def _needs_grad(self, x):
+        if not torch.is_grad_enabled():
+            return False
+        return x.requires_grad or any(p.requires_grad for p in self.parameters())
+
+    @staticmethod
+    def _prep(x):
+        _lib.require_cuda(x)
+        squeeze = x.dim() == 1
+        x2 = x.unsqueeze(0) if squeeze else x
+        if x2.dim() != 2:
+            x2 = x2.reshape(x2.shape[0], -1)
+        return x2, squeeze
+
+    # ------------------------------------------------------------------ density path
+    def log_prob(self, x, context=None):
+        x2, squeeze = self._prep(x)
+        if not self._needs_grad(x2) and context is None:
+            cs = self._stack(True, x2.device)
+            if cs is not None and cs.desc.base_kind >= 0:
+                lp, _, _, n = cs.run(x2, want_logprob=True)
+                self.last_launches = n
+                return lp[0] if squeeze else lp
+        z, neg_ladj = self._inverse_layers(x2, context)
+        lp = self._base_log_prob(z) + neg_ladj
+        return lp[0] if squeeze else lp
+
+    def _inverse_layers(self, y, context=None):
+        """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""
+        total = torch.zeros(y.shape[0], device=y.device, dtype=torch.float32)
+        for layer in reversed(self.layers):
+            if hasattr(layer, "inverse_and_ladj"):
+                x, ladj = layer.inverse_and_ladj(y, context)
+            elif stack._is_coupling(layer) and getattr(layer, "scale_activation", "exp") == "exp":
+                # a foreign coupling class (the reference's own MaskedAffineCoupling): same arithmetic
+                mask = layer.mask.reshape(-1)
+                ym = ops.ScaleFn.apply(y, mask, False)
+                s, t = split_params(run_conditioner(layer.conditioner, ym, context), y)
+                x, ladj = ops.CouplingFn.apply(y, s, t, mask, float(getattr(layer, "clamp", 5.0)), True)
+            else:
+                x = layer.backward(y) if context is None else layer.backward(y, context)
+                ladj = layer.log_abs_det_jacobian(x, y)
+            total = total - ladj
+            y = x
+        return y, total
+
+    def _forward_layers(self, z, context=None):
+        for layer in self.layers:
+            z = layer.forward(z) if context is None else layer.forward(z, context)
+        return z
+
+    def _base_log_prob(self, z):
+        base = self.base_distribution
+        bp = stack.base_params(base, z.shape[1], z.device)
+        if bp is not None:
+            kind, _, _ = bp
+            inner = base
+            while isinstance(inner, torch.distributions.Independent):
+                inner = inner.base_dist
+            loc = torch.as_tensor(inner.loc, device=z.device)
+            scale = torch.as_tensor(inner.scale, device=z.device)
+            return ops.BaseLogProbFn.apply(z, loc.expand(z.shape[1]) if loc.numel() == 1 else loc, scale, kind)
+        lp = base.log_prob(z)                      # unsupported base: evaluated as given
+        while lp.dim() > 1:
+            lp = lp.sum(-1)
+        return lp
+
+    def backward(self, x, context=None):
+        """data -> latent."""
+        x2, squeeze = self._prep(x)
+        if not self._needs_grad(x2) and context is None:
+            cs = self._stack(True, x2.device)
+            if cs is not None:
+                _, z, _, n = cs.run(x2, want_y=True)
+                self.last_launches = n
+                return z[0] if squeeze else z
+        z, _ = self._inverse_layers(x2, context)
+        return z[0] if squeeze else z
+
+    def latent_to_data(self, z, context=None):
+        z2, squeeze = self._prep(z)
+        if not self._needs_grad(z2) and context is None:
+            cs = self._stack(False, z2.device)
+            if cs is not None:
+                _, x, _, n = cs.run(z2, want_y=True)
+                self.last_launches = n
+                return x[0] if squeeze else x
+        x = self._forward_layers(z2, context)
+        return x[0] if squeeze else x
+
+    def sample(self, sample_shape=None, context=None):
+        shape = torch.Size() if sample_shape is None else torch.Size(sample_shape)
+        with torch.no_grad():
+            z = self.base_distribution.sample(shape)
+            flat = z.reshape(-1, z.shape[-1])
+            x = self.latent_to_data(flat, context)
+            return x.reshape(z.shape)
+
+    def rsample(self, sample_shape=None, context=None):
+        shape = torch.Size() if sample_shape is None else torch.Size(sample_shape)
+        z = self.base_distribution.rsample(shape)
+        return self.latent_to_data(z.reshape(-1, z.shape[-1]), context).reshape(z.shape)
+
+    def forward(self, x=None, context=None):
+        """`export` switch (`visualization.py:85-86`)."""
+        if self.export == "log_prob":
+            return self.log_prob(x, context)
+        if self.export == "sample":
+            return self.sample()
+        if self.export == "backward":
+            return self.backward(x, context)
+        return self.latent_to_data(x, context)
+
+    # ------------------------------------------------------------------ housekeeping
+    def is_feasible(self) -> bool:
+        return all(bool(l.is_feasible()) for l in self.layers if hasattr(l, "is_feasible"))
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        for l in self.layers:
+            if hasattr(l, "jitter"):
+                l.jitter(jitter)
+
+    def log_prior(self):
+        total = 0.0
+        for l in self.layers:
+            if hasattr(l, "log_prior"):
+                total = total + l.log_prior()
+        return total
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        base = self.base_distribution
+        if not isinstance(base, torch.nn.Module):
+            seen = set()
+            while base is not None and id(base) not in seen:
+                seen.add(id(base))
+                for k, v in list(base.__dict__.items()):
+                    if isinstance(v, torch.Tensor):
+                        base.__dict__[k] = fn(v)
+                base = getattr(base, "base_dist", None)
+        self._compiled = {}
+        return out
+
+    def to(self, *args, **kwargs):
+        out = super().to(*args, **kwargs)
+        if args and isinstance(args[0], (str, torch.device)):
+            self.device = args[0]
+        elif "device" in kwargs:
+            self.device = kwargs["device"]
+        return out
+
+    def fit(self, data_train, optim=torch.optim.Adam, optim_params=None, batch_size=32, shuffle=True,
+            gradient_clip=None, device=None, jitter=1e-6, epochs=1):
+        """Feasibility check + jitter, then minimise -mean log_prob (- log_prior / N)."""
+        if device is not None:
+            self.to(device)
+        opt = optim(self.parameters(), **(optim_params or {}))
+        n = len(data_train)
+        losses = []
+        for _ in range(epochs):
+            perm = torch.randperm(n) if shuffle else torch.arange(n)
+            total = 0.0
+            for i in range(0, n, batch_size):
+                idx = perm[i:i + batch_size]
+                rows = [data_train[int(j)] for j in idx]
+                rows = [r[0] if isinstance(r, (tuple, list)) else r for r in rows]
+                batch = torch.stack(rows).to(self.device)
+                while not self.is_feasible():
+                    self.add_jitter(jitter)
+                opt.zero_grad()
+                loss = -self.log_prob(batch).mean()
+                if getattr(self, "prior_scale", None) is not None:
+                    loss = loss - self.log_prior() / n
+                loss.backward()
+                if gradient_clip is not None:
+                    torch.nn.utils.clip_grad_norm_(self.parameters(), gradient_clip)
+                opt.step()
+                total += float(loss.detach()) * len(idx)
+            losses.append(total / n)
+        return losses
+
+
+def _parity_mask(in_dims, channel_only=False, invert=False):
+    """`create_checkerboard_mask` / `create_channel_mask` (`nf4ad/flows.py:127-145`)."""
+    grids = torch.meshgrid(*[torch.arange(d, dtype=torch.int32) for d in in_dims], indexing="ij")
+    idx = torch.stack(grids)
+    m = torch.fmod(idx[0] if channel_only else idx.sum(dim=0), 2).to(torch.float32).view(1, *in_dims)
+    return 1 - m if invert else m
+
+
+class _StackedFlow(Flow):
+    """Shared builder of USFlow / NonUSFlow: per block
+    `BlockAffine(Sequential(LU x lu, Householder))`, coupling, `Inverse(block)` if conjugated,
+    alternating masks; tail `BlockAffine(LU)`, `Scale`  (`nf4ad/flows.py:78-114`)."""
+
+    MASKTYPE = ("checkerboard", "channel")
+    _coupling_cls = None
+
+    def __init__(self, base_distribution, in_dims: List[int], coupling_blocks: int,
+                 conditioner_cls: Type[torch.nn.Module], conditioner_args: Dict[str, Any],
+                 soft_training: bool = False, prior_scale: Optional[float] = None,
+                 training_noise_prior=None, affine_conjugation: bool = False, nonlinearity=None,
+                 lu_transform: int = 1, householder: int = 1, masktype: str = "checkerboard",
+                 device="cpu", *args, **kwargs):
+        self.coupling_blocks, self.in_dims = coupling_blocks, list(in_dims)
+        self.conditioner_cls, self.conditioner_args = conditioner_cls, conditioner_args
+        self.prior_scale = prior_scale
+        if masktype not in self.MASKTYPE:
+            raise ValueError(f"Unknown mask type {masktype}")
+        if lu_transform < 0:
+            raise ValueError("Number of LU transforms must be non-negative")
+        if householder < 0:
+            raise ValueError("Number of Householder vectors transforms must be non-negative")
+        if len(in_dims) != 1:
+            raise NotImplementedError("only 1-D event shapes in_dims=[D] are supported on the B200 path")
+        self.lu_transform, self.householder = lu_transform, householder
+        D = in_dims[0]
+        mask = _parity_mask(in_dims, masktype == "channel")
+        layers = []
+        for _ in range(coupling_blocks):
+            affine = [LUTransform(D, prior_scale) for _ in range(lu_transform)]
+            if householder > 0:
+                affine.append(HouseholderTransform(dim=D, nvs=householder, device="cpu"))
+            conj = BlockAffineTransform(in_dims, SequentialAffineTransform(affine)) if affine else None
+            if conj is not None:
+                layers.append(conj)
+            layers.append(self._coupling_cls(mask, conditioner_cls(**conditioner_args)))
+            if affine_conjugation and conj is not None:
+                layers.append(InverseTransform(conj))
+            mask = 1 - mask
+        layers.append(BlockAffineTransform(in_dims, LUTransform(D, prior_scale)))
+        layers.append(ScaleTransform(in_dims))
+        super().__init__(base_distribution, layers, soft_training=soft_training,
+                         training_noise_prior=training_noise_prior, device=device)
+        if str(device) != "cpu":
+            self.to(device)
+
+    create_checkerboard_mask = staticmethod(lambda in_dims, invert=False: _parity_mask(in_dims, False, invert))
+    create_channel_mask = staticmethod(lambda in_dims, invert=False: _parity_mask(in_dims, True, invert))
+
+    def log_prior(self):
+        if self.prior_scale is None:
+            return 0
+        return super().log_prior()
+
+
+class USFlow(_StackedFlow):
+    """`src.usflows.flows.USFlow`: additive couplings => data-independent total log-det."""
+
+    _coupling_cls = MaskedCoupling
+
+
+class NonUSFlow(_StackedFlow):
+    """Mirror of `nf4ad.flows.NonUSFlow` (`nf4ad/flows.py:27-125`): affine couplings."""
+
+    _coupling_cls = MaskedAffineCoupling

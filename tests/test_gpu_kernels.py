@@ -1,0 +1,135 @@
+"""GPU parity, kernel level: every C-ABI layer kernel against the fp64 CPU oracle on the same seeded
+inputs.  Tolerances: fp32 kernels max-norm relative error <= 2e-5 (well inside the 1e-4 log_prob
+tier); the tcgen05 bf16 GEMM is compared against an exact fp32 product of the bf16-rounded operands."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from nf4ad_b200 import _lib, ops as _ops
+    assert _lib.lib().usf_device_ok() == 1, "expected an sm_100 device"
+    return _ops
+
+
+@pytest.mark.parametrize("B,N,K,relu", [(5, 7, 3, False), (1, 1, 1, True), (300, 130, 70, True),
+                                        (257, 64, 129, False), (1000, 784, 784, False), (129, 1568, 256, True)])
+def test_linear_fp32(ops, B, N, K, relu):
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = x.double() @ W.double().t() + b.double()
+    ref = ref.clamp_min(0) if relu else ref
+    y = ops.linear(x.cuda(), W.cuda(), b.cuda(), relu)
+    assert relerr(y, ref) < 2e-5
+    # strided input (leading dimension > K)
+    xp = torch.zeros(B, K + 5)
+    xp[:, :K] = x
+    y2 = ops.linear(xp.cuda()[:, :K], W.cuda(), b.cuda(), relu)
+    assert relerr(y2, ref) < 2e-5
+
+
+@pytest.mark.parametrize("D", [1, 5, 32, 100, 257])
+def test_lu_pack_apply_solve(ops, O, D):
+    torch.manual_seed(D)
+    lu = O.transforms.LUTransform(D, 1.0).double()
+    with torch.no_grad():
+        lu.U_raw.diagonal().copy_((0.6 + torch.rand(D, dtype=torch.float64)) *
+                                  torch.where(torch.rand(D) < 0.3, -1.0, 1.0))
+        lu.L_raw.add_(torch.randn(D, D, dtype=torch.float64))      # junk in the unused triangles must be ignored
+        lu.U_raw.add_(torch.randn(D, D, dtype=torch.float64).tril(-1))
+    x = torch.randn(77, D, dtype=torch.float64)
+    with torch.no_grad():
+        y_ref = lu.forward(x)
+        x_ref = lu.backward(y_ref)
+    L, U, b = (t.detach().float().cuda() for t in (lu.L_raw, lu.U_raw, lu.bias))
+    W = ops.lu_pack(L, U)
+    assert relerr(W, lu.weight) < 2e-5
+    y = ops.linear(x.float().cuda(), W, b)
+    assert relerr(y, y_ref) < 2e-5
+    xs = ops.lu_solve(y_ref.float().cuda(), L, U, b)
+    assert relerr(xs, x_ref) < 1e-4
+    # transposed solve: (LU)^T g = r
+    r = torch.randn(33, D, dtype=torch.float64)
+    g_ref = torch.linalg.solve(lu.weight.detach().t(), r.t()).t()
+    g = ops.lu_solve(r.float().cuda(), L, U, None, transpose=True)
+    assert relerr(g, g_ref) < 1e-4
+
+
+@pytest.mark.parametrize("D,nvs", [(6, 1), (33, 3), (784, 2)])
+def test_householder_scale(ops, O, D, nvs):
+    torch.manual_seed(D + nvs)
+    hh = O.transforms.HouseholderTransform(D, nvs).double()
+    x = torch.randn(41, D, dtype=torch.float64)
+    V = hh.vk_householder.detach().float().cuda()
+    with torch.no_grad():
+        assert relerr(ops.householder(x.float().cuda(), V, False), hh.forward(x)) < 2e-5
+        assert relerr(ops.householder(x.float().cuda(), V, True), hh.backward(x)) < 2e-5
+    s = (torch.rand(D, dtype=torch.float64) + 0.5) * torch.where(torch.rand(D) < 0.5, -1.0, 1.0)
+    assert relerr(ops.scale(x.float().cuda(), s.float().cuda(), False), x * s) < 1e-6
+    assert relerr(ops.scale(x.float().cuda(), s.float().cuda(), True), x / s) < 1e-6
+
+
+@pytest.mark.parametrize("D,affine", [(7, True), (64, True), (785, True), (20, False)])
+def test_coupling_and_base(ops, D, affine):
+    torch.manual_seed(D)
+    B = 37
+    x = torch.randn(B, D, dtype=torch.float64)
+    s = torch.randn(B, D, dtype=torch.float64) * 2
+    t = torch.randn(B, D, dtype=torch.float64)
+    m = (torch.arange(D) % 2).double()
+    ls = 5.0 * torch.tanh(s) if affine else torch.zeros_like(s)
+    for inverse in (False, True):
+        ref = x * m + (1 - m) * ((x - t) * torch.exp(-ls) if inverse else x * torch.exp(ls) + t)
+        ladj_ref = ((1 - m) * ls).sum(1)
+        y, ladj = ops.coupling(x.float().cuda(), s.float().cuda() if affine else None, t.float().cuda(),
+                               m.float().cuda(), 5.0, inverse)
+        assert relerr(y, ref) < 1e-5
+        assert float((ladj.double().cpu() - ladj_ref).abs().max()) < 1e-4 * max(1.0, float(ladj_ref.abs().max()))
+    loc = torch.randn(D, dtype=torch.float64)
+    for kind, dist in ((0, torch.distributions.Normal), (1, torch.distributions.Laplace)):
+        for scale in (torch.rand(D, dtype=torch.float64) + 0.5, torch.tensor([1.7], dtype=torch.float64)):
+            ref = dist(loc, scale.expand(D)).log_prob(x).sum(1)
+            out = ops.base_logprob(kind, x.float().cuda(), loc.float().cuda(), scale.float().cuda())
+            assert relerr(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,K,relu,f32out", [(128, 16, 16, False, True), (128, 256, 64, False, True),
+                                               (300, 208, 104, True, False), (1000, 784, 784, False, False),
+                                               (4096, 1568, 256, True, False), (77, 48, 392, False, True),
+                                               (20000, 256, 392, True, False)])
+def test_tcgen05_linear_bf16(ops, B, N, K, relu, f32out):
+    """tcgen05 GEMM (TMA 128B swizzle, TMEM accumulators) vs exact fp32 product of the same bf16 operands."""
+    from nf4ad_b200 import _lib
+    from nf4ad_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(B + N + K)
+    ldx, ldw = (K + 7) // 8 * 8, (K + 7) // 8 * 8
+    x = torch.zeros(B, ldx)
+    x[:, :K] = torch.randn(B, K, generator=g)
+    W = torch.zeros(N, ldw)
+    W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    xb, Wb = x.cuda().bfloat16(), W.cuda().bfloat16()
+    ref = xb.float().double().cpu()[:, :K] @ Wb.float().double().cpu()[:, :K].t() + b.double()
+    ref = ref.clamp_min(0) if relu else ref
+    y = torch.full((B, N), float("nan"), device="cuda", dtype=torch.float32 if f32out else torch.bfloat16)
+    _lib.check(lib().usf_linear_bf16(ptr(xb), ldx, ptr(Wb), ldw, ptr(b.cuda()), int(relu), ptr(y), N,
+                                     0 if f32out else 1, B, N, K, stream()), "usf_linear_bf16")
+    torch.cuda.synchronize()
+    flag = C.c_int(0)
+    _lib.check(lib().usf_debug_tc_timeout(C.byref(flag), 1))
+    assert flag.value == 0, "a bounded mbarrier wait expired inside the tcgen05 GEMM"
+    assert torch.isfinite(y.float()).all()
+    tol = 1e-5 if f32out else 6e-3
+    assert relerr(y.float(), ref) < tol

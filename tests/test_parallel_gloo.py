@@ -1,0 +1,72 @@
+"""CPU, world_size 2 over gloo: the sharding / score-gather / gradient all-reduce plumbing of
+nf4ad_b200.parallel.  The scoring callable here is the CPU oracle flow (test infrastructure): the
+product kernels themselves need a GPU and are covered by the -m gpu tests."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_rows_in_order():
+    from nf4ad_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 8, 1000, 65536 + 3):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from _cases import build_flow, tame
+        from nf4ad_b200.parallel import DataParallelTrainer, ShardedScorer
+        O = oracle.load()
+        torch.manual_seed(0)
+        flow = build_flow(O, "NonUSFlow", 6, 2, ("mlp", [8]), affine_conjugation=True)
+        tame(flow, 0.5)
+        X = torch.randn(101, 6, generator=torch.Generator().manual_seed(1))
+        # ---- sharded scoring == single-process scoring
+        scorer = ShardedScorer(flow, score_fn=lambda x: flow.log_prob(x))
+        scores = scorer.predict_score(X)
+        with torch.no_grad():
+            ref = -flow.log_prob(X)
+        assert scores.shape == (101,)
+        assert torch.allclose(scores, ref, rtol=1e-6, atol=1e-6)
+        # ---- data-parallel step == single-process step on the concatenated batch
+        import copy
+        single = copy.deepcopy(flow)
+        opt_s = torch.optim.SGD(single.parameters(), lr=1e-2)
+        opt_s.zero_grad()
+        (-single.log_prob(X[:64]).mean()).backward()
+        opt_s.step()
+        opt = torch.optim.SGD(flow.parameters(), lr=1e-2)
+        tr = DataParallelTrainer(flow, opt)
+        tr.broadcast_parameters()
+        lo, hi = (0, 32) if rank == 0 else (32, 64)
+        tr.step(X[lo:hi])
+        for (n, a), (_, b) in zip(flow.named_parameters(), single.named_parameters()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), n
+        if rank == 0:
+            open(tmp, "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_scoring_and_dp_step(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    marker = str(tmp_path / "ok")
+    mp.spawn(_worker, args=(2, port, marker), nprocs=2, join=True)
+    assert open(marker).read() == "ok"
