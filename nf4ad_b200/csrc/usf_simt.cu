@@ -747,14 +747,39 @@ __global__ void usf_pack_matrix_kernel(const float* __restrict__ src, int64_t ld
 }
 
 // fp32 (B,D) -> bf16 and/or fp32 copy with padded leading dimension (pad columns zeroed); optional row_init.
+// Each thread converts 8 consecutive columns (ldy is a multiple of 8): two 16-byte loads when the source
+// row is 16-byte aligned, one 16-byte bf16 store (or two fp32 stores).  HBM-bound: 4*D B read + 2*ldy B written.
 __global__ void usf_convert_rows_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* yb, float* yf,
                                         int64_t ldy, int64_t B, int64_t D, float* row_init, float init_value) {
-  const int64_t total = B * ldy;
+  const int64_t groups = ldy >> 3;
+  const int64_t total = B * groups;
+  const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / ldy, c = i - r * ldy;
-    const float v = c < D ? x[r * ldx + c] : 0.f;
-    if (yb) yb[i] = __float2bfloat16_rn(v);
-    if (yf) yf[i] = v;
+    const int64_t r = i / groups, c = (i - r * groups) << 3;
+    float v[8];
+    const float* src = x + r * ldx + c;
+    if (vec_ok && c + 8 <= D) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c + j < D ? src[j] : 0.f;
+    }
+    if (yb) {
+      uint4 q;
+      __nv_bfloat162 h;
+      h = __floats2bfloat162_rn(v[0], v[1]); q.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[2], v[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[4], v[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[6], v[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
+      *reinterpret_cast<uint4*>(yb + r * ldy + c) = q;
+    }
+    if (yf) {
+      float4* dst = reinterpret_cast<float4*>(yf + r * ldy + c);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
     if (c == 0 && row_init) row_init[r] = init_value;
   }
 }
@@ -781,7 +806,11 @@ inline unsigned ew_grid(int64_t total, int threads = 256) {
 int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_f32, int64_t ldy, int64_t B,
                         int64_t D, float* row_init, float init_value, cudaStream_t stream) {
   if (B <= 0) return USF_OK;
-  usf_convert_rows_kernel<<<ew_grid(B * ldy), 256, 0, stream>>>(
+  if ((ldy & 7) != 0 || (reinterpret_cast<uintptr_t>(y_bf16) & 15) != 0 || (reinterpret_cast<uintptr_t>(y_f32) & 15) != 0) {
+    set_error("convert_rows: destination must be 16-byte aligned with ld %% 8 == 0");
+    return USF_E_ARG;
+  }
+  usf_convert_rows_kernel<<<ew_grid(B * (ldy >> 3)), 256, 0, stream>>>(
       x, ldx, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy, B, D, row_init, init_value);
   USF_LAUNCH_CHECK("usf_convert_rows_kernel");
   return USF_OK;

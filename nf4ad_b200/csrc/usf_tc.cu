@@ -6,7 +6,7 @@
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into a 4-stage smem ring
 //   warp 1   : MMA issuer    -- one lane issues tcgen05.mma (M=128, N=bn<=256, K=16) into TMEM;
 //                               tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM, 2 x 256 cols)
+//   warps 2-9: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM, 2 x 256 cols)
 //                               and apply the layer epilogue (bias / ReLU / coupling / base density)
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 // Every mbarrier wait is bounded (g_tc_timeout flag) so a protocol bug cannot hang the GPU.
@@ -26,12 +26,13 @@ constexpr int TC_BK = 64;  // bf16 elements per k-block: 128 bytes = one swizzle
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_STAGES = 4;
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_MAX_BN * TC_BK * 2;  // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_BAR_BYTES = 256;
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + 1024;  // + alignment slack
+constexpr uint32_t TC_EPI_BYTES = 2 * 3 * 256 * 4;  // per accumulator stage: bias / loc / inv_scale of the tile's columns
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + TC_EPI_BYTES + 1024;  // + alignment slack
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr long long TC_WAIT_LIMIT_CYCLES = 400000000LL;  // ~0.2 s
 
@@ -170,6 +171,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * TC_STAGES + 4);
+  const uint32_t epi_base = bar_base + TC_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,7 +183,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -260,147 +262,185 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------------ epilogue warps (2..9)
+    // Two warps per TMEM lane group (32 rows): `half` 0/1 takes the even/odd 16-column chunks.
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int half = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;  // 0..255 within the epilogue group
     const EpiParams& ep = args.ep;
+    float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [2][3][256]
+    const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+    const bool is_base = ep.mode == EPI_BASE_NORMAL || ep.mode == EPI_BASE_LAPLACE;
     int a = 0;
     uint32_t aph = 0;
-    bool ok = true;
-    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
       const int64_t row = (int64_t)mt * TC_BM + lane_grp * 32 + lane;
       const bool rvalid = row < args.M;
       const int64_t n0 = (int64_t)nt * args.bn;
       int width = (int)(args.N - n0);
       if (width > args.bn) width = args.bn;
-      ok = mbar_wait(tfull_bar(a), aph);
-      if (!ok) break;
-      tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+      float* ev = epi + a * 768;  // [0,256) bias, [256,512) loc, [512,768) inv_scale of this tile's columns
 
-      if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
-        for (int c = 0; c < width; c += 16) {
-          float v[16];
-          tmem_ld16(t_base + c, v);
-          tmem_ld_wait();
-          if (rvalid) {
+      // (1) stage the per-column vectors of this tile in shared memory (one element per epilogue thread)
+      {
+        const int64_t col = n0 + et;
+        const bool cv = et < width;
+        ev[et] = (cv && ep.bias != nullptr) ? ep.bias[col] : 0.f;
+        if (is_base) {
+          const bool v2 = cv && col < args.n_valid && ep.loc != nullptr;
+          ev[256 + et] = v2 ? ep.loc[col] : 0.f;
+          ev[512 + et] = v2 ? ep.inv_scale[col] : 0.f;
+        }
+      }
+      // (2) coupling: prefetch this thread's slice of the transformed coordinates (independent of the MMA)
+      uint4 uq[8];
+      if (is_cpl) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[j] += ep.bias[n0 + c + j];
-              if (ep.mode == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (ep.out_bf16) {
-              uint4 q0, q1;
-              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c);
-              dst[0] = q0;
-              dst[1] = q1;
-            } else {
-              float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c + j < args.n_valid) dst[j] = v[j];
-            }
+        for (int i = 0; i < 4; ++i) {
+          const int c = (2 * i + half) * 16;
+          const int coord0 = nt * ep.C + c;
+          if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
+            const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0);
+            uq[2 * i] = up[0];
+            uq[2 * i + 1] = up[1];
           }
         }
-      } else if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD) {
-        const int C = ep.C;
-        float lsum = 0.f;
-        for (int c = 0; c < C; c += 16) {
-          float sv[16], tv[16];
-          tmem_ld16(t_base + c, sv);
-          tmem_ld16(t_base + C + c, tv);
-          tmem_ld_wait();
-          const int coord0 = nt * C + c;
-          if (rvalid && coord0 < ep.Db) {
-            uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-            float u[16];
-            const bool full = coord0 + 16 <= ep.Db;
-            if (full) {
-              const uint4 q0 = reinterpret_cast<const uint4*>(up)[0];
-              const uint4 q1 = reinterpret_cast<const uint4*>(up)[1];
-              unpack_bf16x8(q0, u);
-              unpack_bf16x8(q1, u + 8);
-            } else {
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      const bool ok = mbar_wait(tfull_bar(a), aph);
+      if (ok) {
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+
+        if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+              const float4* bv = reinterpret_cast<const float4*>(ev + c);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
-            }
-            float y[16];
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = bv[j4];
+                v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+              }
+              if (ep.mode == EPI_BIAS_RELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float s = sv[j] + ep.bias[n0 + c + j];
-              const float tt = tv[j] + ep.bias[n0 + C + c + j];
-              const float ls = ep.clamp * fast_tanh(s);
-              y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
-              if (coord0 + j < ep.Db) lsum += ls;
-            }
-            if (full) {
-              uint4 q0, q1;
-              q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
-              q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
-              q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
-              q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-              reinterpret_cast<uint4*>(up)[0] = q0;
-              reinterpret_cast<uint4*>(up)[1] = q1;
-            } else {
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (ep.out_bf16) {
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c);
+                dst[0] = q0;
+                dst[1] = q1;
+              } else {
+                float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
-            }
-          }
-        }
-        if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
-      } else if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) {
-        const int C = ep.C;
-        for (int c = 0; c < C; c += 16) {
-          float tv[16];
-          tmem_ld16(t_base + c, tv);
-          tmem_ld_wait();
-          const int coord0 = nt * C + c;
-          if (rvalid && coord0 < ep.Db) {
-            uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (coord0 + j < ep.Db) {
-                const float u = __uint_as_float((uint32_t)up[j] << 16);
-                const float tt = tv[j] + ep.bias[n0 + c + j];
-                up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c + j < args.n_valid) dst[j] = v[j];
               }
             }
           }
-        }
-      } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE
-        float lsum = 0.f;
-        for (int c = 0; c < width; c += 16) {
-          float v[16];
-          tmem_ld16(t_base + c, v);
-          tmem_ld_wait();
-          if (rvalid) {
+        } else if (is_cpl) {
+          const int C = ep.C;
+          float lsum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int64_t col = n0 + c + j;
-              if (col < args.n_valid) {
-                const float z = v[j] + ep.bias[col];
-                if (ep.out != nullptr) reinterpret_cast<float*>(ep.out)[row * ep.ldo + col] = z;
-                if (ep.loc != nullptr) {
-                  const float d = (z - ep.loc[col]) * ep.inv_scale[col];
-                  lsum += (ep.mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+          for (int i = 0; i < 4; ++i) {
+            const int c = (2 * i + half) * 16;
+            if (c < C) {  // warp-uniform
+              float sv[16], tv[16];
+              tmem_ld16(t_base + c, sv);
+              tmem_ld16(t_base + C + c, tv);
+              tmem_ld_wait();
+              const int coord0 = nt * C + c;
+              if (rvalid && coord0 < ep.Db) {
+                uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+                float u[16];
+                const bool full = coord0 + 16 <= ep.Db;
+                if (full) {
+                  unpack_bf16x8(uq[2 * i], u);
+                  unpack_bf16x8(uq[2 * i + 1], u + 8);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
+                }
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float s = sv[j] + ev[c + j];
+                  const float tt = tv[j] + ev[C + c + j];
+                  const float ls = ep.clamp * fast_tanh(s);
+                  y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
+                  if (coord0 + j < ep.Db) lsum += ls;
+                }
+                if (full) {
+                  uint4 q0, q1;
+                  q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
+                  q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
+                  q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
+                  q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
+                  reinterpret_cast<uint4*>(up)[0] = q0;
+                  reinterpret_cast<uint4*>(up)[1] = q1;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
                 }
               }
             }
           }
+          if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
+        } else if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) {
+          const int C = ep.C;
+          for (int c = half * 16; c < C; c += 32) {
+            float tv[16];
+            tmem_ld16(t_base + c, tv);
+            tmem_ld_wait();
+            const int coord0 = nt * C + c;
+            if (rvalid && coord0 < ep.Db) {
+              uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (coord0 + j < ep.Db) {
+                  const float u = __uint_as_float((uint32_t)up[j] << 16);
+                  const float tt = tv[j] + ev[c + j];
+                  up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
+                }
+              }
+            }
+          }
+        } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE  (padded columns have inv_scale = 0 -> contribute 0)
+          float lsum = 0.f;
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float z = v[j] + ev[c + j];
+                if (ep.out != nullptr && n0 + c + j < args.n_valid)
+                  reinterpret_cast<float*>(ep.out)[row * ep.ldo + n0 + c + j] = z;
+                const float d = (z - ev[256 + c + j]) * ev[512 + c + j];
+                lsum += (ep.mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+              }
+            }
+          }
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
         }
-        if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
-      }
 
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(a));
+        // accumulator drained: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(a));
+      }
       a ^= 1;
       if (a == 0) aph ^= 1u;
     }

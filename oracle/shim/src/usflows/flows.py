@@ -45,8 +45,9 @@ class Flow(torch.nn.Module):
     def _rebuild(self):
         base = self.base_distribution
         nb = len(base.batch_shape)
-        self._event_base = dist.Independent(base, nb) if nb > 0 else base
-        self.transform = dist.TransformedDistribution(self._event_base, self.layers)
+        # plain attributes (not registered sub-modules): keep state_dict keys = parameters of the layers + base
+        self.__dict__["_event_base"] = dist.Independent(base, nb) if nb > 0 else base
+        self.__dict__["transform"] = dist.TransformedDistribution(self._event_base, self.layers)
 
     # ---- density path (transformed_distribution.py:143-190) ----
     def log_prob(self, x, context=None):

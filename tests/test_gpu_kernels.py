@@ -47,8 +47,8 @@ def test_lu_pack_apply_solve(ops, O, D):
     with torch.no_grad():
         lu.U_raw.diagonal().copy_((0.6 + torch.rand(D, dtype=torch.float64)) *
                                   torch.where(torch.rand(D) < 0.3, -1.0, 1.0))
-        lu.L_raw.add_(torch.randn(D, D, dtype=torch.float64))      # junk in the unused triangles must be ignored
-        lu.U_raw.add_(torch.randn(D, D, dtype=torch.float64).tril(-1))
+        lu.L_raw.add_(torch.randn(D, D, dtype=torch.float64).triu(0))   # junk in the unused triangles
+        lu.U_raw.add_(torch.randn(D, D, dtype=torch.float64).tril(-1))  # (and L's diagonal) must be ignored
     x = torch.randn(77, D, dtype=torch.float64)
     with torch.no_grad():
         y_ref = lu.forward(x)
