@@ -31,6 +31,8 @@ ALG_FLOP_PER_SAMPLE = 26.84e6      # mask-pruned, conditioner counted once (SURV
 ALG_BYTES_PER_SAMPLE = 4 * D + 4
 LAST_LAYER_GAIN = 0.25             # trained-flow-like activations (see DESIGN.md "Synthetic weights")
 CPU_SAMPLE_ROWS = 4096
+# DRAM bytes per GEMM launch at 65536 rows from the committed ncu capture (8*(160.3+69.2+34.0+103.6) MB / 33)
+NCU_DRAM_BYTES_PER_LAUNCH = 89.0e6
 
 
 def build_flow(ns, device, dtype=torch.float32):
@@ -213,6 +215,8 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-s", type=float, default=1.0, help="untimed clock pre-warm (0 for profiler runs)")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps (0 disables the leg)")
+    ap.add_argument("--train-rows", type=int, default=4096, help="per-GPU training batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -320,10 +324,31 @@ def main():
         per_tag = {}
         for i in range(n.value):
             per_tag.setdefault(tags[i], []).append(ms[i])
-    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
+    train_ms, train_B, train_steps = float("nan"), args.train_rows, args.train_steps
+    if train_steps > 0:
+        from nf4ad_b200.parallel import DataParallelTrainer
+        tflow = build_flow(P, dev).train()
+        opt = torch.optim.Adam(tflow.parameters(), lr=1e-4)
+        trainer = DataParallelTrainer(tflow, opt)
+        trainer.broadcast_parameters()
+        xb = x[:train_B]
+        for _ in range(3):
+            trainer.step(xb)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(train_steps):
+            loss = trainer.step(xb)
+        g1.record()
+        barrier()
+        train_ms = g0.elapsed_time(g1)
+        assert bool(torch.isfinite(loss))
+        del tflow, opt, trainer
+    t = torch.tensor([ms_total, e2e_ms, train_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         n_gemm = sum(len(v) for k, v in per_tag.items() if k != 0)
@@ -349,12 +374,18 @@ def main():
             "roofline": {"bound": "tensor", "kernel": _lib.lib().usf_gemm_kernel_name(
                              _lib.USF_PREC_BF16 if args.precision == "bf16" else _lib.USF_PREC_FP32).decode(),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 GEMM kinds "
+                                           "weighted by launches/step, profiles/r1_run2/tc_gemm_full_raw.csv",
                          "alg_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_ms,
                          "gemm_share_of_step": gemm_ms_per_step / (ms_total / args.steps),
                          "launch_ms_by_kind": {names[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},
                          "launches_by_kind": {names[k]: len(v) // steps_prof for k, v in sorted(per_tag.items())}},
         }
+        if train_steps > 0:
+            line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam, fp32 path)",
+                             "value": train_B * world * train_steps / (train_ms * 1e-3), "unit": "samples/s",
+                             "batch_per_gpu": train_B, "steps": train_steps, "ms_per_step": train_ms / train_steps}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, cms = cpu_reference_run(3, 1, CPU_SAMPLE_ROWS)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",

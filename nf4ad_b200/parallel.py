@@ -30,6 +30,8 @@ class ShardedScorer:
         self.flow, self.group = flow, group
         self.score_fn = score_fn or (lambda x: flow.log_prob(x))
         self.rank, self.world = _world(group)
+        self.chunk_rows = 16384         # rows per H2D / compute pipeline stage of predict_score_host
+        self._copy_stream = None
 
     def score_local(self, x_dev):
         """log_prob of rows already resident on this rank's device."""
@@ -53,10 +55,34 @@ class ShardedScorer:
     def predict_score_host(self, x_host, gather=False):
         """This rank's rows from (pinned) host memory -> device -> log_prob -> -scores back on the host.
         H2D and D2H happen inside the call (adbench_wrapper.py:419,433)."""
-        dev = next(self.flow.parameters()).device if hasattr(self.flow, "parameters") else "cpu"
-        x = x_host.to(dev, non_blocking=True)
-        with torch.no_grad():
-            scores = -self.score_fn(x)
+        dev = next(self.flow.parameters()).device if hasattr(self.flow, "parameters") else torch.device("cpu")
+        n = x_host.shape[0]
+        if dev.type != "cuda" or n < 2 * self.chunk_rows:
+            x = x_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                scores = -self.score_fn(x)
+        else:
+            # chunked, double-buffered: the H2D copy of chunk i+1 (copy stream) overlaps the launch chain
+            # of chunk i (current stream); rows are independent so results are identical
+            cur = torch.cuda.current_stream(dev)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+            cs.wait_stream(cur)
+            scores = torch.empty(n, device=dev, dtype=torch.float32)
+            pending = []
+            for lo in range(0, n, self.chunk_rows):
+                hi = min(n, lo + self.chunk_rows)
+                with torch.cuda.stream(cs):
+                    xc = x_host[lo:hi].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                pending.append((lo, hi, xc, ev))
+            with torch.no_grad():
+                for lo, hi, xc, ev in pending:
+                    cur.wait_event(ev)
+                    xc.record_stream(cur)
+                    torch.neg(self.score_fn(xc), out=scores[lo:hi])
         if gather:
             scores = self.gather(scores)
         return scores.cpu()

@@ -276,3 +276,49 @@ def test_adbench_style_fit_and_score(P):
         scores = (-flow.log_prob(torch.from_numpy(Xte).cuda())).cpu().numpy()
     assert scores.shape == (100,) and np.all(np.isfinite(scores)) and scores.std() > 0
     assert np.median(scores[50:]) > np.median(scores[:50])
+
+
+def test_foreign_coupling_class_is_recognised(O, P):
+    """The reference's own `MaskedAffineCoupling` is a *foreign* class to this package (it subclasses the
+    drop-in `BaseTransform` and does its arithmetic in eager torch).  `Flow` must recognise such a layer
+    structurally (mask / conditioner / clamp / scale_activation) and run it on the fused kernels.  The
+    stand-in below has the same attributes and an eager implementation that would be wrong if it were
+    ever called (it raises), proving the fused and layer-wise paths do not route through it."""
+    from _cases import MLP
+    T = P.transforms
+
+    class ForeignCoupling(T.BaseTransform):
+        def __init__(self, mask, conditioner):
+            super().__init__()
+            self.register_buffer("mask", mask.float())
+            self.conditioner = conditioner
+            self.scale_activation = "exp"
+            self.clamp = 5.0
+
+        def forward(self, x, context=None):
+            raise AssertionError("eager coupling must not be used on the CUDA path")
+
+        backward = forward
+        log_abs_det_jacobian = forward
+
+    D, K = 24, 2
+    torch.manual_seed(11)
+    fo = build_flow(O, "NonUSFlow", D, K, ("mlp", [32]), affine_conjugation=True)
+    tame(fo, 0.25)
+    ref_layers = build_flow(P, "NonUSFlow", D, K, ("mlp", [32]), affine_conjugation=True)
+    ref_layers.load_state_dict(fo.state_dict())
+    layers = []
+    for l in ref_layers.layers:
+        if isinstance(l, T.MaskedAffineCoupling):
+            l = ForeignCoupling(l.mask, l.conditioner)
+        layers.append(l)
+    flow = P.Flow(torch.distributions.Normal(torch.zeros(D), torch.ones(D)), layers).to("cuda").eval()
+    x = torch.randn(130, D)
+    with torch.no_grad():
+        ref = fo.double().log_prob(x.double())
+        lp = flow.log_prob(x.cuda())
+        assert flow.last_launches > 0
+        assert rel(lp, ref) < FP32_TOL
+    flow.train()
+    lp2 = flow.log_prob(x.cuda())          # autograd (layer-wise) path
+    assert lp2.requires_grad and rel(lp2, ref) < FP32_TOL
