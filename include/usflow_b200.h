@@ -236,6 +236,11 @@ int usf_profile_end(float* ms, int* tags, int* n_out);
  * GEMM expired (a pipeline protocol bug); synchronises the device. */
 int usf_debug_tc_timeout(int* flag, int reset);
 
+/* Debug: in-kernel pipeline trace of the tcgen05 GEMM.  on != 0 enables recording for subsequent launches
+ * (CTAs 0 and 1; roles 0 TMA producer, 1 MMA issuer, 2 first epilogue warp; 2048 records of
+ * {tile<<8 | event, SM clock} per (CTA, role)); out != NULL copies the last launch's 12288 records. */
+int usf_debug_tc_trace(int on, unsigned long long* out, int max_records);
+
 /* Standalone bf16 tensor-core GEMM y = act(x W^T + bias) (testing / conditioner layers):
  * x:(B,K) bf16 ldx, W:(N,K) bf16 ldw (ld multiples of 8, N multiple of 16), y:(B,N) bf16 or fp32. */
 int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias, int relu,

@@ -122,6 +122,10 @@ extern "C" const char* usf_gemm_kernel_name(int precision) {
 
 extern "C" int usf_debug_tc_timeout(int* flag, int reset) { return tc_timeout_flag(flag, reset); }
 
+extern "C" int usf_debug_tc_trace(int on, unsigned long long* out, int max_records) {
+  return tc_trace_ctl(on, out, max_records);
+}
+
 extern "C" int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias,
                                int relu, void* y, int64_t ldy, int y_is_bf16, int64_t B, int64_t N, int64_t K,
                                usf_stream_t stream) {

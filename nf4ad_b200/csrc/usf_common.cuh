@@ -91,6 +91,7 @@ int tc_pick_bn(int64_t N);
 extern const char* const kTcGemmKernelName;
 extern const char* const kSimtGemmKernelName;
 int tc_timeout_flag(int* out, int reset);
+int tc_trace_ctl(int on, unsigned long long* out, int max_records);
 int trsm_rows(const float* T, int64_t D, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr,
               const float* bias, float* X, int64_t ldx, int64_t B, cudaStream_t stream);
 

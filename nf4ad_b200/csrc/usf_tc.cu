@@ -14,6 +14,7 @@
 // Roofline: tensor-pipe bound for K >= 256 (4096 bf16 MAC/clk/SM); smem operand traffic per MMA is
 // (128 + bn) * 32 B per 128*bn/256... cycles, below the 128 B/clk smem port for bn >= 128.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "usf_common.cuh"
 
@@ -24,15 +25,24 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // bf16 elements per k-block: 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_STAGES = 4;
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
-constexpr uint32_t TC_B_BYTES = TC_MAX_BN * TC_BK * 2;  // 32 KB
-constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_BAR_BYTES = 256;
+constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_EPI_BYTES = 2 * 3 * 256 * 4;  // per accumulator stage: bias / loc / inv_scale of the tile's columns
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + TC_EPI_BYTES + 1024;  // + alignment slack
+constexpr uint32_t TC_STG_WARP_BYTES = 32 * 128;            // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled
+constexpr uint32_t TC_STG_BYTES = 8 * TC_STG_WARP_BYTES;    // coalescing transpose buffers of the 8 epilogue warps
+// CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x bn tile; 2 = a CTA pair (cluster of 2) owns a
+// 256 x bn tile, each CTA staging its own 128 rows of A and HALF of the W tile, which halves the L2->SMEM weight
+// traffic per CTA (the measured bound of the 1-CTA kernel) and the SMEM operand reads per MMA.
+template <int CG>
+struct TcCfg {
+  static constexpr uint32_t B_BYTES = (TC_MAX_BN / CG) * TC_BK * 2;  // 32 KB / 16 KB
+  static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;      // 48 KB / 32 KB
+  static constexpr uint32_t FIXED_BYTES = TC_BAR_BYTES + TC_EPI_BYTES + TC_STG_BYTES + 1024;  // + alignment slack
+  static constexpr uint32_t SMEM_BYTES = 227 * 1024;   // request the whole carve-out; the ring takes what is left
+};
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr long long TC_WAIT_LIMIT_CYCLES = 400000000LL;  // ~0.2 s
 
@@ -82,6 +92,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// 2-CTA variants: the load lands in this CTA's smem but signals the LEADER CTA's mbarrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  uint32_t leader_bar;   // shared::cluster address of the same-offset barrier in CTA 0 of the pair
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(bar), "r"(0));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-offset mbarrier of CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -96,9 +134,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TC_BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=m (128, or 256 for a CTA pair), N=n.
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n, uint32_t m) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -111,6 +149,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of a CTA-pair MMA: arrives on the same-offset mbarrier of BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -151,20 +204,151 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// Warp-private staging tile: 32 rows x (up to) 8 pieces of 16 bytes, piece p of row r at r*128 + ((p ^ (r&7)) << 4)
+// (the XOR swizzle makes both the row-per-thread accesses and the 8-lanes-per-row accesses bank-conflict free).
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int r, int p) {
+  return base + (uint32_t)r * 128u + (uint32_t)((p ^ (r & 7)) << 4);
+}
+// Coalesced copy between the staging tile and global bf16 rows: 8 (ppr) consecutive lanes move one row's
+// contiguous pieces, so every warp instruction touches full 128-byte lines instead of 32 different rows.
+//   g: element pointer of (row0, col0); ld: row pitch in elements; nrows <= 32 valid rows; ppr = pieces per row;
+//   valid_elems = number of valid elements per row from col0 (partial last piece handled element-wise).
+// Fast path of stg_copy for a full 32-row x 64-column slab: no divisions, all eight 16-byte shared loads (or global
+// loads) of a lane issued before their stores so the latencies overlap.  `sp` = staging tile as uint4[32*8].
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void stg_copy_full(uint4* sp, uint16_t* g, int64_t ld, int lane) {
+  const int pp = lane & 7, r0 = lane >> 3;   // 8 lanes per row, 4 rows per pass
+  uint4 q[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + r0;
+    if (TO_GLOBAL) q[it] = sp[r * 8 + (pp ^ (r & 7))];
+    else q[it] = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + pp * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + r0;
+    if (TO_GLOBAL) *reinterpret_cast<uint4*>(g + (int64_t)r * ld + pp * 8) = q[it];
+    else sp[r * 8 + (pp ^ (r & 7))] = q[it];
+  }
+}
+
+// Full 32 rows, PPR full 16-byte pieces per row (PPR compile-time => no runtime division), loads before stores.
+template <bool TO_GLOBAL, int PPR>
+__device__ __forceinline__ void stg_copy_rows(uint4* sp, uint16_t* g, int64_t ld, int lane) {
+  uint4 q[PPR];
+#pragma unroll
+  for (int it = 0; it < PPR; ++it) {
+    const int idx = it * 32 + lane, r = idx / PPR, pp = idx - r * PPR;
+    if (TO_GLOBAL) q[it] = sp[r * 8 + (pp ^ (r & 7))];
+    else q[it] = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + pp * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < PPR; ++it) {
+    const int idx = it * 32 + lane, r = idx / PPR, pp = idx - r * PPR;
+    if (TO_GLOBAL) *reinterpret_cast<uint4*>(g + (int64_t)r * ld + pp * 8) = q[it];
+    else sp[r * 8 + (pp ^ (r & 7))] = q[it];
+  }
+}
+// Dispatch: full tiles take the unrolled constant-PPR path, ragged ones (row / column tails) the generic loop.
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void stg_copy_any(uint32_t base, uint4* sp, uint16_t* g, int64_t ld, int nrows, int ppr,
+                                             int valid_elems, int lane);
+
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void stg_copy(uint32_t base, uint16_t* g, int64_t ld, int nrows, int ppr, int valid_elems, int lane) {
+  const int total = 32 * ppr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / ppr, pp = idx - r * ppr;
+    if (r >= nrows) continue;
+    const int e0 = pp * 8;
+    if (e0 >= valid_elems) continue;
+    uint16_t* gp = g + (int64_t)r * ld + e0;
+    const uint32_t sa = stg_addr(base, r, pp);
+    if (e0 + 8 <= valid_elems) {
+      if (TO_GLOBAL) *reinterpret_cast<uint4*>(gp) = ld_shared_v4(sa);
+      else st_shared_v4(sa, *reinterpret_cast<const uint4*>(gp));
+    } else {
+      for (int e = 0; e0 + e < valid_elems; ++e) {
+        if (TO_GLOBAL) {
+          uint16_t h;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sa + 2 * e) : "memory");
+          gp[e] = h;
+        } else {
+          const uint16_t h = gp[e];
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa + 2 * e), "h"(h) : "memory");
+        }
+      }
+    }
+  }
+}
+
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void stg_copy_any(uint32_t base, uint4* sp, uint16_t* g, int64_t ld, int nrows, int ppr,
+                                             int valid_elems, int lane) {
+  if (nrows == 32 && valid_elems == ppr * 8) {
+    switch (ppr) {
+      case 8: stg_copy_full<TO_GLOBAL>(sp, g, ld, lane); return;
+      case 7: stg_copy_rows<TO_GLOBAL, 7>(sp, g, ld, lane); return;
+      case 6: stg_copy_rows<TO_GLOBAL, 6>(sp, g, ld, lane); return;
+      case 5: stg_copy_rows<TO_GLOBAL, 5>(sp, g, ld, lane); return;
+      case 4: stg_copy_rows<TO_GLOBAL, 4>(sp, g, ld, lane); return;
+      case 3: stg_copy_rows<TO_GLOBAL, 3>(sp, g, ld, lane); return;
+      case 2: stg_copy_rows<TO_GLOBAL, 2>(sp, g, ld, lane); return;
+      case 1: stg_copy_rows<TO_GLOBAL, 1>(sp, g, ld, lane); return;
+      default: break;
+    }
+  }
+  stg_copy<TO_GLOBAL>(base, g, ld, nrows, ppr, valid_elems, lane);
+}
+
 struct TcArgs {
   int64_t M, N, K;
   int bn;        // N-tile width (multiple of 16, <= 256)
   int n_tiles;   // ceil(N / bn)
-  int m_tiles;
+  int m_tiles;   // ceil(M / (128 * CG))
   int n_valid;   // valid output columns for fp32 stores / base density (<= N)
+  int stages;                 // smem ring depth (<= TC_MAX_STAGES)
+  uint32_t stage_bytes;       // bytes per stage (A tile + this CTA's W rows), multiple of 1024
+  int stage_out;              // 1: bf16 outputs / coupling I/O go through the warp-private smem staging tiles (coalesced
+                              // global access, costs smem bandwidth + 32 KB of ring); 0: direct row-per-thread access
+  int dbg;                    // debug experiments (env USF_TC_DBG): 1 = copy-out without the global store, 2 = no copy-out
+  unsigned long long* trace;  // debug: per-role timestamp records of CTA 0/1 (NULL = off), see usf_debug_tc_trace
   EpiParams ep;
 };
 
+// Debug tracing: record (role, tile, event) with an SM clock stamp.  3 roles x 2 CTAs x TC_TRACE_CAP records.
+constexpr int TC_TRACE_CAP = 2048;
+__device__ unsigned long long g_tc_trace[2 * 3 * TC_TRACE_CAP * 2];
+__device__ __forceinline__ void tc_trace(unsigned long long* buf, int& n, int tile, int ev) {
+  if (buf != nullptr && n < TC_TRACE_CAP) {
+    buf[2 * n] = ((unsigned long long)tile << 8) | (unsigned long long)ev;
+    buf[2 * n + 1] = (unsigned long long)clock64();
+    ++n;
+  }
+}
+
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs args) {
+  using Cfg = TcCfg<CG>;
+  // runtime ring geometry: a stage holds 128 rows of A and bn/CG rows of W (1 KB granularity), as many stages as fit
+  const int TC_STAGES = args.stages;
+  const uint32_t TC_STAGE_BYTES = args.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent work unit (CTA / CTA pair)
+  const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
@@ -178,30 +362,44 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), CG);       // leader's arrive.expect_tx (+ the peer's remote arrive)
+      mbar_init(empty_bar(s), 1);       // one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * CG);  // 8 epilogue warps per CTA, all arriving on the leader's barrier
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
   const int total_tiles = args.m_tiles * args.n_tiles;
+  // trace region of this (CTA, role): only CTAs 0 and 1 record
+  int trn = 0;
+  unsigned long long* trb = nullptr;
+  if (args.trace != nullptr && blockIdx.x < 2) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    if (warp <= 2 && lane == 0) trb = args.trace + (size_t)(blockIdx.x * 3 + role) * TC_TRACE_CAP * 2;
+  }
   const int num_kb = (int)((args.K + TC_BK - 1) / TC_BK);
-  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)args.bn * TC_BK * 2;
+  // bytes landing per stage on the (leader's) full barrier: every CTA loads 128 rows of A and bn/CG rows of W
+  const uint32_t stage_tx = CG * (TC_A_BYTES + (uint32_t)(args.bn / CG) * TC_BK * 2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -209,38 +407,57 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      for (int t = unit; t < total_tiles && ok; t += num_units) {
         const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+        int width = (int)(args.N - (int64_t)nt * args.bn);
+        if (width > args.bn) width = args.bn;
+        // a pair splits the tile's N columns evenly: CTA r stages W rows [n0 + r*width/2, +width/2)
+        const int w_row = nt * args.bn + (CG == 2 ? (int)cta_rank * (width >> 1) : 0);
+        const int a_row = (mt * CG + (int)cta_rank) * TC_BM;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (kb == 0) tc_trace(trb, trn, t, 0);
           ok = mbar_wait(empty_bar(s), ph ^ 1u);
           if (!ok) break;
-          mbar_expect_tx(full_bar(s), stage_tx);
+          if (kb == 0) tc_trace(trb, trn, t, 1);
+          if (kb == num_kb - 1) tc_trace(trb, trn, t, 2);
           const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
-          tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, mt * TC_BM);
-          tma_load_2d(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, nt * args.bn);
+          if (CG == 1) {
+            mbar_expect_tx(full_bar(s), stage_tx);
+            tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+            tma_load_2d(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
+          } else {
+            if (cta_rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+            else mbar_arrive_cluster(full_bar(s), 0);
+            tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+            tma_load_2d_2sm(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
+          }
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      for (int t = unit; t < total_tiles && ok; t += num_units) {
         const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
         (void)mt;
         int width = (int)(args.N - (int64_t)nt * args.bn);
         if (width > args.bn) width = args.bn;
-        const uint32_t idesc = make_idesc((uint32_t)width);
+        const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * CG);
+        tc_trace(trb, trn, t, 0);
         ok = mbar_wait(tempty_bar(a), aph ^ 1u);
         if (!ok) break;
+        tc_trace(trb, trn, t, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ok = mbar_wait(full_bar(s), ph);
           if (!ok) break;
+          if (kb == 0) tc_trace(trb, trn, t, 2);
+          if (kb == num_kb - 1) tc_trace(trb, trn, t, 3);
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * TC_STAGE_BYTES;
           const uint32_t b_addr = a_addr + TC_A_BYTES;
@@ -250,20 +467,24 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = make_smem_desc(a_addr + k * TC_UMMA_K * 2);
             const uint64_t bd = make_smem_desc(b_addr + k * TC_UMMA_K * 2);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 1) umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));  // smem stage reusable once these MMAs retire
+          if (CG == 1) umma_commit(empty_bar(s));  // smem stage reusable once these MMAs retire
+          else umma_commit_2sm(empty_bar(s));      // ... in both CTAs of the pair
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
         if (!ok) break;
-        umma_commit(tfull_bar(a));    // accumulator ready for the epilogue
+        if (CG == 1) umma_commit(tfull_bar(a));    // accumulator ready for the epilogue
+        else umma_commit_2sm(tfull_bar(a));        // (each CTA of the pair holds its own 128 rows in its TMEM)
         a ^= 1;
         if (a == 0) aph ^= 1u;
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..9)
-    // Two warps per TMEM lane group (32 rows): `half` 0/1 takes the even/odd 16-column chunks.
+    // Two warps per TMEM lane group (32 rows): `half` 0/1 takes the even/odd 64-column slabs (bf16 outputs, staged
+    // through a warp-private smem tile for coalesced global access) or the even/odd 16-column chunks (fp32 / density).
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int half = (warp - 2) >> 2;
     const int et = (int)threadIdx.x - 64;  // 0..255 within the epilogue group
@@ -273,9 +494,9 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const bool is_base = ep.mode == EPI_BASE_NORMAL || ep.mode == EPI_BASE_LAPLACE;
     int a = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit; t < total_tiles; t += num_units) {
       const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
-      const int64_t row = (int64_t)mt * TC_BM + lane_grp * 32 + lane;
+      const int64_t row = (int64_t)(mt * CG + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
       const bool rvalid = row < args.M;
       const int64_t n0 = (int64_t)nt * args.bn;
       int width = (int)(args.N - n0);
@@ -296,6 +517,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // (2) coupling: prefetch this thread's slice of the transformed coordinates (independent of the MMA)
       uint4 uq[8];
       if (is_cpl) {
+        // each thread prefetches its own row's 16-coordinate chunks (even/odd chunks per warp half)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = (2 * i + half) * 16;
@@ -307,14 +529,44 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      __syncwarp();
+      tc_trace(trb, trn, t, 0);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_trace(trb, trn, t, 1);
 
       const bool ok = mbar_wait(tfull_bar(a), aph);
+      tc_trace(trb, trn, t, 2);
       if (ok) {
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
 
-        if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
+        if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16) {
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+              const float4* bv = reinterpret_cast<const float4*>(ev + c);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = bv[j4];
+                v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+              }
+              if (ep.mode == EPI_BIAS_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c);
+              dst[0] = q0;
+              dst[1] = q1;
+            }
+          }
+        } else if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
           for (int c = half * 16; c < width; c += 32) {
             float v[16];
             tmem_ld16(t_base + c, v);
@@ -439,7 +691,11 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(a));
+        if (lane == 0) {
+          if (CG == 1 || cta_rank == 0) mbar_arrive(tempty_bar(a));
+          else mbar_arrive_cluster(tempty_bar(a), 0);
+        }
+        tc_trace(trb, trn, t, 3);
       }
       a ^= 1;
       if (a == 0) aph ^= 1u;
@@ -447,10 +703,12 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still be reading this CTA's smem / arriving on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -498,6 +756,18 @@ int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols,
 
 const char* const kTcGemmKernelName = "usf_tc_gemm_kernel";
 
+bool g_trace_on = false;
+
+// CTAs per MMA: 2 (CTA pairs, tcgen05 cta_group::2) unless USF_TC_CTA_GROUP=1 selects the single-CTA kernel.
+int tc_cta_group() {
+  static int cg = 0;
+  if (cg == 0) {
+    const char* e = getenv("USF_TC_CTA_GROUP");
+    cg = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return cg;
+}
+
 int tc_pick_bn(int64_t N) {
   // balanced N tiles: as few tiles as possible, equal width, multiple of 16, <= 256
   const int64_t nt = ceil_div(N, TC_MAX_BN);
@@ -519,15 +789,17 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD)
     USF_CHECK_ARG(bn == ep.C && (N % bn) == 0, "tc_gemm: additive tile must be [t(C)]");
 
+  const int cg = tc_cta_group();
   static bool attr_set = false;
   if (!attr_set) {
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<1>::SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<2>::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap tmA, tmW;
   int rc = make_tmap(&tmA, A, M, K, lda, TC_BM);
   if (rc) return rc;
-  rc = make_tmap(&tmW, W, N, K, ldw, bn);
+  rc = make_tmap(&tmW, W, N, K, ldw, bn / cg);
   if (rc) return rc;
 
   TcArgs args;
@@ -536,14 +808,66 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   args.K = K;
   args.bn = bn;
   args.n_tiles = (int)ceil_div(N, bn);
-  args.m_tiles = (int)ceil_div(M, TC_BM);
+  args.m_tiles = (int)ceil_div(M, TC_BM * cg);
   args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
   args.ep = ep;
+  args.stage_out = 0;
+  args.stage_bytes = TC_A_BYTES + (uint32_t)round_up((int64_t)(bn / cg) * TC_BK * 2, 1024);
+  args.stages = (int)((227 * 1024 - (TcCfg<1>::FIXED_BYTES - TC_STG_BYTES)) / args.stage_bytes);
+  if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
+  {
+    static int cap = -1;   // tuning knob: USF_TC_MAX_STAGES caps the ring depth
+    if (cap < 0) { const char* e = getenv("USF_TC_MAX_STAGES"); cap = e ? atoi(e) : TC_MAX_STAGES; }
+    if (cap >= 2 && args.stages > cap) args.stages = cap;
+  }
+  if (args.stages < 2) { set_error("tc_gemm: tile does not fit in shared memory"); return USF_E_ARG; }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("USF_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    args.dbg = dbg;
+  }
+  args.trace = nullptr;
+  if (g_trace_on) {
+    void* p = nullptr;
+    USF_CUDA(cudaGetSymbolAddress(&p, g_tc_trace));
+    USF_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned long long) * 2 * 3 * TC_TRACE_CAP * 2, stream));
+    args.trace = reinterpret_cast<unsigned long long*>(p);
+  }
   const int64_t total = (int64_t)args.m_tiles * args.n_tiles;
-  int grid = num_sms();
-  if (grid > total) grid = (int)total;
-  usf_tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
-  USF_LAUNCH_CHECK("usf_tc_gemm_kernel");
+  if (cg == 1) {
+    int grid = num_sms();
+    if (grid > total) grid = (int)total;
+    usf_tc_gemm_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(tmA, tmW, args);
+    USF_LAUNCH_CHECK("usf_tc_gemm_kernel<1>");
+    return USF_OK;
+  }
+  int64_t pairs = num_sms() / 2;
+  if (pairs > total) pairs = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<2>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2>, tmA, tmW, args));
+  return USF_OK;
+}
+
+// Debug: enable tracing for subsequent launches (on != 0) / read back the records of the LAST launch.
+int tc_trace_ctl(int on, unsigned long long* out, int max_records) {
+  g_trace_on = on != 0;
+  if (out != nullptr) {
+    const size_t n = (size_t)2 * 3 * TC_TRACE_CAP * 2;
+    const size_t want = (size_t)max_records * 2 < n ? (size_t)max_records * 2 : n;
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * want);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyFromSymbol(g_tc_trace)");
+  }
   return USF_OK;
 }
 
