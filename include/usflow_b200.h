@@ -71,7 +71,10 @@ int usf_linear(const float* x, int64_t ldx, const float* W, int64_t ldw, const f
  * (x == y) is allowed.  bias may be NULL.  transpose != 0 solves with (L U)^T instead
  * (the input-gradient of the same layer).  nf4ad/flows.py:85 -> Flow.log_prob inverse direction. */
 int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, const float* U_raw, const float* bias,
-                 int transpose, float* x, int64_t ldx, int64_t B, int64_t D, usf_stream_t stream);
+                 int transpose, float* x, int64_t ldx, int64_t B, int64_t D,
+                 float* scratch /* usf_lu_solve_scratch_floats(D) floats, or NULL for the slow generic kernel */,
+                 usf_stream_t stream);
+int64_t usf_lu_solve_scratch_floats(int64_t D);
 
 /* Product of nvs Householder reflections H_v = I - 2 v v^T/|v|^2, applied in storage
  * order (reverse != 0: last first = the inverse map).  V:(nvs,D).  nf4ad/flows.py:90. */

@@ -292,9 +292,9 @@ int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, in
   if (M <= 0 || N <= 0) return USF_OK;
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
   int split = 1;
-  if (K >= 1024 && tiles < num_sms()) {
+  if (K >= 512 && tiles < num_sms()) {
     split = (int)((2 * num_sms()) / tiles);
-    const int64_t max_split = ceil_div(K, 256);
+    const int64_t max_split = ceil_div(K, 128);
     if (split > max_split) split = (int)max_split;
     if (split < 1) split = 1;
   }
@@ -668,20 +668,21 @@ __global__ void usf_scale_bwd_kernel(const float* __restrict__ dy, int64_t lddy,
   }
 }
 
-__global__ void usf_colsum_kernel(const float* __restrict__ a, int64_t lda, float* out, float coef, int accumulate,
-                                  int64_t B, int64_t N) {
+__global__ void usf_colsum_kernel(const float* __restrict__ a, int64_t lda, float* out, float coef, int64_t B,
+                                  int64_t N) {
+  // grid (N/32, row slices): each CTA reduces its row slice of 32 columns and adds ONE partial per column atomically
   const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
   float s = 0.f;
   if (c < N)
-    for (int64_t r = rl; r < B; r += 8) s += a[r * lda + c];
+    for (int64_t r = (int64_t)blockIdx.y * 8 + rl; r < B; r += (int64_t)gridDim.y * 8) s += a[r * lda + c];
   __shared__ float sm[8][33];
   sm[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && c < N) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
-    out[c] = (accumulate ? out[c] : 0.f) + coef * t;
+    atomicAdd(out + c, coef * t);
   }
 }
 
@@ -803,6 +804,19 @@ inline unsigned ew_grid(int64_t total, int threads = 256) {
 
 }  // namespace
 
+int launch_colsum(const float* a, int64_t lda, float* out, float coef, int accumulate, int64_t B, int64_t N,
+                  cudaStream_t stream) {
+  if (!accumulate) USF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, stream));
+  if (B <= 0) return USF_OK;
+  int gy = (int)ceil_div(B, 8 * 32);
+  if (gy < 1) gy = 1;
+  if (gy > 64) gy = 64;
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)gy);
+  usf_colsum_kernel<<<grid, 256, 0, stream>>>(a, lda, out, coef, B, N);
+  USF_LAUNCH_CHECK("usf_colsum_kernel");
+  return USF_OK;
+}
+
 int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_f32, int64_t ldy, int64_t B,
                         int64_t D, float* row_init, float init_value, cudaStream_t stream) {
   if (B <= 0) return USF_OK;
@@ -862,21 +876,29 @@ extern "C" int usf_linear(const float* x, int64_t ldx, const float* W, int64_t l
   return simt_gemm(x, ldx, 0, W, ldw, 0, B, N, K, ep, as_stream(stream));
 }
 
+extern "C" int64_t usf_lu_solve_scratch_floats(int64_t D) { return D > 0 ? trsm_fast_scratch_floats(D) : 0; }
+
 extern "C" int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, const float* U_raw, const float* bias,
-                            int transpose, float* x, int64_t ldx, int64_t B, int64_t D, usf_stream_t stream) {
+                            int transpose, float* x, int64_t ldx, int64_t B, int64_t D, float* scratch,
+                            usf_stream_t stream) {
   USF_CHECK_ARG(y && L_raw && U_raw && x && D > 0 && B >= 0, "usf_lu_solve: null pointer or bad size");
   cudaStream_t st = as_stream(stream);
+  const bool fast = scratch != nullptr && trsm_fast_supported(D);
+  auto solve = [&](const float* T, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr, const float* b) {
+    if (fast) return trsm_rows_fast(T, D, lower, unit, trans, rhs, ldr, b, x, ldx, B, scratch, st);
+    return trsm_rows(T, D, lower, unit, trans, rhs, ldr, b, x, ldx, B, st);
+  };
   int rc;
   if (!transpose) {
     // L z = y - b (unit lower), U x = z (upper)
-    rc = trsm_rows(L_raw, D, true, true, false, y, ldy, bias, x, ldx, B, st);
+    rc = solve(L_raw, true, true, false, y, ldy, bias);
     if (rc) return rc;
-    return trsm_rows(U_raw, D, false, false, false, x, ldx, nullptr, x, ldx, B, st);
+    return solve(U_raw, false, false, false, x, ldx, nullptr);
   }
   // (LU)^T x = y : U^T z = y (lower, non-unit), L^T x = z (upper, unit)
-  rc = trsm_rows(U_raw, D, true, false, true, y, ldy, bias, x, ldx, B, st);
+  rc = solve(U_raw, true, false, true, y, ldy, bias);
   if (rc) return rc;
-  return trsm_rows(L_raw, D, false, true, true, x, ldx, nullptr, x, ldx, B, st);
+  return solve(L_raw, false, true, true, x, ldx, nullptr);
 }
 
 extern "C" int usf_householder(const float* x, int64_t ldx, const float* V, int64_t nvs, int reverse, float* y,
@@ -960,8 +982,8 @@ extern "C" int usf_linear_bwd(const float* dy, int64_t lddy, const float* x, int
     if (rc) return rc;
   }
   if (db) {
-    usf_colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(g, ldg, db, 1.f, accumulate, B, N);
-    USF_LAUNCH_CHECK("usf_colsum_kernel");
+    rc = launch_colsum(g, ldg, db, 1.f, accumulate, B, N, st);
+    if (rc) return rc;
   }
   return USF_OK;
 }
@@ -1088,9 +1110,7 @@ extern "C" int usf_scale_bwd(const float* dy, int64_t lddy, const float* xy, int
 extern "C" int usf_colsum(const float* a, int64_t lda, float coef, int accumulate, float* out, int64_t B, int64_t N,
                           usf_stream_t stream) {
   USF_CHECK_ARG(a && out && N > 0 && B >= 0, "usf_colsum: bad arguments");
-  usf_colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, as_stream(stream)>>>(a, lda, out, coef, accumulate, B, N);
-  USF_LAUNCH_CHECK("usf_colsum_kernel");
-  return USF_OK;
+  return launch_colsum(a, lda, out, coef, accumulate, B, N, as_stream(stream));
 }
 
 extern "C" int usf_gemm(const float* A, int64_t lda, int a_trans, const float* Bm, int64_t ldb, int b_trans,

@@ -2,17 +2,22 @@
 //
 //   acc[m, n] = sum_k A[m, k] * W[n, k]        A: activations (M x K, bf16), W: packed weights (N x K, bf16)
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into a 4-stage smem ring
-//   warp 1   : MMA issuer    -- one lane issues tcgen05.mma (M=128, N=bn<=256, K=16) into TMEM;
-//                               tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-9: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM, 2 x 256 cols)
-//                               and apply the layer epilogue (bias / ReLU / coupling / base density)
+// Persistent, warp-specialised, 320 threads per CTA, one CTA per SM; by default two CTAs form a pair
+// (cluster of 2, tcgen05 cta_group::2) that owns a 256 x bn output tile:
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into an smem ring (as many stages as fit,
+//                               5-7); each CTA of a pair stages its own 128 rows of A and HALF of the W tile and
+//                               signals the leader's mbarrier
+//   warp 1   : MMA issuer    -- one lane of the leader issues tcgen05.mma (M=128*CG, N=bn<=256, K=16) into TMEM;
+//                               tcgen05.commit (multicast to both CTAs) releases smem stages / publishes the accumulator
+//   warps 2-9: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM, 2 x 256 cols) and apply
+//                               the layer epilogue (bias / ReLU / coupling / base density); per-tile column vectors
+//                               staged in smem, coupling inputs prefetched before the accumulator barrier
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 // Every mbarrier wait is bounded (g_tc_timeout flag) so a protocol bug cannot hang the GPU.
+// USF_TC_CTA_GROUP=1 selects the single-CTA variant; usf_debug_tc_trace records per-role timelines.
 //
-// Roofline: tensor-pipe bound for K >= 256 (4096 bf16 MAC/clk/SM); smem operand traffic per MMA is
-// (128 + bn) * 32 B per 128*bn/256... cycles, below the 128 B/clk smem port for bn >= 128.
+// Measured bounds (profiles/): the MMA side waits on operand delivery (~820 cycles per 64-wide k-block vs 416 of
+// MMA at N=208) and short-K GEMMs are epilogue-bound (TMEM drain + row-strided stores ~7k cycles per 128x256 tile).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -31,18 +36,11 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
 constexpr uint32_t TC_BAR_BYTES = 256;
 constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_EPI_BYTES = 2 * 3 * 256 * 4;  // per accumulator stage: bias / loc / inv_scale of the tile's columns
-constexpr uint32_t TC_STG_WARP_BYTES = 32 * 128;            // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled
-constexpr uint32_t TC_STG_BYTES = 8 * TC_STG_WARP_BYTES;    // coalescing transpose buffers of the 8 epilogue warps
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x bn tile; 2 = a CTA pair (cluster of 2) owns a
 // 256 x bn tile, each CTA staging its own 128 rows of A and HALF of the W tile, which halves the L2->SMEM weight
 // traffic per CTA (the measured bound of the 1-CTA kernel) and the SMEM operand reads per MMA.
-template <int CG>
-struct TcCfg {
-  static constexpr uint32_t B_BYTES = (TC_MAX_BN / CG) * TC_BK * 2;  // 32 KB / 16 KB
-  static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;      // 48 KB / 32 KB
-  static constexpr uint32_t FIXED_BYTES = TC_BAR_BYTES + TC_EPI_BYTES + TC_STG_BYTES + 1024;  // + alignment slack
-  static constexpr uint32_t SMEM_BYTES = 227 * 1024;   // request the whole carve-out; the ring takes what is left
-};
+constexpr uint32_t TC_FIXED_BYTES = TC_BAR_BYTES + TC_EPI_BYTES + 1024;  // barriers + per-tile column vectors + alignment slack
+constexpr uint32_t TC_SMEM_BYTES = 227 * 1024;                           // whole carve-out; the operand ring takes what is left
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr long long TC_WAIT_LIMIT_CYCLES = 400000000LL;  // ~0.2 s
 
@@ -204,112 +202,6 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
   }
 }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-// Warp-private staging tile: 32 rows x (up to) 8 pieces of 16 bytes, piece p of row r at r*128 + ((p ^ (r&7)) << 4)
-// (the XOR swizzle makes both the row-per-thread accesses and the 8-lanes-per-row accesses bank-conflict free).
-__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int r, int p) {
-  return base + (uint32_t)r * 128u + (uint32_t)((p ^ (r & 7)) << 4);
-}
-// Coalesced copy between the staging tile and global bf16 rows: 8 (ppr) consecutive lanes move one row's
-// contiguous pieces, so every warp instruction touches full 128-byte lines instead of 32 different rows.
-//   g: element pointer of (row0, col0); ld: row pitch in elements; nrows <= 32 valid rows; ppr = pieces per row;
-//   valid_elems = number of valid elements per row from col0 (partial last piece handled element-wise).
-// Fast path of stg_copy for a full 32-row x 64-column slab: no divisions, all eight 16-byte shared loads (or global
-// loads) of a lane issued before their stores so the latencies overlap.  `sp` = staging tile as uint4[32*8].
-template <bool TO_GLOBAL>
-__device__ __forceinline__ void stg_copy_full(uint4* sp, uint16_t* g, int64_t ld, int lane) {
-  const int pp = lane & 7, r0 = lane >> 3;   // 8 lanes per row, 4 rows per pass
-  uint4 q[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + r0;
-    if (TO_GLOBAL) q[it] = sp[r * 8 + (pp ^ (r & 7))];
-    else q[it] = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + pp * 8);
-  }
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + r0;
-    if (TO_GLOBAL) *reinterpret_cast<uint4*>(g + (int64_t)r * ld + pp * 8) = q[it];
-    else sp[r * 8 + (pp ^ (r & 7))] = q[it];
-  }
-}
-
-// Full 32 rows, PPR full 16-byte pieces per row (PPR compile-time => no runtime division), loads before stores.
-template <bool TO_GLOBAL, int PPR>
-__device__ __forceinline__ void stg_copy_rows(uint4* sp, uint16_t* g, int64_t ld, int lane) {
-  uint4 q[PPR];
-#pragma unroll
-  for (int it = 0; it < PPR; ++it) {
-    const int idx = it * 32 + lane, r = idx / PPR, pp = idx - r * PPR;
-    if (TO_GLOBAL) q[it] = sp[r * 8 + (pp ^ (r & 7))];
-    else q[it] = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + pp * 8);
-  }
-#pragma unroll
-  for (int it = 0; it < PPR; ++it) {
-    const int idx = it * 32 + lane, r = idx / PPR, pp = idx - r * PPR;
-    if (TO_GLOBAL) *reinterpret_cast<uint4*>(g + (int64_t)r * ld + pp * 8) = q[it];
-    else sp[r * 8 + (pp ^ (r & 7))] = q[it];
-  }
-}
-// Dispatch: full tiles take the unrolled constant-PPR path, ragged ones (row / column tails) the generic loop.
-template <bool TO_GLOBAL>
-__device__ __forceinline__ void stg_copy_any(uint32_t base, uint4* sp, uint16_t* g, int64_t ld, int nrows, int ppr,
-                                             int valid_elems, int lane);
-
-template <bool TO_GLOBAL>
-__device__ __forceinline__ void stg_copy(uint32_t base, uint16_t* g, int64_t ld, int nrows, int ppr, int valid_elems, int lane) {
-  const int total = 32 * ppr;
-  for (int idx = lane; idx < total; idx += 32) {
-    const int r = idx / ppr, pp = idx - r * ppr;
-    if (r >= nrows) continue;
-    const int e0 = pp * 8;
-    if (e0 >= valid_elems) continue;
-    uint16_t* gp = g + (int64_t)r * ld + e0;
-    const uint32_t sa = stg_addr(base, r, pp);
-    if (e0 + 8 <= valid_elems) {
-      if (TO_GLOBAL) *reinterpret_cast<uint4*>(gp) = ld_shared_v4(sa);
-      else st_shared_v4(sa, *reinterpret_cast<const uint4*>(gp));
-    } else {
-      for (int e = 0; e0 + e < valid_elems; ++e) {
-        if (TO_GLOBAL) {
-          uint16_t h;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sa + 2 * e) : "memory");
-          gp[e] = h;
-        } else {
-          const uint16_t h = gp[e];
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa + 2 * e), "h"(h) : "memory");
-        }
-      }
-    }
-  }
-}
-
-template <bool TO_GLOBAL>
-__device__ __forceinline__ void stg_copy_any(uint32_t base, uint4* sp, uint16_t* g, int64_t ld, int nrows, int ppr,
-                                             int valid_elems, int lane) {
-  if (nrows == 32 && valid_elems == ppr * 8) {
-    switch (ppr) {
-      case 8: stg_copy_full<TO_GLOBAL>(sp, g, ld, lane); return;
-      case 7: stg_copy_rows<TO_GLOBAL, 7>(sp, g, ld, lane); return;
-      case 6: stg_copy_rows<TO_GLOBAL, 6>(sp, g, ld, lane); return;
-      case 5: stg_copy_rows<TO_GLOBAL, 5>(sp, g, ld, lane); return;
-      case 4: stg_copy_rows<TO_GLOBAL, 4>(sp, g, ld, lane); return;
-      case 3: stg_copy_rows<TO_GLOBAL, 3>(sp, g, ld, lane); return;
-      case 2: stg_copy_rows<TO_GLOBAL, 2>(sp, g, ld, lane); return;
-      case 1: stg_copy_rows<TO_GLOBAL, 1>(sp, g, ld, lane); return;
-      default: break;
-    }
-  }
-  stg_copy<TO_GLOBAL>(base, g, ld, nrows, ppr, valid_elems, lane);
-}
-
 struct TcArgs {
   int64_t M, N, K;
   int bn;        // N-tile width (multiple of 16, <= 256)
@@ -318,8 +210,6 @@ struct TcArgs {
   int n_valid;   // valid output columns for fp32 stores / base density (<= N)
   int stages;                 // smem ring depth (<= TC_MAX_STAGES)
   uint32_t stage_bytes;       // bytes per stage (A tile + this CTA's W rows), multiple of 1024
-  int stage_out;              // 1: bf16 outputs / coupling I/O go through the warp-private smem staging tiles (coalesced
-                              // global access, costs smem bandwidth + 32 KB of ring); 0: direct row-per-thread access
   int dbg;                    // debug experiments (env USF_TC_DBG): 1 = copy-out without the global store, 2 = no copy-out
   unsigned long long* trace;  // debug: per-role timestamp records of CTA 0/1 (NULL = off), see usf_debug_tc_trace
   EpiParams ep;
@@ -339,7 +229,6 @@ __device__ __forceinline__ void tc_trace(unsigned long long* buf, int& n, int ti
 template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs args) {
-  using Cfg = TcCfg<CG>;
   // runtime ring geometry: a stage holds 128 rows of A and bn/CG rows of W (1 KB granularity), as many stages as fit
   const int TC_STAGES = args.stages;
   const uint32_t TC_STAGE_BYTES = args.stage_bytes;
@@ -792,8 +681,8 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   const int cg = tc_cta_group();
   static bool attr_set = false;
   if (!attr_set) {
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<1>::SMEM_BYTES));
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<2>::SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap tmA, tmW;
@@ -811,9 +700,8 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   args.m_tiles = (int)ceil_div(M, TC_BM * cg);
   args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
   args.ep = ep;
-  args.stage_out = 0;
   args.stage_bytes = TC_A_BYTES + (uint32_t)round_up((int64_t)(bn / cg) * TC_BK * 2, 1024);
-  args.stages = (int)((227 * 1024 - (TcCfg<1>::FIXED_BYTES - TC_STG_BYTES)) / args.stage_bytes);
+  args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES) / args.stage_bytes);
   if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
   {
     static int cap = -1;   // tuning knob: USF_TC_MAX_STAGES caps the ring depth
@@ -837,7 +725,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if (cg == 1) {
     int grid = num_sms();
     if (grid > total) grid = (int)total;
-    usf_tc_gemm_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(tmA, tmW, args);
+    usf_tc_gemm_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
     USF_LAUNCH_CHECK("usf_tc_gemm_kernel<1>");
     return USF_OK;
   }
@@ -846,7 +734,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<2>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

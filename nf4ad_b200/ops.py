@@ -55,8 +55,9 @@ def lu_solve(y, L_raw, U_raw, bias=None, transpose=False):
     B, D = y.shape
     x = torch.empty(B, D, device=y.device, dtype=torch.float32)
     b = f32c(bias) if bias is not None else None
-    check(lib().usf_lu_solve(ptr(y), ldy, ptr(L_raw), ptr(U_raw), ptr(b), int(transpose), ptr(x), D, B, D, stream()),
-          "usf_lu_solve")
+    scratch = torch.empty(lib().usf_lu_solve_scratch_floats(D), device=y.device, dtype=torch.float32)
+    check(lib().usf_lu_solve(ptr(y), ldy, ptr(L_raw), ptr(U_raw), ptr(b), int(transpose), ptr(x), D, B, D, ptr(scratch),
+                             stream()), "usf_lu_solve")
     return x
 
 
