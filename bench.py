@@ -286,10 +286,12 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        t_host = time.perf_counter()
         for i in range(args.steps):
             lp = scorer.score_local(x)
             if rank == 0 and i == args.steps // 2 and not sampler.sm:
                 sampler.sample_once()          # kernels are in flight: launches are asynchronous
+        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to enqueue one step
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -361,13 +363,14 @@ def main():
         peak, peak_src = measured_peak_tflops()
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
-        names = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base"}
+        names = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base",
+                 5: "fused_conditioner+coupling"}
         line = {
             "metric": "log_prob samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
-            "clocks": clocks,
+            "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,

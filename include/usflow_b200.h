@@ -15,7 +15,11 @@
  *   - all entry points return 0 on success, or a negative USF_E_* code;
  *     `usf_last_error()` gives the thread-local message.
  *   - every call only enqueues work on `stream` (no host sync), so the chain is
- *     CUDA-graph capturable; re-entrant across streams/threads.
+ *     CUDA-graph capturable; re-entrant across streams/threads.  The only state
+ *     the library keeps is per-thread caches of things derived from ADDRESSES and
+ *     shapes, never from buffer contents: encoded TMA tensor maps, and (for
+ *     usf_stack_run, unless USF_GRAPHS=0) instantiated CUDA graphs of launch
+ *     chains that were requested twice with identical arguments.
  *   - there is NO CPU fallback: without a CUDA device the compute entry points
  *     return USF_E_CUDA.
  *
@@ -231,7 +235,8 @@ int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch
  * (0 input pack, 1 affine GEMM, 2 conditioner hidden GEMM, 3 last conditioner GEMM + coupling
- * epilogue, 4 final GEMM + base density).  ms/tags must hold max_launches entries. */
+ * epilogue, 4 final GEMM + base density, 5 fused conditioner chain + coupling).  ms/tags must hold
+ * max_launches entries. */
 int usf_profile_begin(int max_launches);
 int usf_profile_end(float* ms, int* tags, int* n_out);
 

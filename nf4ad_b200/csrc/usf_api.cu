@@ -1,6 +1,7 @@
 // Host side of the C ABI: error plumbing, device probe, and the fused-stack runner that turns a packed
 // layer-descriptor array into one launch chain (Flow.log_prob / Flow.backward / Flow.forward).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "usf_common.cuh"
 
@@ -177,9 +178,9 @@ extern "C" size_t usf_stack_workspace_bytes(const usf_stack_desc* st, int64_t B,
   return p.total;
 }
 
-extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
-                             float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
-                             int precision, int* gpu_launches, usf_stream_t stream) {
+static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                           float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                           int precision, int* gpu_launches, usf_stream_t stream) {
   USF_CHECK_ARG(st != nullptr && x != nullptr && B >= 0, "usf_stack_run: bad arguments");
   USF_CHECK_ARG(!(out_logprob && (st->base_kind < 0 || !st->inverse)),
                 "usf_stack_run: log_prob needs the inverse direction and a base distribution");
@@ -250,9 +251,42 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
         cur ^= 1;
       }
       // (2) conditioner MLP on the a-part, last layer fused with the coupling update of the b-part
+      bool fused = false;
+      if (bf16 && blk.n_mlp >= 2) {
+        int Ns[USF_MAX_MLP], Ks[USF_MAX_MLP], ldws[USF_MAX_MLP];
+        const uint16_t* Wbs[USF_MAX_MLP];
+        const float* biases[USF_MAX_MLP];
+        bool have = true;
+        for (int l = 0; l < blk.n_mlp; ++l) {
+          Ns[l] = blk.mlp[l].N; Ks[l] = blk.mlp[l].K; ldws[l] = blk.mlp[l].ldw;
+          Wbs[l] = blk.mlp[l].Wb; biases[l] = blk.mlp[l].bias;
+          have = have && Wbs[l] != nullptr && biases[l] != nullptr;
+        }
+        if (have && blk.n_mlp <= 4 && tc_mlp_supported(blk.n_mlp, Ns, Ks, blk.Da)) {
+          // ONE kernel: the whole conditioner chain with hidden activations resident in shared memory + coupling
+          EpiParams ep{};
+          if (blk.affine) ep.mode = st->inverse ? EPI_COUPLING_INV : EPI_COUPLING_FWD;
+          else ep.mode = st->inverse ? EPI_ADD_INV : EPI_ADD_FWD;
+          ep.ub = act[cur] + (size_t)blk.b_off * esz;
+          ep.ldub = p.ld_act;
+          ep.ub_bf16 = 1;
+          ep.Db = blk.Db;
+          ep.C = blk.C;
+          ep.clamp = blk.clamp;
+          ep.row_acc = row_acc;
+          {
+            ProfScope ps(s, 5);
+            rc = tc_mlp_coupling(reinterpret_cast<const uint16_t*>(act[cur]), p.ld_act, rows, blk.n_mlp, Wbs, ldws, biases,
+                                 Ns, Ks, blk.affine ? 2 * blk.C : blk.C, ep, s);
+          }
+          if (rc) return rc;
+          ++launches;
+          fused = true;
+        }
+      }
       const void* in = act[cur];
       int64_t ld_in = p.ld_act;
-      for (int l = 0; l < blk.n_mlp; ++l) {
+      for (int l = 0; l < blk.n_mlp && !fused; ++l) {
         const usf_linear_desc& L = blk.mlp[l];
         EpiParams ep{};
         ep.bias = L.bias;
@@ -313,6 +347,115 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
       ++launches;
     }
   }
+  if (gpu_launches) *gpu_launches = launches;
+  return USF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of the launch chain.  A scoring loop calls usf_stack_run with the SAME descriptors, buffers and
+// row count step after step; the second identical call captures the chain (on a private capture stream) into a
+// graph and later calls replay it with one cudaGraphLaunch, which takes the per-launch host cost (cluster launches
+// with 227 KB of smem, tensor-map parameters) off the critical path.  The cache is per thread, bounded, keyed by a
+// hash of every descriptor byte and pointer, and can be disabled with USF_GRAPHS=0.  A graph only bakes in
+// addresses, shapes and scalars, never buffer contents, so re-using it after the weights were updated in place
+// (same storage) is valid.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct GraphEntry {
+  uint64_t key = 0;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  int seen = 0;
+  uint64_t stamp = 0;
+};
+constexpr int kGraphSlots = 16;
+thread_local GraphEntry g_graphs[kGraphSlots];
+thread_local cudaStream_t g_capture_stream = nullptr;
+thread_local uint64_t g_graph_clock = 0;
+
+inline uint64_t fnv(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+bool graphs_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("USF_GRAPHS"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+}  // namespace
+
+extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                             float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                             int precision, int* gpu_launches, usf_stream_t stream) {
+  if (st == nullptr || !graphs_enabled() || g_prof.on || B <= 0 || st->n_blocks < 0 ||
+      (st->n_blocks > 0 && st->blocks == nullptr))
+    return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                           gpu_launches, stream);
+  uint64_t key = 1469598103934665603ull;
+  key = fnv(key, st, sizeof(*st));
+  if (st->n_blocks > 0) key = fnv(key, st->blocks, sizeof(usf_block_desc) * (size_t)st->n_blocks);
+  const uint64_t extra[9] = {(uint64_t)(uintptr_t)x, (uint64_t)ldx, (uint64_t)B, (uint64_t)(uintptr_t)out_logprob,
+                             (uint64_t)(uintptr_t)out_y, (uint64_t)ldy, (uint64_t)(uintptr_t)out_ladj,
+                             (uint64_t)(uintptr_t)workspace, (uint64_t)workspace_bytes * 4u + (uint64_t)precision};
+  key = fnv(key, extra, sizeof(extra));
+  if (key == 0) key = 1;
+  GraphEntry* slot = nullptr;
+  GraphEntry* victim = &g_graphs[0];
+  for (int i = 0; i < kGraphSlots; ++i) {
+    if (g_graphs[i].key == key) { slot = &g_graphs[i]; break; }
+    if (g_graphs[i].stamp < victim->stamp) victim = &g_graphs[i];
+  }
+  cudaStream_t s = as_stream(stream);
+  if (slot != nullptr && slot->exec != nullptr) {
+    slot->stamp = ++g_graph_clock;
+    USF_CUDA(cudaGraphLaunch(slot->exec, s));
+    if (gpu_launches) *gpu_launches = slot->launches;
+    return USF_OK;
+  }
+  if (slot == nullptr) {   // first sighting: run eagerly and remember the key
+    if (victim->exec != nullptr) cudaGraphExecDestroy(victim->exec);
+    *victim = GraphEntry();
+    victim->key = key;
+    victim->seen = 1;
+    victim->stamp = ++g_graph_clock;
+    return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                           gpu_launches, stream);
+  }
+  // second identical call: capture the chain, instantiate, replay
+  slot->stamp = ++g_graph_clock;
+  if (g_capture_stream == nullptr &&
+      cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                           gpu_launches, stream);
+  }
+  int launches = 0;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                           gpu_launches, stream);
+  }
+  const int rc = stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                                 &launches, g_capture_stream);
+  const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc != USF_OK || ce != cudaSuccess || graph == nullptr ||
+      cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    slot->key = 0;   // do not try again with this key
+    return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                           gpu_launches, stream);
+  }
+  cudaGraphDestroy(graph);
+  slot->exec = exec;
+  slot->launches = launches;
+  USF_CUDA(cudaGraphLaunch(exec, s));
   if (gpu_launches) *gpu_launches = launches;
   return USF_OK;
 }

@@ -88,6 +88,10 @@ int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, in
 int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int64_t M, int64_t N,
             int64_t K, int bn, const EpiParams& ep, cudaStream_t stream);
 int tc_pick_bn(int64_t N);
+bool tc_mlp_supported(int n_layers, const int* N, const int* K, int Da);
+int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, const uint16_t* const* Wb, const int* ldw,
+                    const float* const* bias, const int* N, const int* K, int bn_last, const EpiParams& ep,
+                    cudaStream_t stream);
 extern const char* const kTcGemmKernelName;
 extern const char* const kSimtGemmKernelName;
 int64_t trsm_fast_scratch_floats(int64_t D);

@@ -601,6 +601,319 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ================================================================================================
+// Fused conditioner chain + coupling (CTA pairs, cta_group::2):   per 256-row tile, ONE kernel runs
+//   h_1 = relu(u_a W_1^T + b_1), ..., h_{L-1} = relu(h_{L-2} W_{L-1}^T + b_{L-1}),  (s|t) = h_{L-1} W_L^T + b_L,
+// followed by the coupling update of the transformed columns and the per-row log-det.  Hidden activations never
+// leave the SM: each hidden epilogue writes its bf16 tile straight into shared memory in the K-major / 128B-swizzled
+// layout the next layer's tcgen05.mma reads as operand A (in place: layer l+1's output overwrites layer l's, which is
+// safe because its epilogue only starts after every MMA that read the old contents has completed).  Weights stream
+// from L2 through the same TMA ring as the plain GEMM (each CTA stages half of every W tile); only layer 1 also
+// streams A (the conditioning columns of the activation).  Replaces L launches + 2(L-1) HBM round trips of h.
+// ================================================================================================
+constexpr int MLP_MAX_LAYERS = 4;
+constexpr int MLP_STAGES = 4;
+constexpr uint32_t MLP_STAGE_BYTES = 2 * TC_A_BYTES;          // [A 16 KB | W half-tile <= 128 rows 16 KB]
+constexpr uint32_t MLP_H_BYTES = 4 * TC_A_BYTES;              // 128 rows x 256 cols bf16 = 4 k-blocks of 16 KB
+constexpr uint32_t MLP_SMEM_BYTES = MLP_STAGES * MLP_STAGE_BYTES + MLP_H_BYTES + TC_BAR_BYTES + TC_EPI_BYTES + 1024;
+
+struct MlpMaps {
+  CUtensorMap w[MLP_MAX_LAYERS];
+};
+
+struct MlpArgs {
+  int64_t M;
+  int m_tiles;                   // 256-row pair tiles
+  int L;                         // layers: L-1 hidden + the coupling layer
+  int K[MLP_MAX_LAYERS];         // valid K of layer l
+  int N[MLP_MAX_LAYERS];         // packed N of layer l (multiple of 16)
+  int bn[MLP_MAX_LAYERS];        // N-tile width of layer l (hidden: = N <= 256)
+  int ntile[MLP_MAX_LAYERS];
+  const float* bias[MLP_MAX_LAYERS];
+  EpiParams ep;                  // coupling epilogue of the last layer
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ MlpMaps maps, MlpArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t h_base = smem_base + MLP_STAGES * MLP_STAGE_BYTES;   // hidden activation tile (operand A of layers >= 2)
+  const uint32_t bar_base = h_base + MLP_H_BYTES;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), num_units = (int)(gridDim.x >> 1);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MLP_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MLP_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MLP_STAGES + 2 + a); };
+  const uint32_t hready_bar = bar_base + 8u * (2 * MLP_STAGES + 4);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * MLP_STAGES + 5);
+  const uint32_t epi_base = bar_base + TC_BAR_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < MLP_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 16);
+    }
+    mbar_init(hready_bar, 16);   // 8 epilogue warps of each CTA of the pair
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    for (int l = 0; l < args.L; ++l)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[l])) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  const int L = args.L;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int t = unit; t < args.m_tiles && ok; t += num_units) {
+        const int a_row = (t * 2 + (int)cta_rank) * TC_BM;
+        for (int l = 0; l < L && ok; ++l) {
+          const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
+          const uint32_t tx = 2u * ((l == 0 ? TC_A_BYTES : 0u) + (uint32_t)(args.bn[l] >> 1) * TC_BK * 2);
+          for (int nt = 0; nt < args.ntile[l] && ok; ++nt) {
+            int width = args.N[l] - nt * args.bn[l];
+            if (width > args.bn[l]) width = args.bn[l];
+            const int w_row = nt * args.bn[l] + (int)cta_rank * (width >> 1);
+            for (int kb = 0; kb < nkb; ++kb) {
+              ok = mbar_wait(empty_bar(s), ph ^ 1u);
+              if (!ok) break;
+              const uint32_t dst = smem_base + s * MLP_STAGE_BYTES;
+              if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx);
+              else mbar_arrive_cluster(full_bar(s), 0);
+              if (l == 0) tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+              tma_load_2d_2sm(dst + TC_A_BYTES, &maps.w[l], full_bar(s), kb * TC_BK, w_row);
+              if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && cta_rank == 0) {
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0, hph = 0;
+      bool ok = true;
+      for (int t = unit; t < args.m_tiles && ok; t += num_units) {
+        for (int l = 0; l < L && ok; ++l) {
+          const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
+          for (int nt = 0; nt < args.ntile[l] && ok; ++nt) {
+            int width = args.N[l] - nt * args.bn[l];
+            if (width > args.bn[l]) width = args.bn[l];
+            const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * 2);
+            ok = mbar_wait(tempty_bar(a), aph ^ 1u);
+            if (!ok) break;
+            if (l > 0 && nt == 0) {      // operand A = the hidden tile written by the previous layer's epilogue (both CTAs)
+              ok = mbar_wait(hready_bar, hph);
+              if (!ok) break;
+              hph ^= 1u;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+              ok = mbar_wait(full_bar(s), ph);
+              if (!ok) break;
+              tc_fence_after();
+              const uint32_t slot = smem_base + s * MLP_STAGE_BYTES;
+              const uint32_t a_addr = l == 0 ? slot : h_base + (uint32_t)kb * TC_A_BYTES;
+              const uint32_t b_addr = slot + TC_A_BYTES;
+              int krem = args.K[l] - kb * TC_BK;
+              if (krem > TC_BK) krem = TC_BK;
+              const int ksteps = (krem + TC_UMMA_K - 1) / TC_UMMA_K;
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16_2sm(d_tmem, make_smem_desc(a_addr + k * TC_UMMA_K * 2), make_smem_desc(b_addr + k * TC_UMMA_K * 2),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit_2sm(empty_bar(s));
+              if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
+            }
+            if (!ok) break;
+            umma_commit_2sm(tfull_bar(a));
+            a ^= 1;
+            if (a == 0) aph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2..9), both CTAs
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;
+    const EpiParams& ep = args.ep;
+    float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));
+    uint4* hp = reinterpret_cast<uint4*>(smem_raw + (h_base - smem_u32(smem_raw)));   // H as uint4[kb][128 rows][8 pieces]
+    const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+    const int rloc = lane_grp * 32 + lane;           // row within this CTA's 128-row tile
+    int a = 0;
+    uint32_t aph = 0;
+    for (int t = unit; t < args.m_tiles; t += num_units) {
+      const int64_t row = (int64_t)(t * 2 + (int)cta_rank) * TC_BM + rloc;
+      const bool rvalid = row < args.M;
+      for (int l = 0; l < L; ++l) {
+        const bool last = l == L - 1;
+        for (int nt = 0; nt < args.ntile[l]; ++nt) {
+          const int n0 = nt * args.bn[l];
+          int width = args.N[l] - n0;
+          if (width > args.bn[l]) width = args.bn[l];
+          float* ev = epi + a * 768;
+          ev[et] = (et < width) ? args.bias[l][n0 + et] : 0.f;
+          uint4 uq[8];
+          if (last && is_cpl) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = (2 * i + half) * 16;
+              const int coord0 = nt * ep.C + c;
+              if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
+                const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0);
+                uq[2 * i] = up[0];
+                uq[2 * i + 1] = up[1];
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const bool ok = mbar_wait(tfull_bar(a), aph);
+          if (ok) {
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+            if (!last) {
+              // hidden layer: bias + ReLU -> bf16 -> operand-A layout of the next layer (in place in shared memory)
+              for (int c = half * 16; c < width; c += 32) {
+                float v[16];
+                tmem_ld16(t_base + c, v);
+                tmem_ld_wait();
+                const float4* bv = reinterpret_cast<const float4*>(ev + c);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 b4 = bv[j4];
+                  v[4 * j4] = fmaxf(v[4 * j4] + b4.x, 0.f);
+                  v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b4.y, 0.f);
+                  v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b4.z, 0.f);
+                  v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b4.w, 0.f);
+                }
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+                const int kb = c >> 6, p = (c & 63) >> 3;    // k-block of 64 columns, 16-byte piece within the 128-byte row
+                uint4* rowp = hp + (size_t)kb * (TC_A_BYTES / 16) + rloc * 8;
+                rowp[p ^ (rloc & 7)] = q0;
+                rowp[(p + 1) ^ (rloc & 7)] = q1;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+            } else if (is_cpl) {
+              const int C = ep.C;
+              float lsum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int c = (2 * i + half) * 16;
+                if (c < C) {
+                  float sv[16], tv[16];
+                  tmem_ld16(t_base + c, sv);
+                  tmem_ld16(t_base + C + c, tv);
+                  tmem_ld_wait();
+                  const int coord0 = nt * C + c;
+                  if (rvalid && coord0 < ep.Db) {
+                    uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+                    float u[16];
+                    const bool full = coord0 + 16 <= ep.Db;
+                    if (full) {
+                      unpack_bf16x8(uq[2 * i], u);
+                      unpack_bf16x8(uq[2 * i + 1], u + 8);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j)
+                        u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
+                    }
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float s = sv[j] + ev[c + j];
+                      const float tt = tv[j] + ev[C + c + j];
+                      const float ls = ep.clamp * fast_tanh(s);
+                      y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
+                      if (coord0 + j < ep.Db) lsum += ls;
+                    }
+                    if (full) {
+                      uint4 q0, q1;
+                      q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
+                      q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
+                      q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
+                      q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
+                      reinterpret_cast<uint4*>(up)[0] = q0;
+                      reinterpret_cast<uint4*>(up)[1] = q1;
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j)
+                        if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
+                    }
+                  }
+                }
+              }
+              if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
+            } else {   // additive coupling: tile = [t(C)]
+              const int C = ep.C;
+              for (int c = half * 16; c < C; c += 32) {
+                float tv[16];
+                tmem_ld16(t_base + c, tv);
+                tmem_ld_wait();
+                const int coord0 = nt * C + c;
+                if (rvalid && coord0 < ep.Db) {
+                  uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    if (coord0 + j < ep.Db) {
+                      const float u = __uint_as_float((uint32_t)up[j] << 16);
+                      const float tt = tv[j] + ev[c + j];
+                      up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
+                    }
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (cta_rank == 0) mbar_arrive(tempty_bar(a));
+              else mbar_arrive_cluster(tempty_bar(a), 0);
+              if (!last) {            // this warp's part of the hidden tile is in place (in this CTA's smem)
+                if (cta_rank == 0) mbar_arrive(hready_bar);
+                else mbar_arrive_cluster(hready_bar, 0);
+              }
+            }
+          }
+          a ^= 1;
+          if (a == 0) aph ^= 1u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -620,7 +933,33 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major tensor (rows x cols, leading dimension ld elements), box = box_rows x 64 cols, 128B swizzle.
+// Encoding costs a driver call (~several us); a launch chain re-uses the same few (pointer, shape) combinations every
+// step (packed weights, workspace slices), so encoded maps are memoised per thread.
+struct TmapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int TMAP_CACHE_SLOTS = 256;
+
 int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  static thread_local TmapSlot cache[TMAP_CACHE_SLOTS];
+  const TmapKey key{base, rows, cols, ld, box_rows};
+  const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 4) * 0x9E3779B97F4A7C15ull ^ (uint64_t)rows * 0xC2B2AE3D27D4EB4Full ^
+                     (uint64_t)cols * 0x165667B19E3779F9ull ^ (uint64_t)ld * 31 ^ (uint64_t)box_rows;
+  TmapSlot& slot = cache[(h >> 20) % TMAP_CACHE_SLOTS];
+  if (slot.used && slot.key == key) {
+    *tm = slot.map;
+    return USF_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -638,6 +977,9 @@ int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols,
               (const void*)base, (long long)rows, (long long)cols, (long long)ld, box_rows);
     return USF_E_CUDA;
   }
+  slot.key = key;
+  slot.map = *tm;
+  slot.used = true;
   return USF_OK;
 }
 
@@ -744,6 +1086,75 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2>, tmA, tmW, args));
+  return USF_OK;
+}
+
+// Fused conditioner chain + coupling (see usf_tc_mlp_coupling_kernel).  Returns USF_E_UNSUPPORTED when the shapes do
+// not fit the fused kernel (the caller then runs the layer-by-layer chain).
+bool tc_mlp_supported(int n_layers, const int* N, const int* K, int Da) {
+  if (tc_cta_group() != 2 || n_layers < 2 || n_layers > MLP_MAX_LAYERS) return false;
+  if (K[0] != Da || Da <= 0) return false;
+  for (int l = 0; l + 1 < n_layers; ++l)
+    if (N[l] > 256 || (N[l] % 16) != 0 || K[l + 1] > N[l]) return false;
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("USF_TC_FUSED_MLP"); off = (e != nullptr && e[0] == '0') ? 1 : 0; }
+  return off == 0;
+}
+
+int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, const uint16_t* const* Wb, const int* ldw,
+                    const float* const* bias, const int* N, const int* K, int bn_last, const EpiParams& ep,
+                    cudaStream_t stream) {
+  if (M <= 0) return USF_OK;
+  USF_CHECK_ARG(tc_mlp_supported(n_layers, N, K, K[0]), "tc_mlp_coupling: unsupported shape");
+  USF_CHECK_ARG((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "tc_mlp_coupling: bad activation layout");
+  static bool attr_set = false;
+  if (!attr_set) {
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_mlp_coupling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    attr_set = true;
+  }
+  MlpArgs args;
+  memset(&args, 0, sizeof(args));
+  MlpMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  CUtensorMap tmA;
+  int rc = make_tmap(&tmA, A, M, K[0], lda, TC_BM);
+  if (rc) return rc;
+  args.M = M;
+  args.m_tiles = (int)ceil_div(M, 2 * TC_BM);
+  args.L = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    const bool last = l == n_layers - 1;
+    args.K[l] = K[l];
+    args.N[l] = N[l];
+    args.bn[l] = last ? bn_last : N[l];
+    args.ntile[l] = (int)ceil_div(N[l], args.bn[l]);
+    args.bias[l] = bias[l];
+    USF_CHECK_ARG((ldw[l] % 8) == 0 && (N[l] % 16) == 0 && (args.bn[l] % 16) == 0 && args.bn[l] <= TC_MAX_BN,
+                  "tc_mlp_coupling: bad layer %d", l);
+    rc = make_tmap(&maps.w[l], Wb[l], N[l], K[l], ldw[l], args.bn[l] / 2);
+    if (rc) return rc;
+  }
+  if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD)
+    USF_CHECK_ARG(bn_last == 2 * ep.C && (ep.C % 16) == 0 && (N[n_layers - 1] % bn_last) == 0, "tc_mlp_coupling: bad coupling tile");
+  else
+    USF_CHECK_ARG((ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) && bn_last == ep.C && (N[n_layers - 1] % bn_last) == 0,
+                  "tc_mlp_coupling: bad additive tile");
+  args.ep = ep;
+  int64_t pairs = num_sms() / 2;
+  if (pairs > args.m_tiles) pairs = args.m_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = MLP_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel, tmA, maps, args));
   return USF_OK;
 }
 

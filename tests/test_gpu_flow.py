@@ -322,3 +322,42 @@ def test_foreign_coupling_class_is_recognised(O, P):
     flow.train()
     lp2 = flow.log_prob(x.cuda())          # autograd (layer-wise) path
     assert lp2.requires_grad and rel(lp2, ref) < FP32_TOL
+
+
+def test_graph_replay_matches_eager_and_tracks_weight_updates(O, P):
+    """usf_stack_run replays a captured CUDA graph from the third identical call on.  Replays must be
+    bit-identical to the eager chain, and an in-place weight update (new packed weights at new addresses or
+    the same ones) must be reflected, never a stale result."""
+    fo, fp = _pair(O, P, "NonUSFlow", 64, 3, ("mlp", [128, 128]), "normal", 0.25, seed=9, affine_conjugation=True)
+    x = torch.randn(1000, 64).cuda()
+    for precision in ("fp32", "bf16"):
+        fp.precision = precision
+        with torch.no_grad():
+            cs = fp._stack(True, x.device)
+            outs = []
+            lp = torch.empty(1000, device="cuda")
+            import ctypes
+            from nf4ad_b200._lib import lib, ptr, stream, check
+            nbytes = lib().usf_stack_workspace_bytes(ctypes.byref(cs.desc), 1000, cs.precision)
+            ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+            n = ctypes.c_int(0)
+            for _ in range(5):      # same descriptors, same buffers: eager, capture, replay, replay, replay
+                check(lib().usf_stack_run(ctypes.byref(cs.desc), ptr(x), 64, 1000, ptr(lp), None, 64, None, ptr(ws), nbytes,
+                                          cs.precision, ctypes.byref(n), stream()))
+                torch.cuda.synchronize()
+                outs.append(lp.clone())
+                assert n.value > 0
+            if precision == "fp32":
+                for o in outs[1:]:
+                    assert rel(o, outs[0]) < 1e-6      # atomics make the row sums order-dependent in the last ulp
+            ref = fo.log_prob(x.cpu().double())
+            assert rel(outs[-1], ref) < (FP32_TOL if precision == "fp32" else 5e-2)
+            # change a weight in place: the flow must follow it (no stale packed weights / stale graph)
+            before = fp.log_prob(x).clone()
+            fp.layers[-1].scale.mul_(1.5)
+            fo.layers[-1].scale.mul_(1.5)
+            after = fp.log_prob(x)
+            assert float((after - before).abs().mean()) > 1.0
+            assert rel(after, fo.log_prob(x.cpu().double())) < (FP32_TOL if precision == "fp32" else 5e-2)
+            fp.layers[-1].scale.div_(1.5)
+            fo.layers[-1].scale.div_(1.5)
