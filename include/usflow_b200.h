@@ -197,7 +197,7 @@ typedef struct {
 
 typedef struct {
   usf_linear_desc G;   /* dense affine map applied BEFORE the coupling: u = G x + g; output columns are
-                          [a-part (Da) | zero pad | b-part (Db) starting at column b_off] */
+                          [a-part (Da) | zero pad | b-part (Db) starting at column b_off (multiple of 16)] */
   int32_t b_off;       /* first column of the transformed (b) coordinates in the activation row */
   int32_t n_mlp;       /* conditioner Linear layers; all but the last are followed by ReLU */
   usf_linear_desc mlp[USF_MAX_MLP]; /* first: K = Da (conditioning coords); last: rows packed per tile [s(C)|t(C)] or [t(C)] */

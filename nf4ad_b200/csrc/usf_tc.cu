@@ -202,6 +202,21 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
   }
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one LSU request per thread for a 32-byte row segment.  The
+// epilogues are row-per-thread (TMEM lane = row), so every request hits a different row and the LSU request rate,
+// not bytes, is their bound: halving the request count matters.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& lo, uint4& hi) {
+  uint64_t a, b, c, d;
+  asm volatile("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+  lo = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+  hi = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& lo, const uint4& hi) {
+  const uint64_t a = (uint64_t)lo.x | ((uint64_t)lo.y << 32), b = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+  const uint64_t c = (uint64_t)hi.x | ((uint64_t)hi.y << 32), d = (uint64_t)hi.z | ((uint64_t)hi.w << 32);
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
 struct TcArgs {
   int64_t M, N, K;
   int bn;        // N-tile width (multiple of 16, <= 256)
@@ -412,9 +427,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int c = (2 * i + half) * 16;
           const int coord0 = nt * ep.C + c;
           if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
-            const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0);
-            uq[2 * i] = up[0];
-            uq[2 * i + 1] = up[1];
+            ld_global_256(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0, uq[2 * i], uq[2 * i + 1]);
           }
         }
       }
@@ -450,9 +463,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c);
-              dst[0] = q0;
-              dst[1] = q1;
+              st_global_256(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c, q0, q1);
             }
           }
         } else if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
@@ -527,8 +538,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
                   q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
                   q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-                  reinterpret_cast<uint4*>(up)[0] = q0;
-                  reinterpret_cast<uint4*>(up)[1] = q1;
+                  st_global_256(up, q0, q1);
                 } else {
 #pragma unroll
                   for (int j = 0; j < 16; ++j)
@@ -631,6 +641,7 @@ struct MlpArgs {
   int ntile[MLP_MAX_LAYERS];
   const float* bias[MLP_MAX_LAYERS];
   EpiParams ep;                  // coupling epilogue of the last layer
+  unsigned long long* trace;     // debug timeline (see usf_debug_tc_trace); events use tile = (m_tile << 4) | gemm index
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -675,6 +686,12 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
   const int L = args.L;
+  int trn = 0;
+  unsigned long long* trb = nullptr;
+  if (args.trace != nullptr && blockIdx.x < 2) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    if (warp <= 2 && lane == 0) trb = args.trace + (size_t)(blockIdx.x * 3 + role) * TC_TRACE_CAP * 2;
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -718,13 +735,17 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             int width = args.N[l] - nt * args.bn[l];
             if (width > args.bn[l]) width = args.bn[l];
             const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * 2);
+            const int gi = (t << 4) | (l * 4 + nt);
+            tc_trace(trb, trn, gi, 0);
             ok = mbar_wait(tempty_bar(a), aph ^ 1u);
             if (!ok) break;
+            tc_trace(trb, trn, gi, 1);
             if (l > 0 && nt == 0) {      // operand A = the hidden tile written by the previous layer's epilogue (both CTAs)
               ok = mbar_wait(hready_bar, hph);
               if (!ok) break;
               hph ^= 1u;
             }
+            tc_trace(trb, trn, gi, 2);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -745,6 +766,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             }
             if (!ok) break;
             umma_commit_2sm(tfull_bar(a));
+            tc_trace(trb, trn, gi, 3);
             a ^= 1;
             if (a == 0) aph ^= 1u;
           }
@@ -781,14 +803,15 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
               const int c = (2 * i + half) * 16;
               const int coord0 = nt * ep.C + c;
               if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
-                const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0);
-                uq[2 * i] = up[0];
-                uq[2 * i + 1] = up[1];
+                ld_global_256(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0, uq[2 * i], uq[2 * i + 1]);
               }
             }
           }
+          const int gi = (t << 4) | (l * 4 + nt);
+          tc_trace(trb, trn, gi, 0);
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const bool ok = mbar_wait(tfull_bar(a), aph);
+          tc_trace(trb, trn, gi, 2);
           if (ok) {
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
@@ -857,8 +880,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                       q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
                       q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
                       q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-                      reinterpret_cast<uint4*>(up)[0] = q0;
-                      reinterpret_cast<uint4*>(up)[1] = q1;
+                      st_global_256(up, q0, q1);
                     } else {
 #pragma unroll
                       for (int j = 0; j < 16; ++j)
@@ -898,6 +920,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 else mbar_arrive_cluster(hready_bar, 0);
               }
             }
+            tc_trace(trb, trn, gi, 3);
           }
           a ^= 1;
           if (a == 0) aph ^= 1u;
@@ -987,7 +1010,7 @@ int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols,
 
 const char* const kTcGemmKernelName = "usf_tc_gemm_kernel";
 
-bool g_trace_on = false;
+int g_trace_on = 0;   // 1: trace plain GEMM launches, 2: trace fused conditioner launches
 
 // CTAs per MMA: 2 (CTA pairs, tcgen05 cta_group::2) unless USF_TC_CTA_GROUP=1 selects the single-CTA kernel.
 int tc_cta_group() {
@@ -1016,7 +1039,11 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   USF_CHECK_ARG(bn >= 16 && bn <= TC_MAX_BN && (bn % 16) == 0 && (N % 16) == 0 && K > 0,
                 "tc_gemm: bad tile/shape (bn=%d N=%lld K=%lld)", bn, (long long)N, (long long)K);
   if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD)
-    USF_CHECK_ARG(bn == 2 * ep.C && (ep.C % 16) == 0 && (N % bn) == 0, "tc_gemm: coupling tile must be [s(C)|t(C)]");
+    USF_CHECK_ARG(bn == 2 * ep.C && (ep.C % 16) == 0 && (N % bn) == 0 && (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 &&
+                      (ep.ldub % 16) == 0,
+                  "tc_gemm: coupling tile must be [s(C)|t(C)] and the b-part 32-byte aligned");
+  if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16)
+    USF_CHECK_ARG((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0 && (ep.ldo % 16) == 0, "tc_gemm: bf16 output must be 32-byte aligned");
   if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD)
     USF_CHECK_ARG(bn == ep.C && (N % bn) == 0, "tc_gemm: additive tile must be [t(C)]");
 
@@ -1057,7 +1084,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
     args.dbg = dbg;
   }
   args.trace = nullptr;
-  if (g_trace_on) {
+  if (g_trace_on == 1) {
     void* p = nullptr;
     USF_CUDA(cudaGetSymbolAddress(&p, g_tc_trace));
     USF_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned long long) * 2 * 3 * TC_TRACE_CAP * 2, stream));
@@ -1135,11 +1162,20 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
     if (rc) return rc;
   }
   if (ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD)
-    USF_CHECK_ARG(bn_last == 2 * ep.C && (ep.C % 16) == 0 && (N[n_layers - 1] % bn_last) == 0, "tc_mlp_coupling: bad coupling tile");
+    USF_CHECK_ARG(bn_last == 2 * ep.C && (ep.C % 16) == 0 && (N[n_layers - 1] % bn_last) == 0 &&
+                      (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 && (ep.ldub % 16) == 0,
+                  "tc_mlp_coupling: bad coupling tile");
   else
     USF_CHECK_ARG((ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) && bn_last == ep.C && (N[n_layers - 1] % bn_last) == 0,
                   "tc_mlp_coupling: bad additive tile");
   args.ep = ep;
+  args.trace = nullptr;
+  if (g_trace_on == 2) {
+    void* tp = nullptr;
+    USF_CUDA(cudaGetSymbolAddress(&tp, g_tc_trace));
+    USF_CUDA(cudaMemsetAsync(tp, 0, sizeof(unsigned long long) * 2 * 3 * TC_TRACE_CAP * 2, stream));
+    args.trace = reinterpret_cast<unsigned long long*>(tp);
+  }
   int64_t pairs = num_sms() / 2;
   if (pairs > args.m_tiles) pairs = args.m_tiles;
   cudaLaunchConfig_t cfg{};
@@ -1160,7 +1196,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
 
 // Debug: enable tracing for subsequent launches (on != 0) / read back the records of the LAST launch.
 int tc_trace_ctl(int on, unsigned long long* out, int max_records) {
-  g_trace_on = on != 0;
+  g_trace_on = on;
   if (out != nullptr) {
     const size_t n = (size_t)2 * 3 * TC_TRACE_CAP * 2;
     const size_t want = (size_t)max_records * 2 < n ? (size_t)max_records * 2 : n;

@@ -107,7 +107,7 @@ class CompiledStack:
                 Da, Db = idx_a.numel(), idx_b.numel()
                 if Db == 0:
                     raise Unsupported("coupling transforms no coordinate")
-                b_off = _round_up(Da, 8)
+                b_off = _round_up(Da, 16)      # 32-byte aligned b-part: the epilogues use 256-bit row accesses
                 width = _round_up(b_off + Db, 16)
                 cols = torch.full((width,), -1, dtype=torch.int32, device=device)
                 cols[:Da] = idx_a
