@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--prewarm-s", type=float, default=1.0, help="untimed clock pre-warm (0 for profiler runs)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps (0 disables the leg)")
     ap.add_argument("--train-rows", type=int, default=4096, help="per-GPU training batch")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the batch-size sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +327,31 @@ def main():
         per_tag = {}
         for i in range(n.value):
             per_tag.setdefault(tags[i], []).append(ms[i])
+    # ---- batch-size sweep of the resident-input scoring call (1 024 ... 1 048 576 plus the reference's
+    # own small batches); rank 0 only, short, reported as extra information
+    sweep = {}
+    if rank == 0 and args.sweep:
+        with torch.no_grad():
+            for rows_s in (64, 1024, 16384, 262144):
+                for prec in ("bf16", "fp32"):
+                    if prec == "fp32" and rows_s > 16384:
+                        continue
+                    flow.precision = prec
+                    xs = torch.randn(rows_s, D, device=dev)
+                    for _ in range(5):
+                        flow.log_prob(xs)
+                    torch.cuda.synchronize()
+                    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 20 if rows_s <= 16384 else 5
+                    h0.record()
+                    for _ in range(reps):
+                        flow.log_prob(xs)
+                    h1.record()
+                    torch.cuda.synchronize()
+                    ms_s = h0.elapsed_time(h1) / reps
+                    sweep[f"{prec}_rows{rows_s}"] = {"ms_per_call": ms_s, "samples_per_s": rows_s / (ms_s * 1e-3)}
+            flow.precision = args.precision
+
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
     train_ms, train_B, train_steps = float("nan"), args.train_rows, args.train_steps
     if train_steps > 0:
@@ -385,6 +411,8 @@ def main():
                          "launch_ms_by_kind": {names[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},
                          "launches_by_kind": {names[k]: len(v) // steps_prof for k, v in sorted(per_tag.items())}},
         }
+        if sweep:
+            line["sweep"] = sweep
         if train_steps > 0:
             line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam, fp32 path)",
                              "value": train_B * world * train_steps / (train_ms * 1e-3), "unit": "samples/s",
