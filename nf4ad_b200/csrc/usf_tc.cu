@@ -183,12 +183,6 @@ __device__ __forceinline__ float fast_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float fast_exp(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-  return y;
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -215,6 +209,36 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4& lo, const ui
   const uint64_t a = (uint64_t)lo.x | ((uint64_t)lo.y << 32), b = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
   const uint64_t c = (uint64_t)hi.x | ((uint64_t)hi.y << 32), d = (uint64_t)hi.z | ((uint64_t)hi.w << 32);
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// One 16-coordinate chunk of the affine coupling update (row-per-thread):
+//   th = tanh(s + bs),  e = exp(+-clamp*th) = ex2(k1*th),  y = INV ? (u - (t + bt)) * e : u * e + (t + bt)
+// Biases come as float4 from the per-tile smem vectors; the log-det accumulates tanh only (scaled by clamp once per
+// row by the caller).  2 MUFU + ~7 ALU per coordinate.
+template <bool INV>
+__device__ __forceinline__ void coupling_chunk16(const float (&sv)[16], const float (&tv)[16], const float* bs,
+                                                 const float* bt, float k1, const float (&u)[16], float (&y)[16],
+                                                 float& th_sum, int nvalid) {
+  float b_s[16], b_t[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 a = reinterpret_cast<const float4*>(bs)[j4];
+    const float4 b = reinterpret_cast<const float4*>(bt)[j4];
+    b_s[4 * j4] = a.x; b_s[4 * j4 + 1] = a.y; b_s[4 * j4 + 2] = a.z; b_s[4 * j4 + 3] = a.w;
+    b_t[4 * j4] = b.x; b_t[4 * j4 + 1] = b.y; b_t[4 * j4 + 2] = b.z; b_t[4 * j4 + 3] = b.w;
+  }
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float th = fast_tanh(sv[j] + b_s[j]);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(k1 * th));
+    const float tt = tv[j] + b_t[j];
+    y[j] = INV ? (u[j] - tt) * e : fmaf(u[j], e, tt);
+    if (nvalid >= 16) part += th;
+    else part += (j < nvalid) ? th : 0.f;
+  }
+  th_sum += part;
 }
 
 struct TcArgs {
@@ -524,14 +548,11 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
                 }
                 float y[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float s = sv[j] + ev[c + j];
-                  const float tt = tv[j] + ev[C + c + j];
-                  const float ls = ep.clamp * fast_tanh(s);
-                  y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
-                  if (coord0 + j < ep.Db) lsum += ls;
-                }
+                const int nvalid = ep.Db - coord0;
+                if (ep.mode == EPI_COUPLING_INV)
+                  coupling_chunk16<true>(sv, tv, ev + c, ev + C + c, -ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
+                else
+                  coupling_chunk16<false>(sv, tv, ev + c, ev + C + c, ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
                 if (full) {
                   uint4 q0, q1;
                   q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
@@ -547,7 +568,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
           }
-          if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
+          if (rvalid && ep.row_acc != nullptr)
+            atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
         } else if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) {
           const int C = ep.C;
           for (int c = half * 16; c < C; c += 32) {
@@ -866,14 +888,11 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
                     }
                     float y[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                      const float s = sv[j] + ev[c + j];
-                      const float tt = tv[j] + ev[C + c + j];
-                      const float ls = ep.clamp * fast_tanh(s);
-                      y[j] = (ep.mode == EPI_COUPLING_INV) ? (u[j] - tt) * fast_exp(-ls) : fmaf(u[j], fast_exp(ls), tt);
-                      if (coord0 + j < ep.Db) lsum += ls;
-                    }
+                    const int nvalid = ep.Db - coord0;
+                    if (ep.mode == EPI_COUPLING_INV)
+                      coupling_chunk16<true>(sv, tv, ev + c, ev + C + c, -ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
+                    else
+                      coupling_chunk16<false>(sv, tv, ev + c, ev + C + c, ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
                     if (full) {
                       uint4 q0, q1;
                       q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
@@ -889,7 +908,8 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                   }
                 }
               }
-              if (rvalid && ep.row_acc != nullptr) atomicAdd(ep.row_acc + row, ep.mode == EPI_COUPLING_INV ? -lsum : lsum);
+              if (rvalid && ep.row_acc != nullptr)
+                atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
             } else {   // additive coupling: tile = [t(C)]
               const int C = ep.C;
               for (int c = half * 16; c < C; c += 32) {

@@ -361,3 +361,32 @@ def test_graph_replay_matches_eager_and_tracks_weight_updates(O, P):
             assert rel(after, fo.log_prob(x.cpu().double())) < (FP32_TOL if precision == "fp32" else 5e-2)
             fp.layers[-1].scale.div_(1.5)
             fo.layers[-1].scale.div_(1.5)
+
+
+def test_adbench_wrapper_mirror(P):
+    """`nf4ad_b200.adbench.ADBenchFlow` against the reference wrapper's behavioural tests
+    (`/root/reference/tests/test_adbench_flow_wrapper.py:56-158`): init, fit + finite scores, binary
+    predictions, percentile threshold rate, score spread / separation."""
+    from nf4ad_b200.adbench import ADBenchFlow
+    rng = np.random.RandomState(42)
+    n_features = 20
+    X_train = rng.randn(200, n_features).astype(np.float32)
+    X_test = np.vstack([rng.randn(50, n_features), rng.randn(50, n_features) * 3 + 5]).astype(np.float32)
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", n_features, 3, ("mlp", [20]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    wrapper = ADBenchFlow(flow_model=flow, epochs=3, batch_size=32, lr=1e-3, device="cuda", verbose=False)
+    assert wrapper.flow_model is not None and wrapper.epochs == 3 and wrapper.batch_size == 32
+    wrapper.fit(X_train)
+    assert len(wrapper.training_losses) == 3 and np.all(np.isfinite(wrapper.training_losses))
+    assert wrapper.training_losses[-1] < wrapper.training_losses[0]
+    scores = wrapper.predict_score(X_test)
+    assert scores.shape == (len(X_test),) and np.all(np.isfinite(scores)) and scores.std() > 0
+    preds = wrapper.predict(X_test)
+    assert preds.shape == (len(X_test),) and np.all(np.isin(preds, [0, 1]))
+    thr = np.percentile(scores, 75)
+    rate = wrapper.predict(X_test, threshold=thr).mean()
+    assert 0.15 < rate < 0.35
+    assert np.median(scores[50:]) > np.median(scores[:50])
+    with pytest.raises(RuntimeError):
+        ADBenchFlow(flow_model=flow, device="cpu")
