@@ -339,6 +339,18 @@ class _StackedFlow(Flow):
             return 0
         return super().log_prior()
 
+    def log_abs_det_jacobian(self, x):
+        """`NonUSFlow.log_abs_det_jacobian(x)` (`nf4ad/flows.py:160-169`), quirk included: every layer is
+        evaluated at the data point `x` (it is never advanced through the stack), so the value is the true
+        log-det only for data-independent layers (USFlow).  Only the evaluation notebook calls it."""
+        total = 0
+        for layer in reversed(self.layers):
+            try:
+                total = total - layer.log_abs_det_jacobian(layer.backward(x), x)
+            except Exception:
+                continue
+        return total
+
 
 class USFlow(_StackedFlow):
     """`src.usflows.flows.USFlow`: additive couplings => data-independent total log-det."""

@@ -1,5 +1,7 @@
 """CPU: the oracle restatement reproduces the golden vectors that the
 reference's own in-tree classes produced (tests/golden/make_golden.py)."""
+import os
+
 import pytest
 import torch
 
@@ -56,3 +58,19 @@ def test_usflow_logdet_is_data_independent(O):
         z = flow.backward(x)
         ld = flow.log_prob(x) - flow._event_base.log_prob(z)
     assert float(ld.max() - ld.min()) < 1e-10
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference checkout only exists in the build container")
+def test_reference_own_tests_pass_on_the_oracle_shim():
+    """the reference's unmodified flow tests (`tests/test_flows.py`,
+    `tests/test_adbench_flow_wrapper.py`, 9 tests) run against the oracle's `src.usflows` / `pyro` shim."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "oracle", "shim"), "/root/reference/src"]),
+               PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-m", "not slow",
+                        "/root/reference/tests/test_flows.py", "/root/reference/tests/test_adbench_flow_wrapper.py"],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
