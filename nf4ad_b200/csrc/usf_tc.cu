@@ -69,18 +69,45 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false (and raises the global flag) if the barrier never completes.
+// Bounded wait: returns false (and raises the global flag) if the barrier never completes.  The hot spin is
+// try_wait only; the clock and the global abort flag (an L2 round trip) are looked at once per 1024 failed polls.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*reinterpret_cast<volatile int*>(&g_tc_timeout) != 0) return false;
-    if (clock64() - t0 > TC_WAIT_LIMIT_CYCLES) {
-      atomicExch(&g_tc_timeout, 1);
-      return false;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile int*>(&g_tc_timeout) != 0) return false;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TC_WAIT_LIMIT_CYCLES) {
+        atomicExch(&g_tc_timeout, 1);
+        return false;
+      }
     }
   }
-  return true;
+}
+
+// Wait with back-off: warps that are far from the critical path (epilogue warps waiting for a whole tile of MMAs, the
+// producer waiting for a ring slot) sleep between polls instead of competing with the MMA warp for the barrier unit.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return true;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile int*>(&g_tc_timeout) != 0) return false;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TC_WAIT_LIMIT_CYCLES) {
+        atomicExch(&g_tc_timeout, 1);
+        return false;
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
@@ -116,6 +143,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}"
       ::"r"(bar), "r"(cta)
       : "memory");
+}
+
+// One lane of a fully converged warp.  The producer / MMA warps run their loops with all 32 lanes (barrier waits are
+// warp-wide) and issue the TMA / tcgen05 instructions from the elected lane: inside a `lane == 0` branch the compiler
+// cannot prove the operands warp-uniform and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -241,6 +281,64 @@ __device__ __forceinline__ void coupling_chunk16(const float (&sv)[16], const fl
   th_sum += part;
 }
 
+// One 16-coordinate chunk of the additive coupling update (row-per-thread): y = u -+ (t + bt).
+template <bool INV>
+__device__ __forceinline__ void additive_chunk16(const float (&tv)[16], const float* bt, const float (&u)[16], float (&y)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b = reinterpret_cast<const float4*>(bt)[j4];
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tt = tv[4 * j4 + j] + bb[j];
+      y[4 * j4 + j] = INV ? u[4 * j4 + j] - tt : u[4 * j4 + j] + tt;
+    }
+  }
+}
+
+// Additive coupling epilogue of one accumulator tile [t(C)], C <= 128: same row-per-thread 256-bit access pattern as the
+// affine one (the transformed coordinates were prefetched into `uq` before the accumulator barrier).
+__device__ __forceinline__ void additive_tile(uint32_t t_base, const EpiParams& ep, const float* ev, const uint4 (&uq)[8],
+                                              int half, int nt, int64_t row, bool rvalid) {
+  const int C = ep.C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (2 * i + half) * 16;
+    if (c < C) {  // warp-uniform
+      float tv[16];
+      tmem_ld16(t_base + c, tv);
+      tmem_ld_wait();
+      const int coord0 = nt * C + c;
+      if (rvalid && coord0 < ep.Db) {
+        uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+        float u[16], y[16];
+        const bool full = coord0 + 16 <= ep.Db;
+        if (full) {
+          unpack_bf16x8(uq[2 * i], u);
+          unpack_bf16x8(uq[2 * i + 1], u + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
+        }
+        if (ep.mode == EPI_ADD_INV) additive_chunk16<true>(tv, ev + c, u, y);
+        else additive_chunk16<false>(tv, ev + c, u, y);
+        if (full) {
+          uint4 q0, q1;
+          q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
+          q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
+          q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
+          q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
+          st_global_256(up, q0, q1);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
+        }
+      }
+    }
+  }
+}
+
 struct TcArgs {
   int64_t M, N, K;
   int bn;        // N-tile width (multiple of 16, <= 256)
@@ -257,15 +355,18 @@ struct TcArgs {
 // Debug tracing: record (role, tile, event) with an SM clock stamp.  3 roles x 2 CTAs x TC_TRACE_CAP records.
 constexpr int TC_TRACE_CAP = 2048;
 __device__ unsigned long long g_tc_trace[2 * 3 * TC_TRACE_CAP * 2];
+template <bool DBG>
 __device__ __forceinline__ void tc_trace(unsigned long long* buf, int& n, int tile, int ev) {
-  if (buf != nullptr && n < TC_TRACE_CAP) {
+  if (DBG && buf != nullptr && n < TC_TRACE_CAP) {
     buf[2 * n] = ((unsigned long long)tile << 8) | (unsigned long long)ev;
     buf[2 * n + 1] = (unsigned long long)clock64();
     ++n;
   }
 }
 
-template <int CG>
+// DBG = true: the instrumented variant (pipeline tracing + ablation switches); production launches use DBG = false, whose
+// producer / MMA loops carry no instrumentation at all (their instruction count is what bounds the MMA issue rate).
+template <int CG, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs args) {
   // runtime ring geometry: a stage holds 128 rows of A and bn/CG rows of W (1 KB granularity), as many stages as fit
@@ -290,7 +391,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), CG);       // leader's arrive.expect_tx (+ the peer's remote arrive)
+      mbar_init(full_bar(s), 1);        // the leader's arrive.expect_tx; the peer's loads only add transaction bytes
       mbar_init(empty_bar(s), 1);       // one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int a = 0; a < 2; ++a) {
@@ -321,17 +422,20 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // trace region of this (CTA, role): only CTAs 0 and 1 record
   int trn = 0;
   unsigned long long* trb = nullptr;
-  if (args.trace != nullptr && blockIdx.x < 2) {
+  if (DBG && args.trace != nullptr && blockIdx.x < 2) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
     if (warp <= 2 && lane == 0) trb = args.trace + (size_t)(blockIdx.x * 3 + role) * TC_TRACE_CAP * 2;
   }
   const int num_kb = (int)((args.K + TC_BK - 1) / TC_BK);
   // bytes landing per stage on the (leader's) full barrier: every CTA loads 128 rows of A and bn/CG rows of W
-  const uint32_t stage_tx = CG * (TC_A_BYTES + (uint32_t)(args.bn / CG) * TC_BK * 2);
+  // debug ablations (usf_debug_tc_trace, bits 8+ of `on`): 1 = epilogue without global stores, 2 = epilogue only
+  // hands the accumulator back, 4 = producer skips the A loads, 8 = producer skips the W loads, 16 = no MMAs issued
+  const int dbg = DBG ? args.dbg : 0;
+  const uint32_t stage_tx = CG * (((dbg & 4) ? 0u : TC_A_BYTES) + ((dbg & 8) ? 0u : (uint32_t)(args.bn / CG) * TC_BK * 2));
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -343,68 +447,94 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int w_row = nt * args.bn + (CG == 2 ? (int)cta_rank * (width >> 1) : 0);
         const int a_row = (mt * CG + (int)cta_rank) * TC_BM;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (kb == 0) tc_trace(trb, trn, t, 0);
-          ok = mbar_wait(empty_bar(s), ph ^ 1u);
+          if (kb == 0) tc_trace<DBG>(trb, trn, t, 0);
+          ok = (dbg & 32) ? mbar_wait_relaxed(empty_bar(s), ph ^ 1u, 40) : mbar_wait(empty_bar(s), ph ^ 1u);
           if (!ok) break;
-          if (kb == 0) tc_trace(trb, trn, t, 1);
-          if (kb == num_kb - 1) tc_trace(trb, trn, t, 2);
+          if (kb == 0) tc_trace<DBG>(trb, trn, t, 1);
+          if (kb == num_kb - 1) tc_trace<DBG>(trb, trn, t, 2);
+          tc_trace<DBG>(trb, trn, t, 4);   // slot acquired
           const uint32_t a_dst = smem_base + s * TC_STAGE_BYTES;
-          if (CG == 1) {
-            mbar_expect_tx(full_bar(s), stage_tx);
-            tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
-            tma_load_2d(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
-          } else {
-            if (cta_rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
-            else mbar_arrive_cluster(full_bar(s), 0);
-            tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
-            tma_load_2d_2sm(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
+          if (elect_one()) {
+            if (CG == 1) {
+              mbar_expect_tx(full_bar(s), stage_tx);
+              if (!(dbg & 4)) tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+              if (!(dbg & 8)) tma_load_2d(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
+            } else {
+              // The peer's bytes can only land in the leader's CURRENT phase: its empty barrier for this slot was
+              // released by the commit that followed the MMAs which consumed the slot's previous contents.
+              if (cta_rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+              if (!(dbg & 4)) tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+              if (!(dbg & 8)) tma_load_2d_2sm(a_dst + TC_A_BYTES, &tmW, full_bar(s), kb * TC_BK, w_row);
+            }
           }
+          tc_trace<DBG>(trb, trn, t, 5);   // loads issued
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane issues)
+    if (cta_rank == 0) {
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       bool ok = true;
+      // K=16 steps of the last k-block (earlier k-blocks always run all four)
+      const int tail_steps = ((int)args.K - (num_kb - 1) * TC_BK + TC_UMMA_K - 1) / TC_UMMA_K;
+      // operand descriptors: only the 14-bit start-address field changes from stage to stage
+      const uint64_t desc_hi = make_smem_desc(0);
+      const uint32_t desc_lo0 = (smem_base & 0x3FFFFu) >> 4, desc_stage = TC_STAGE_BYTES >> 4;
       for (int t = unit; t < total_tiles && ok; t += num_units) {
-        const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
-        (void)mt;
+        const int nt = t % args.n_tiles;
         int width = (int)(args.N - (int64_t)nt * args.bn);
         if (width > args.bn) width = args.bn;
         const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * CG);
-        tc_trace(trb, trn, t, 0);
+        tc_trace<DBG>(trb, trn, t, 0);
         ok = mbar_wait(tempty_bar(a), aph ^ 1u);
         if (!ok) break;
-        tc_trace(trb, trn, t, 1);
+        tc_trace<DBG>(trb, trn, t, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ok = mbar_wait(full_bar(s), ph);
-          if (!ok) break;
-          if (kb == 0) tc_trace(trb, trn, t, 2);
-          if (kb == num_kb - 1) tc_trace(trb, trn, t, 3);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + s * TC_STAGE_BYTES;
-          const uint32_t b_addr = a_addr + TC_A_BYTES;
-          int64_t krem = args.K - (int64_t)kb * TC_BK;
-          if (krem > TC_BK) krem = TC_BK;
-          const int ksteps = (int)((krem + TC_UMMA_K - 1) / TC_UMMA_K);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * TC_UMMA_K * 2);
-            const uint64_t bd = make_smem_desc(b_addr + k * TC_UMMA_K * 2);
-            if (CG == 1) umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          // TMA (async proxy) -> mbarrier -> tcgen05.mma needs no further fence
+          if (DBG && (dbg & 64)) {
+            if (lane == 0) ok = mbar_wait(full_bar(s), ph);
+            ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+          } else {
+            ok = mbar_wait(full_bar(s), ph);
           }
-          if (CG == 1) umma_commit(empty_bar(s));  // smem stage reusable once these MMAs retire
-          else umma_commit_2sm(empty_bar(s));      // ... in both CTAs of the pair
+          if (!ok) break;
+          if (kb == 0) tc_trace<DBG>(trb, trn, t, 2);
+          if (kb == num_kb - 1) tc_trace<DBG>(trb, trn, t, 3);
+          tc_trace<DBG>(trb, trn, t, 4);   // operands landed
+          if (elect_one()) {
+            // descriptors advance by 32 bytes (2 x 16-byte units) per K=16 step inside the 128-byte swizzle row
+            const uint64_t ad0 = desc_hi | (uint64_t)(desc_lo0 + (uint32_t)s * desc_stage);
+            const uint64_t bd0 = ad0 + (TC_A_BYTES >> 4);
+            if (!(DBG && (dbg & 16))) {
+              if (kb + 1 < num_kb) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                  if (CG == 1) umma_bf16(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  else umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+              } else {
+                for (int k = 0; k < tail_steps; ++k) {
+                  if (CG == 1) umma_bf16(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  else umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            if (CG == 1) umma_commit(empty_bar(s));  // smem stage reusable once these MMAs retire
+            else umma_commit_2sm(empty_bar(s));      // ... in both CTAs of the pair
+          }
+          tc_trace<DBG>(trb, trn, t, 6);   // MMAs + commit issued
           if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
         }
         if (!ok) break;
-        if (CG == 1) umma_commit(tfull_bar(a));    // accumulator ready for the epilogue
-        else umma_commit_2sm(tfull_bar(a));        // (each CTA of the pair holds its own 128 rows in its TMEM)
+        if (elect_one()) {
+          if (CG == 1) umma_commit(tfull_bar(a));    // accumulator ready for the epilogue
+          else umma_commit_2sm(tfull_bar(a));        // (each CTA of the pair holds its own 128 rows in its TMEM)
+        }
         a ^= 1;
         if (a == 0) aph ^= 1u;
       }
@@ -419,6 +549,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const EpiParams& ep = args.ep;
     float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [2][3][256]
     const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+    const bool is_add = ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD;
     const bool is_base = ep.mode == EPI_BASE_NORMAL || ep.mode == EPI_BASE_LAPLACE;
     int a = 0;
     uint32_t aph = 0;
@@ -444,7 +575,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       // (2) coupling: prefetch this thread's slice of the transformed coordinates (independent of the MMA)
       uint4 uq[8];
-      if (is_cpl) {
+      if (is_cpl || is_add) {
         // each thread prefetches its own row's 16-coordinate chunks (even/odd chunks per warp half)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -456,17 +587,19 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
       __syncwarp();
-      tc_trace(trb, trn, t, 0);
+      tc_trace<DBG>(trb, trn, t, 0);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      tc_trace(trb, trn, t, 1);
+      tc_trace<DBG>(trb, trn, t, 1);
 
-      const bool ok = mbar_wait(tfull_bar(a), aph);
-      tc_trace(trb, trn, t, 2);
+      const bool ok = (dbg & 32) ? mbar_wait_relaxed(tfull_bar(a), aph, 100) : mbar_wait(tfull_bar(a), aph);
+      tc_trace<DBG>(trb, trn, t, 2);
       if (ok) {
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
 
-        if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16) {
+        if (dbg & 2) {
+          // ablation: accumulator handed straight back
+        } else if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16) {
           for (int c = half * 16; c < width; c += 32) {
             float v[16];
             tmem_ld16(t_base + c, v);
@@ -487,7 +620,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              st_global_256(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c, q0, q1);
+              if (!(dbg & 1) || q0.x == 0x12345678u)
+                st_global_256(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c, q0, q1);
             }
           }
         } else if (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) {
@@ -570,25 +704,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           if (rvalid && ep.row_acc != nullptr)
             atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
-        } else if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) {
-          const int C = ep.C;
-          for (int c = half * 16; c < C; c += 32) {
-            float tv[16];
-            tmem_ld16(t_base + c, tv);
-            tmem_ld_wait();
-            const int coord0 = nt * C + c;
-            if (rvalid && coord0 < ep.Db) {
-              uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (coord0 + j < ep.Db) {
-                  const float u = __uint_as_float((uint32_t)up[j] << 16);
-                  const float tt = tv[j] + ev[c + j];
-                  up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
-                }
-              }
-            }
-          }
+        } else if (is_add) {
+          additive_tile(t_base, ep, ev, uq, half, nt, row, rvalid);
         } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE  (padded columns have inv_scale = 0 -> contribute 0)
           float lsum = 0.f;
           for (int c = half * 16; c < width; c += 32) {
@@ -616,7 +733,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (CG == 1 || cta_rank == 0) mbar_arrive(tempty_bar(a));
           else mbar_arrive_cluster(tempty_bar(a), 0);
         }
-        tc_trace(trb, trn, t, 3);
+        tc_trace<DBG>(trb, trn, t, 3);
       }
       a ^= 1;
       if (a == 0) aph ^= 1u;
@@ -666,6 +783,7 @@ struct MlpArgs {
   unsigned long long* trace;     // debug timeline (see usf_debug_tc_trace); events use tile = (m_tile << 4) | gemm index
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ MlpMaps maps, MlpArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -685,7 +803,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < MLP_STAGES; ++s) {
-      mbar_init(full_bar(s), 2);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -710,14 +828,14 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const int L = args.L;
   int trn = 0;
   unsigned long long* trb = nullptr;
-  if (args.trace != nullptr && blockIdx.x < 2) {
+  if (DBG && args.trace != nullptr && blockIdx.x < 2) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
     if (warp <= 2 && lane == 0) trb = args.trace + (size_t)(blockIdx.x * 3 + role) * TC_TRACE_CAP * 2;
   }
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; whole warp, elected lane issues)
+    {
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -734,10 +852,11 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
               ok = mbar_wait(empty_bar(s), ph ^ 1u);
               if (!ok) break;
               const uint32_t dst = smem_base + s * MLP_STAGE_BYTES;
-              if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx);
-              else mbar_arrive_cluster(full_bar(s), 0);
-              if (l == 0) tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * TC_BK, a_row);
-              tma_load_2d_2sm(dst + TC_A_BYTES, &maps.w[l], full_bar(s), kb * TC_BK, w_row);
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx);
+                if (l == 0) tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+                tma_load_2d_2sm(dst + TC_A_BYTES, &maps.w[l], full_bar(s), kb * TC_BK, w_row);
+              }
               if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
             }
           }
@@ -745,8 +864,8 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; whole warp, elected lane issues)
+    if (cta_rank == 0) {
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0, hph = 0;
       bool ok = true;
@@ -758,37 +877,37 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             if (width > args.bn[l]) width = args.bn[l];
             const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * 2);
             const int gi = (t << 4) | (l * 4 + nt);
-            tc_trace(trb, trn, gi, 0);
+            tc_trace<DBG>(trb, trn, gi, 0);
             ok = mbar_wait(tempty_bar(a), aph ^ 1u);
             if (!ok) break;
-            tc_trace(trb, trn, gi, 1);
+            tc_trace<DBG>(trb, trn, gi, 1);
             if (l > 0 && nt == 0) {      // operand A = the hidden tile written by the previous layer's epilogue (both CTAs)
               ok = mbar_wait(hready_bar, hph);
               if (!ok) break;
               hph ^= 1u;
             }
-            tc_trace(trb, trn, gi, 2);
+            tc_trace<DBG>(trb, trn, gi, 2);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
             for (int kb = 0; kb < nkb; ++kb) {
               ok = mbar_wait(full_bar(s), ph);
               if (!ok) break;
-              tc_fence_after();
               const uint32_t slot = smem_base + s * MLP_STAGE_BYTES;
               const uint32_t a_addr = l == 0 ? slot : h_base + (uint32_t)kb * TC_A_BYTES;
-              const uint32_t b_addr = slot + TC_A_BYTES;
               int krem = args.K[l] - kb * TC_BK;
               if (krem > TC_BK) krem = TC_BK;
               const int ksteps = (krem + TC_UMMA_K - 1) / TC_UMMA_K;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16_2sm(d_tmem, make_smem_desc(a_addr + k * TC_UMMA_K * 2), make_smem_desc(b_addr + k * TC_UMMA_K * 2),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_commit_2sm(empty_bar(s));
+              if (elect_one()) {
+                const uint64_t ad0 = make_smem_desc(a_addr), bd0 = make_smem_desc(slot + TC_A_BYTES);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit_2sm(empty_bar(s));
+              }
               if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
             }
             if (!ok) break;
-            umma_commit_2sm(tfull_bar(a));
-            tc_trace(trb, trn, gi, 3);
+            if (elect_one()) umma_commit_2sm(tfull_bar(a));
+            tc_trace<DBG>(trb, trn, gi, 3);
             a ^= 1;
             if (a == 0) aph ^= 1u;
           }
@@ -803,7 +922,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const EpiParams& ep = args.ep;
     float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));
     uint4* hp = reinterpret_cast<uint4*>(smem_raw + (h_base - smem_u32(smem_raw)));   // H as uint4[kb][128 rows][8 pieces]
-    const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+    const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;   // else: additive
     const int rloc = lane_grp * 32 + lane;           // row within this CTA's 128-row tile
     int a = 0;
     uint32_t aph = 0;
@@ -819,7 +938,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           float* ev = epi + a * 768;
           ev[et] = (et < width) ? args.bias[l][n0 + et] : 0.f;
           uint4 uq[8];
-          if (last && is_cpl) {
+          if (last) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c = (2 * i + half) * 16;
@@ -830,10 +949,10 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             }
           }
           const int gi = (t << 4) | (l * 4 + nt);
-          tc_trace(trb, trn, gi, 0);
+          tc_trace<DBG>(trb, trn, gi, 0);
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const bool ok = mbar_wait(tfull_bar(a), aph);
-          tc_trace(trb, trn, gi, 2);
+          tc_trace<DBG>(trb, trn, gi, 2);
           if (ok) {
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
@@ -911,24 +1030,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
               if (rvalid && ep.row_acc != nullptr)
                 atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
             } else {   // additive coupling: tile = [t(C)]
-              const int C = ep.C;
-              for (int c = half * 16; c < C; c += 32) {
-                float tv[16];
-                tmem_ld16(t_base + c, tv);
-                tmem_ld_wait();
-                const int coord0 = nt * C + c;
-                if (rvalid && coord0 < ep.Db) {
-                  uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    if (coord0 + j < ep.Db) {
-                      const float u = __uint_as_float((uint32_t)up[j] << 16);
-                      const float tt = tv[j] + ev[c + j];
-                      up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(ep.mode == EPI_ADD_INV ? u - tt : u + tt));
-                    }
-                  }
-                }
-              }
+              additive_tile(t_base, ep, ev, uq, half, nt, row, rvalid);
             }
             tc_fence_before();
             __syncwarp();
@@ -940,7 +1042,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 else mbar_arrive_cluster(hready_bar, 0);
               }
             }
-            tc_trace(trb, trn, gi, 3);
+            tc_trace<DBG>(trb, trn, gi, 3);
           }
           a ^= 1;
           if (a == 0) aph ^= 1u;
@@ -1031,6 +1133,7 @@ int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols,
 const char* const kTcGemmKernelName = "usf_tc_gemm_kernel";
 
 int g_trace_on = 0;   // 1: trace plain GEMM launches, 2: trace fused conditioner launches
+int g_tc_dbg = -1;    // debug ablation bits (see usf_tc_gemm_kernel); -1 = read USF_TC_DBG once
 
 // CTAs per MMA: 2 (CTA pairs, tcgen05 cta_group::2) unless USF_TC_CTA_GROUP=1 selects the single-CTA kernel.
 int tc_cta_group() {
@@ -1065,13 +1168,16 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16)
     USF_CHECK_ARG((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0 && (ep.ldo % 16) == 0, "tc_gemm: bf16 output must be 32-byte aligned");
   if (ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD)
-    USF_CHECK_ARG(bn == ep.C && (N % bn) == 0, "tc_gemm: additive tile must be [t(C)]");
+    USF_CHECK_ARG(bn == ep.C && ep.C <= 128 && (N % bn) == 0 && (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 &&
+                      (ep.ldub % 16) == 0,
+                  "tc_gemm: additive tile must be [t(C <= 128)] and the b-part 32-byte aligned");
 
   const int cg = tc_cta_group();
   static bool attr_set = false;
   if (!attr_set) {
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap tmA, tmW;
@@ -1098,11 +1204,8 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
     if (cap >= 2 && args.stages > cap) args.stages = cap;
   }
   if (args.stages < 2) { set_error("tc_gemm: tile does not fit in shared memory"); return USF_E_ARG; }
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("USF_TC_DBG"); dbg = e ? atoi(e) : 0; }
-    args.dbg = dbg;
-  }
+  if (g_tc_dbg < 0) { const char* e = getenv("USF_TC_DBG"); g_tc_dbg = e ? atoi(e) : 0; }
+  args.dbg = g_tc_dbg;
   args.trace = nullptr;
   if (g_trace_on == 1) {
     void* p = nullptr;
@@ -1114,7 +1217,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if (cg == 1) {
     int grid = num_sms();
     if (grid > total) grid = (int)total;
-    usf_tc_gemm_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
+    usf_tc_gemm_kernel<1, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
     USF_LAUNCH_CHECK("usf_tc_gemm_kernel<1>");
     return USF_OK;
   }
@@ -1132,7 +1235,8 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2>, tmA, tmW, args));
+  if (args.trace != nullptr || args.dbg != 0) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
+  else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, args));
   return USF_OK;
 }
 
@@ -1156,7 +1260,8 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
   USF_CHECK_ARG((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "tc_mlp_coupling: bad activation layout");
   static bool attr_set = false;
   if (!attr_set) {
-    USF_CUDA(cudaFuncSetAttribute(usf_tc_mlp_coupling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_mlp_coupling_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    USF_CUDA(cudaFuncSetAttribute(usf_tc_mlp_coupling_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     attr_set = true;
   }
   MlpArgs args;
@@ -1186,7 +1291,8 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
                       (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 && (ep.ldub % 16) == 0,
                   "tc_mlp_coupling: bad coupling tile");
   else
-    USF_CHECK_ARG((ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) && bn_last == ep.C && (N[n_layers - 1] % bn_last) == 0,
+    USF_CHECK_ARG((ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD) && bn_last == ep.C && ep.C <= 128 &&
+                      (N[n_layers - 1] % bn_last) == 0 && (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 && (ep.ldub % 16) == 0,
                   "tc_mlp_coupling: bad additive tile");
   args.ep = ep;
   args.trace = nullptr;
@@ -1210,13 +1316,15 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel, tmA, maps, args));
+  if (args.trace != nullptr) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel<true>, tmA, maps, args));
+  else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel<false>, tmA, maps, args));
   return USF_OK;
 }
 
 // Debug: enable tracing for subsequent launches (on != 0) / read back the records of the LAST launch.
 int tc_trace_ctl(int on, unsigned long long* out, int max_records) {
-  g_trace_on = on;
+  g_trace_on = on & 0xFF;
+  if (out == nullptr) g_tc_dbg = (on >> 8) & 0xFF;   // bits 8+: ablation switches for subsequent plain-GEMM launches
   if (out != nullptr) {
     const size_t n = (size_t)2 * 3 * TC_TRACE_CAP * 2;
     const size_t want = (size_t)max_records * 2 < n ? (size_t)max_records * 2 : n;

@@ -219,7 +219,7 @@ class CompiledStack:
         dev = self.device
         # tile geometry of the last layer
         if bf16:
-            cap = 128 if affine else 256
+            cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
             nt = -(-Db // cap)
             Cc = _round_up(-(-Db // nt), 16)
         else:

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python scripts/tc_ablate.py > gpurun_out/tc_ablate.log 2>&1; echo "ablate exit $?"
+cat gpurun_out/tc_ablate.log | tail -5
+timeout 300 python scripts/tc_trace2.py > gpurun_out/tc_trace2.log 2>&1; echo "trace exit $?"
+timeout 600 python bench.py --steps 50 --warmup 10 --no-cpu-baseline --train-steps 0 2>&1 | tail -1 | python -c "
+import json,sys
+j=json.loads(sys.stdin.read()); print(j['value'], j['ms_per_step'], j['roofline']['launch_ms_by_kind'], j['roofline']['frac'])"
