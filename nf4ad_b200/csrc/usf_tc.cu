@@ -19,6 +19,7 @@
 // Measured bounds (profiles/): the MMA side waits on operand delivery (~820 cycles per 64-wide k-block vs 416 of
 // MMA at N=208) and short-K GEMMs are epilogue-bound (TMEM drain + row-strided stores ~7k cycles per 128x256 tile).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "usf_common.cuh"
@@ -35,7 +36,9 @@ constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
 constexpr uint32_t TC_BAR_BYTES = 256;
 constexpr int TC_MAX_STAGES = 8;
-constexpr uint32_t TC_EPI_BYTES = 2 * 3 * 256 * 4;  // per accumulator stage: bias / loc / inv_scale of the tile's columns
+constexpr int TC_EPI_COLS = 1024;                    // per-column epilogue vectors resident in smem when N <= this
+constexpr uint32_t TC_EPI_BYTES = 3 * TC_EPI_COLS * 4;  // bias / loc / inv_scale (N <= 1024: whole vectors, staged once;
+                                                        // wider outputs: [2 stages][3][256] re-staged per tile)
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x bn tile; 2 = a CTA pair (cluster of 2) owns a
 // 256 x bn tile, each CTA staging its own 128 rows of A and HALF of the W tile, which halves the L2->SMEM weight
 // traffic per CTA (the measured bound of the 1-CTA kernel) and the SMEM operand reads per MMA.
@@ -251,92 +254,133 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4& lo, const ui
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-// One 16-coordinate chunk of the affine coupling update (row-per-thread):
-//   th = tanh(s + bs),  e = exp(+-clamp*th) = ex2(k1*th),  y = INV ? (u - (t + bt)) * e : u * e + (t + bt)
-// Biases come as float4 from the per-tile smem vectors; the log-det accumulates tanh only (scaled by clamp once per
-// row by the caller).  2 MUFU + ~7 ALU per coordinate.
-template <bool INV>
-__device__ __forceinline__ void coupling_chunk16(const float (&sv)[16], const float (&tv)[16], const float* bs,
-                                                 const float* bt, float k1, const float (&u)[16], float (&y)[16],
-                                                 float& th_sum, int nvalid) {
-  float b_s[16], b_t[16];
-#pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 a = reinterpret_cast<const float4*>(bs)[j4];
-    const float4 b = reinterpret_cast<const float4*>(bt)[j4];
-    b_s[4 * j4] = a.x; b_s[4 * j4 + 1] = a.y; b_s[4 * j4 + 2] = a.z; b_s[4 * j4 + 3] = a.w;
-    b_t[4 * j4] = b.x; b_t[4 * j4 + 1] = b.y; b_t[4 * j4 + 2] = b.z; b_t[4 * j4 + 3] = b.w;
-  }
-  float part = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float th = fast_tanh(sv[j] + b_s[j]);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(k1 * th));
-    const float tt = tv[j] + b_t[j];
-    y[j] = INV ? (u[j] - tt) * e : fmaf(u[j], e, tt);
-    if (nvalid >= 16) part += th;
-    else part += (j < nvalid) ? th : 0.f;
-  }
-  th_sum += part;
+// ---- coupling epilogue (row-per-thread: TMEM lane = row) ---------------------------------------------------------
+// One 16-coordinate chunk of a masked coupling, affine or additive, either direction, in ONE branch-free form:
+//   th = tanh(s + bs),  e = exp(+-clamp*th) = ex2(k1*th)   (additive: e = 1),   tt = t + bt
+//   inverse (sgn = 1): y = (u - tt) * e          forward (sgn = 0): y = u * e + tt
+//   both:              y = fma(u - sgn*tt, e, (1 - sgn)*tt)
+// A single copy of this code serves every mode (the epilogue warps walk it in a rolled loop): with the 16-way
+// unrolled per-mode variants the hot epilogue was ~32 KB of SASS and spent 40-50 % of its samples in instruction
+// fetch (ncu stall_no_inst, profiles/r2).  tanh / ex2 take f16 pairs (th in [-1,1], e in [2^-7.3, 2^7.3]: 11-bit
+// significands, finer than the bf16 activations they multiply); the log-det accumulates tanh in fp32.  Padded
+// coordinates have zero weight rows and zero bias, so s = 0 and tanh(0) = 0 adds nothing to the log-det.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+// +-clamp * log2(e) as a packed f16x2 constant
+__device__ __forceinline__ uint32_t coupling_k1(float clamp, bool inv) {
+  const float k = (inv ? -clamp : clamp) * 1.4426950408889634f;
+  return pack_f16x2(k, k);
 }
 
-// One 16-coordinate chunk of the additive coupling update (row-per-thread): y = u -+ (t + bt).
-template <bool INV>
-__device__ __forceinline__ void additive_chunk16(const float (&tv)[16], const float* bt, const float (&u)[16], float (&y)[16]) {
-#pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 b = reinterpret_cast<const float4*>(bt)[j4];
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float tt = tv[4 * j4 + j] + bb[j];
-      y[4 * j4 + j] = INV ? u[4 * j4 + j] - tt : u[4 * j4 + j] + tt;
-    }
-  }
+// request the 16 transformed coordinates of one chunk (32 bytes, one LDG.256); partial / invalid chunks load nothing
+__device__ __forceinline__ void cpl_load_u(const EpiParams& ep, int64_t row, bool rvalid, int coord0, uint4& q0, uint4& q1) {
+  if (rvalid && coord0 + 16 <= ep.Db)
+    ld_global_256(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0, q0, q1);
 }
 
-// Additive coupling epilogue of one accumulator tile [t(C)], C <= 128: same row-per-thread 256-bit access pattern as the
-// affine one (the transformed coordinates were prefetched into `uq` before the accumulator barrier).
-__device__ __forceinline__ void additive_tile(uint32_t t_base, const EpiParams& ep, const float* ev, const uint4 (&uq)[8],
-                                              int half, int nt, int64_t row, bool rvalid) {
+// t_tile: TMEM address of the tile's first column for this warp's lanes; c: chunk offset inside the tile; ev: the tile's
+// bias vector in smem ([bs(C) | bt(C)] or [bt(C)]).  Must be called by all 32 lanes (tcgen05.ld is warp-collective).
+// Written stage by stage over all 16 coordinates (16-way ILP between the dependent FADD -> F2FP -> MUFU -> HMUL2 -> MUFU
+// -> FFMA links); AFFINE / INV are compile-time so the executed path carries no selects (only one instantiation runs
+// in any launch, so the instruction-cache footprint stays one chunk body).
+template <bool AFFINE, bool INV>
+__device__ __forceinline__ void cpl_chunk(uint32_t t_tile, int c, const float* ev, const EpiParams& ep, uint32_t k1h2,
+                                          int64_t row, bool rvalid, int coord0, const uint4& q0, const uint4& q1, float& lsum) {
   const int C = ep.C;
+  float sv[16], tv[16];
+  if (AFFINE) {
+    tmem_ld16(t_tile + c, sv);
+    tmem_ld16(t_tile + C + c, tv);
+  } else {
+    tmem_ld16(t_tile + c, tv);
+  }
+  tmem_ld_wait();
+  if (!rvalid || coord0 >= ep.Db) return;
+  uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+  const bool full = coord0 + 16 <= ep.Db;
+  float u[16];
+  if (full) {
+    unpack_bf16x8(q0, u);
+    unpack_bf16x8(q1, u + 8);
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = (2 * i + half) * 16;
-    if (c < C) {  // warp-uniform
-      float tv[16];
-      tmem_ld16(t_base + c, tv);
-      tmem_ld_wait();
-      const int coord0 = nt * C + c;
-      if (rvalid && coord0 < ep.Db) {
-        uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-        float u[16], y[16];
-        const bool full = coord0 + 16 <= ep.Db;
-        if (full) {
-          unpack_bf16x8(uq[2 * i], u);
-          unpack_bf16x8(uq[2 * i + 1], u + 8);
-        } else {
+    for (int j = 0; j < 16; ++j) u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
+  }
+  const float4* bt4 = reinterpret_cast<const float4*>(AFFINE ? ev + C + c : ev + c);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
-        }
-        if (ep.mode == EPI_ADD_INV) additive_chunk16<true>(tv, ev + c, u, y);
-        else additive_chunk16<false>(tv, ev + c, u, y);
-        if (full) {
-          uint4 q0, q1;
-          q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
-          q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
-          q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
-          q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-          st_global_256(up, q0, q1);
-        } else {
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b = bt4[j4];
+    tv[4 * j4] += b.x; tv[4 * j4 + 1] += b.y; tv[4 * j4 + 2] += b.z; tv[4 * j4 + 3] += b.w;
+  }
+  if (AFFINE) {
+    const float4* bs4 = reinterpret_cast<const float4*>(ev + c);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
-        }
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = bs4[j4];
+      sv[4 * j4] += b.x; sv[4 * j4 + 1] += b.y; sv[4 * j4 + 2] += b.z; sv[4 * j4 + 3] += b.w;
+    }
+    uint32_t th2[8], e2[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) th2[p] = pack_f16x2(sv[2 * p], sv[2 * p + 1]);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) asm("tanh.approx.f16x2 %0, %1;" : "=r"(th2[p]) : "r"(th2[p]));
+#pragma unroll
+    for (int p = 0; p < 8; ++p) asm("mul.f16x2 %0, %1, %2;" : "=r"(e2[p]) : "r"(th2[p]), "r"(k1h2));
+#pragma unroll
+    for (int p = 0; p < 8; ++p) asm("ex2.approx.f16x2 %0, %1;" : "=r"(e2[p]) : "r"(e2[p]));
+    // log-det: tanh values are summed in pairs in f16 (|sum| <= 2: absolute rounding error <= 2^-11), then in fp32
+    float part = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; p += 2) {
+      uint32_t pr;
+      asm("add.f16x2 %0, %1, %2;" : "=r"(pr) : "r"(th2[p]), "r"(th2[p + 1]));
+      const float2 f = unpack_f16x2(pr);
+      part += f.x + f.y;
+    }
+    lsum += part;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float2 e = unpack_f16x2(e2[p]);
+      if (INV) {
+        u[2 * p] = (u[2 * p] - tv[2 * p]) * e.x;
+        u[2 * p + 1] = (u[2 * p + 1] - tv[2 * p + 1]) * e.y;
+      } else {
+        u[2 * p] = fmaf(u[2 * p], e.x, tv[2 * p]);
+        u[2 * p + 1] = fmaf(u[2 * p + 1], e.y, tv[2 * p + 1]);
       }
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) u[j] = INV ? u[j] - tv[j] : u[j] + tv[j];
   }
+  if (full) {
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(u[0], u[1]);   o0.y = pack_bf16x2(u[2], u[3]);
+    o0.z = pack_bf16x2(u[4], u[5]);   o0.w = pack_bf16x2(u[6], u[7]);
+    o1.x = pack_bf16x2(u[8], u[9]);   o1.y = pack_bf16x2(u[10], u[11]);
+    o1.z = pack_bf16x2(u[12], u[13]); o1.w = pack_bf16x2(u[14], u[15]);
+    st_global_256(up, o0, o1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(u[j]));
+  }
+}
+
+// runtime mode -> the one compile-time instantiation this launch executes
+__device__ __forceinline__ void cpl_chunk_dispatch(int mode, uint32_t t_tile, int c, const float* ev, const EpiParams& ep,
+                                                   uint32_t k1h2, int64_t row, bool rvalid, int coord0, const uint4& q0,
+                                                   const uint4& q1, float& lsum) {
+  if (mode == EPI_COUPLING_INV) cpl_chunk<true, true>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
+  else if (mode == EPI_COUPLING_FWD) cpl_chunk<true, false>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
+  else if (mode == EPI_ADD_INV) cpl_chunk<false, true>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
+  else cpl_chunk<false, false>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
 }
 
 struct TcArgs {
@@ -551,6 +595,20 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
     const bool is_add = ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD;
     const bool is_base = ep.mode == EPI_BASE_NORMAL || ep.mode == EPI_BASE_LAPLACE;
+    const uint32_t k1h2 = coupling_k1(ep.clamp, ep.mode == EPI_COUPLING_INV);
+    // per-column vectors: staged once for the whole kernel when they fit, else re-staged per tile
+    const bool resident = args.N <= TC_EPI_COLS;
+    if (resident) {
+      for (int i = et; i < (int)args.N; i += 256) {
+        epi[i] = ep.bias != nullptr ? ep.bias[i] : 0.f;
+        if (is_base) {
+          const bool v2 = i < args.n_valid && ep.loc != nullptr;
+          epi[TC_EPI_COLS + i] = v2 ? ep.loc[i] : 0.f;
+          epi[2 * TC_EPI_COLS + i] = v2 ? ep.inv_scale[i] : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     int a = 0;
     uint32_t aph = 0;
     for (int t = unit; t < total_tiles; t += num_units) {
@@ -560,10 +618,13 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int64_t n0 = (int64_t)nt * args.bn;
       int width = (int)(args.N - n0);
       if (width > args.bn) width = args.bn;
-      float* ev = epi + a * 768;  // [0,256) bias, [256,512) loc, [512,768) inv_scale of this tile's columns
+      // bias / loc / inv_scale of this tile's columns
+      float* ev = resident ? epi + n0 : epi + a * 768;
+      const float* ev_loc = resident ? ev + TC_EPI_COLS : ev + 256;
+      const float* ev_isc = resident ? ev + 2 * TC_EPI_COLS : ev + 512;
 
-      // (1) stage the per-column vectors of this tile in shared memory (one element per epilogue thread)
-      {
+      // (1) not resident: stage the per-column vectors of this tile in shared memory (one element per epilogue thread)
+      if (!resident) {
         const int64_t col = n0 + et;
         const bool cv = et < width;
         ev[et] = (cv && ep.bias != nullptr) ? ep.bias[col] : 0.f;
@@ -573,22 +634,11 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ev[512 + et] = v2 ? ep.inv_scale[col] : 0.f;
         }
       }
-      // (2) coupling: prefetch this thread's slice of the transformed coordinates (independent of the MMA)
-      uint4 uq[8];
-      if (is_cpl || is_add) {
-        // each thread prefetches its own row's 16-coordinate chunks (even/odd chunks per warp half)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = (2 * i + half) * 16;
-          const int coord0 = nt * ep.C + c;
-          if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
-            ld_global_256(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0, uq[2 * i], uq[2 * i + 1]);
-          }
-        }
-      }
-      __syncwarp();
+      // (2) coupling: request the first chunk of transformed coordinates of this thread's row (independent of the MMA)
+      uint4 cq0 = make_uint4(0, 0, 0, 0), cq1 = cq0;
+      if (is_cpl || is_add) cpl_load_u(ep, row, rvalid, nt * ep.C + half * 16, cq0, cq1);
       tc_trace<DBG>(trb, trn, t, 0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!resident) asm volatile("bar.sync 1, 256;" ::: "memory");
       tc_trace<DBG>(trb, trn, t, 1);
 
       const bool ok = (dbg & 32) ? mbar_wait_relaxed(tfull_bar(a), aph, 100) : mbar_wait(tfull_bar(a), aph);
@@ -657,55 +707,19 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
           }
-        } else if (is_cpl) {
-          const int C = ep.C;
+        } else if (is_cpl || is_add) {
+          // rolled chunk loop (one copy of the chunk code); the next chunk's coordinates are requested before the
+          // current chunk is processed
           float lsum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = (2 * i + half) * 16;
-            if (c < C) {  // warp-uniform
-              float sv[16], tv[16];
-              tmem_ld16(t_base + c, sv);
-              tmem_ld16(t_base + C + c, tv);
-              tmem_ld_wait();
-              const int coord0 = nt * C + c;
-              if (rvalid && coord0 < ep.Db) {
-                uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-                float u[16];
-                const bool full = coord0 + 16 <= ep.Db;
-                if (full) {
-                  unpack_bf16x8(uq[2 * i], u);
-                  unpack_bf16x8(uq[2 * i + 1], u + 8);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
-                }
-                float y[16];
-                const int nvalid = ep.Db - coord0;
-                if (ep.mode == EPI_COUPLING_INV)
-                  coupling_chunk16<true>(sv, tv, ev + c, ev + C + c, -ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
-                else
-                  coupling_chunk16<false>(sv, tv, ev + c, ev + C + c, ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
-                if (full) {
-                  uint4 q0, q1;
-                  q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
-                  q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
-                  q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
-                  q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-                  st_global_256(up, q0, q1);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
-                }
-              }
-            }
+          for (int c = half * 16; c < ep.C; c += 32) {
+            uint4 nq0 = make_uint4(0, 0, 0, 0), nq1 = nq0;
+            if (c + 32 < ep.C) cpl_load_u(ep, row, rvalid, nt * ep.C + c + 32, nq0, nq1);
+            cpl_chunk_dispatch(ep.mode, t_base, c, ev, ep, k1h2, row, rvalid, nt * ep.C + c, cq0, cq1, lsum);
+            cq0 = nq0;
+            cq1 = nq1;
           }
-          if (rvalid && ep.row_acc != nullptr)
+          if (is_cpl && rvalid && ep.row_acc != nullptr)
             atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
-        } else if (is_add) {
-          additive_tile(t_base, ep, ev, uq, half, nt, row, rvalid);
         } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE  (padded columns have inv_scale = 0 -> contribute 0)
           float lsum = 0.f;
           for (int c = half * 16; c < width; c += 32) {
@@ -718,7 +732,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float z = v[j] + ev[c + j];
                 if (ep.out != nullptr && n0 + c + j < args.n_valid)
                   reinterpret_cast<float*>(ep.out)[row * ep.ldo + n0 + c + j] = z;
-                const float d = (z - ev[256 + c + j]) * ev[512 + c + j];
+                const float d = (z - ev_loc[c + j]) * ev_isc[c + j];
                 lsum += (ep.mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
               }
             }
@@ -761,6 +775,14 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // streams A (the conditioning columns of the activation).  Replaces L launches + 2(L-1) HBM round trips of h.
 // ================================================================================================
 constexpr int MLP_MAX_LAYERS = 4;
+// Epilogue warps of the fused kernel: 16 (four per scheduler).  Its epilogues alternate between TMEM reads
+// (~75 B/clk/SM measured), MUFU-heavy and FMA-heavy stretches; with two warps per scheduler those phases barely
+// overlapped (issue slots 29 % busy, ncu profiles/r2).  Warp w owns TMEM lanes 32*(w%4)..+32 and every
+// MLP_EPI_PARTS-th 16-column chunk.
+constexpr int MLP_EPI_WARPS = 16;
+constexpr int MLP_EPI_PARTS = MLP_EPI_WARPS / 4;
+constexpr int MLP_EPI_THREADS = MLP_EPI_WARPS * 32;
+constexpr int MLP_THREADS = 64 + MLP_EPI_THREADS;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int MLP_STAGES = 4;
 constexpr uint32_t MLP_STAGE_BYTES = 2 * TC_A_BYTES;          // [A 16 KB | W half-tile <= 128 rows 16 KB]
 constexpr uint32_t MLP_H_BYTES = 4 * TC_A_BYTES;              // 128 rows x 256 cols bf16 = 4 k-blocks of 16 KB
@@ -778,13 +800,14 @@ struct MlpArgs {
   int N[MLP_MAX_LAYERS];         // packed N of layer l (multiple of 16)
   int bn[MLP_MAX_LAYERS];        // N-tile width of layer l (hidden: = N <= 256)
   int ntile[MLP_MAX_LAYERS];
+  int boff[MLP_MAX_LAYERS];      // offset of layer l's bias vector in the resident smem copy (prefix sums of N)
   const float* bias[MLP_MAX_LAYERS];
   EpiParams ep;                  // coupling epilogue of the last layer
   unsigned long long* trace;     // debug timeline (see usf_debug_tc_trace); events use tile = (m_tile << 4) | gemm index
 };
 
 template <bool DBG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(MLP_THREADS, 1)
 usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ MlpMaps maps, MlpArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -808,9 +831,9 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 16);
+      mbar_init(tempty_bar(a), 2 * MLP_EPI_WARPS);
     }
-    mbar_init(hready_bar, 16);   // 8 epilogue warps of each CTA of the pair
+    mbar_init(hready_bar, 2 * MLP_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     for (int l = 0; l < args.L; ++l)
@@ -915,139 +938,131 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..9), both CTAs
+    // ------------------------------------------------------------------ epilogue warps (2..), both CTAs
     const int lane_grp = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;   // which of the MLP_EPI_PARTS column interleaves this warp takes
     const int et = (int)threadIdx.x - 64;
     const EpiParams& ep = args.ep;
     float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));
     uint4* hp = reinterpret_cast<uint4*>(smem_raw + (h_base - smem_u32(smem_raw)));   // H as uint4[kb][128 rows][8 pieces]
     const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;   // else: additive
     const int rloc = lane_grp * 32 + lane;           // row within this CTA's 128-row tile
+    const uint32_t k1h2 = coupling_k1(ep.clamp, ep.mode == EPI_COUPLING_INV);
+    // every layer's bias vector stays in shared memory for the whole kernel (sum of N <= 3 * TC_EPI_COLS, host-checked)
+    for (int l = 0; l < L; ++l)
+      for (int i = et; i < args.N[l]; i += MLP_EPI_THREADS) epi[args.boff[l] + i] = args.bias[l][i];
+    asm volatile("bar.sync 1, %0;" ::"n"(MLP_EPI_THREADS) : "memory");
     int a = 0;
     uint32_t aph = 0;
+    const int ntl = args.ntile[L - 1];
     for (int t = unit; t < args.m_tiles; t += num_units) {
       const int64_t row = (int64_t)(t * 2 + (int)cta_rank) * TC_BM + rloc;
       const bool rvalid = row < args.M;
-      for (int l = 0; l < L; ++l) {
-        const bool last = l == L - 1;
-        for (int nt = 0; nt < args.ntile[l]; ++nt) {
-          const int n0 = nt * args.bn[l];
-          int width = args.N[l] - n0;
-          if (width > args.bn[l]) width = args.bn[l];
-          float* ev = epi + a * 768;
-          ev[et] = (et < width) ? args.bias[l][n0 + et] : 0.f;
-          uint4 uq[8];
-          if (last) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = (2 * i + half) * 16;
-              const int coord0 = nt * ep.C + c;
-              if (rvalid && c < ep.C && coord0 + 16 <= ep.Db) {
-                ld_global_256(reinterpret_cast<const uint16_t*>(ep.ub) + row * ep.ldub + coord0, uq[2 * i], uq[2 * i + 1]);
-              }
-            }
+      // accumulator hand-over: wait until the MMAs of the next GEMM of the chain are complete / give the buffer back
+      auto acquire = [&](int gi) -> bool {
+        tc_trace<DBG>(trb, trn, gi, 0);
+        const bool ok = mbar_wait(tfull_bar(a), aph);
+        tc_trace<DBG>(trb, trn, gi, 2);
+        if (ok) tc_fence_after();
+        return ok;
+      };
+      auto release = [&](int gi, bool hidden) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(tempty_bar(a));
+          else mbar_arrive_cluster(tempty_bar(a), 0);
+          if (hidden) {            // this warp's part of the hidden tile is in place (in this CTA's smem)
+            if (cta_rank == 0) mbar_arrive(hready_bar);
+            else mbar_arrive_cluster(hready_bar, 0);
           }
-          const int gi = (t << 4) | (l * 4 + nt);
-          tc_trace<DBG>(trb, trn, gi, 0);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const bool ok = mbar_wait(tfull_bar(a), aph);
-          tc_trace<DBG>(trb, trn, gi, 2);
-          if (ok) {
-            tc_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
-            if (!last) {
-              // hidden layer: bias + ReLU -> bf16 -> operand-A layout of the next layer (in place in shared memory)
-              for (int c = half * 16; c < width; c += 32) {
-                float v[16];
-                tmem_ld16(t_base + c, v);
-                tmem_ld_wait();
-                const float4* bv = reinterpret_cast<const float4*>(ev + c);
+        }
+        tc_trace<DBG>(trb, trn, gi, 3);
+      };
+      auto advance = [&]() {
+        a ^= 1;
+        if (a == 0) aph ^= 1u;
+      };
+      // the first coupling chunk's coordinates travel while the hidden layers run
+      uint4 cq0 = make_uint4(0, 0, 0, 0), cq1 = cq0;
+      cpl_load_u(ep, row, rvalid, half * 16, cq0, cq1);
+
+      // ---- hidden layers: bias + ReLU -> bf16 -> operand-A layout of the next layer (in place in shared memory)
+      for (int l = 0; l + 1 < L; ++l) {
+        const int width = args.N[l];
+        const float* ev = epi + args.boff[l];
+        const int gi = (t << 4) | (l * 4);
+        if (acquire(gi)) {
+          const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+          for (int c = half * 16; c < width; c += 16 * MLP_EPI_PARTS) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            const float4* bv = reinterpret_cast<const float4*>(ev + c);
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 b4 = bv[j4];
-                  v[4 * j4] = fmaxf(v[4 * j4] + b4.x, 0.f);
-                  v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b4.y, 0.f);
-                  v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b4.z, 0.f);
-                  v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b4.w, 0.f);
-                }
-                uint4 q0, q1;
-                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-                const int kb = c >> 6, p = (c & 63) >> 3;    // k-block of 64 columns, 16-byte piece within the 128-byte row
-                uint4* rowp = hp + (size_t)kb * (TC_A_BYTES / 16) + rloc * 8;
-                rowp[p ^ (rloc & 7)] = q0;
-                rowp[(p + 1) ^ (rloc & 7)] = q1;
-              }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-            } else if (is_cpl) {
-              const int C = ep.C;
-              float lsum = 0.f;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int c = (2 * i + half) * 16;
-                if (c < C) {
-                  float sv[16], tv[16];
-                  tmem_ld16(t_base + c, sv);
-                  tmem_ld16(t_base + C + c, tv);
-                  tmem_ld_wait();
-                  const int coord0 = nt * C + c;
-                  if (rvalid && coord0 < ep.Db) {
-                    uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
-                    float u[16];
-                    const bool full = coord0 + 16 <= ep.Db;
-                    if (full) {
-                      unpack_bf16x8(uq[2 * i], u);
-                      unpack_bf16x8(uq[2 * i + 1], u + 8);
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 16; ++j)
-                        u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) : 0.f;
-                    }
-                    float y[16];
-                    const int nvalid = ep.Db - coord0;
-                    if (ep.mode == EPI_COUPLING_INV)
-                      coupling_chunk16<true>(sv, tv, ev + c, ev + C + c, -ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
-                    else
-                      coupling_chunk16<false>(sv, tv, ev + c, ev + C + c, ep.clamp * 1.4426950408889634f, u, y, lsum, nvalid);
-                    if (full) {
-                      uint4 q0, q1;
-                      q0.x = pack_bf16x2(y[0], y[1]);   q0.y = pack_bf16x2(y[2], y[3]);
-                      q0.z = pack_bf16x2(y[4], y[5]);   q0.w = pack_bf16x2(y[6], y[7]);
-                      q1.x = pack_bf16x2(y[8], y[9]);   q1.y = pack_bf16x2(y[10], y[11]);
-                      q1.z = pack_bf16x2(y[12], y[13]); q1.w = pack_bf16x2(y[14], y[15]);
-                      st_global_256(up, q0, q1);
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 16; ++j)
-                        if (coord0 + j < ep.Db) up[j] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
-                    }
-                  }
-                }
-              }
-              if (rvalid && ep.row_acc != nullptr)
-                atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
-            } else {   // additive coupling: tile = [t(C)]
-              additive_tile(t_base, ep, ev, uq, half, nt, row, rvalid);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = bv[j4];
+              v[4 * j4] = fmaxf(v[4 * j4] + b4.x, 0.f);
+              v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b4.y, 0.f);
+              v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b4.z, 0.f);
+              v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b4.w, 0.f);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (cta_rank == 0) mbar_arrive(tempty_bar(a));
-              else mbar_arrive_cluster(tempty_bar(a), 0);
-              if (!last) {            // this warp's part of the hidden tile is in place (in this CTA's smem)
-                if (cta_rank == 0) mbar_arrive(hready_bar);
-                else mbar_arrive_cluster(hready_bar, 0);
-              }
-            }
-            tc_trace<DBG>(trb, trn, gi, 3);
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            const int kb = c >> 6, p = (c & 63) >> 3;    // k-block of 64 columns, 16-byte piece within the 128-byte row
+            uint4* rowp = hp + (size_t)kb * (TC_A_BYTES / 16) + rloc * 8;
+            rowp[p ^ (rloc & 7)] = q0;
+            rowp[(p + 1) ^ (rloc & 7)] = q1;
           }
-          a ^= 1;
-          if (a == 0) aph ^= 1u;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          release(gi, true);
+        }
+        advance();
+      }
+
+      // ---- last layer: coupling update of the transformed columns.  This warp walks its chunks of every [s|t] (or
+      //      [t]) tile in ONE rolled loop; the coordinates of the next chunk (possibly of the next tile) are requested
+      //      before the current chunk is processed, so their latency hides behind ~one chunk of work.
+      const float* evl = epi + args.boff[L - 1];
+      const int C = ep.C, bnl = args.bn[L - 1];
+      float lsum = 0.f;
+      if (half * 16 >= C) {
+        // no chunk of any tile belongs to this warp (narrow tiles): only hand the accumulators back
+        for (int nt = 0; nt < ntl; ++nt) {
+          const int gi = (t << 4) | ((L - 1) * 4 + nt);
+          if (acquire(gi)) release(gi, false);
+          advance();
+        }
+      } else {
+        int nt = 0, c = half * 16;
+        bool ok = true;
+        uint32_t t_tile = 0;
+        while (nt < ntl) {
+          int nc = c + 16 * MLP_EPI_PARTS, nnt = nt;
+          if (nc >= C) { nc = half * 16; nnt = nt + 1; }
+          uint4 nq0 = make_uint4(0, 0, 0, 0), nq1 = nq0;
+          if (nnt < ntl) cpl_load_u(ep, row, rvalid, nnt * C + nc, nq0, nq1);
+          const int gi = (t << 4) | ((L - 1) * 4 + nt);
+          if (c == half * 16) {   // first chunk of the tile
+            ok = acquire(gi);
+            t_tile = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+          }
+          if (ok) cpl_chunk_dispatch(ep.mode, t_tile, c, evl + nt * bnl, ep, k1h2, row, rvalid, nt * C + c, cq0, cq1, lsum);
+          if (nnt != nt) {        // last chunk of the tile
+            if (ok) release(gi, false);
+            advance();
+          }
+          cq0 = nq0;
+          cq1 = nq1;
+          c = nc;
+          nt = nnt;
         }
       }
+      if (is_cpl && rvalid && ep.row_acc != nullptr)
+        atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
     }
   }
 
@@ -1245,6 +1260,9 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
 bool tc_mlp_supported(int n_layers, const int* N, const int* K, int Da) {
   if (tc_cta_group() != 2 || n_layers < 2 || n_layers > MLP_MAX_LAYERS) return false;
   if (K[0] != Da || Da <= 0) return false;
+  int total_n = 0;
+  for (int l = 0; l < n_layers; ++l) total_n += N[l];
+  if (total_n > 3 * TC_EPI_COLS) return false;   // all bias vectors stay resident in shared memory
   for (int l = 0; l + 1 < n_layers; ++l)
     if (N[l] > 256 || (N[l] % 16) != 0 || K[l + 1] > N[l]) return false;
   static int off = -1;
@@ -1281,6 +1299,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
     args.bn[l] = last ? bn_last : N[l];
     args.ntile[l] = (int)ceil_div(N[l], args.bn[l]);
     args.bias[l] = bias[l];
+    args.boff[l] = l == 0 ? 0 : args.boff[l - 1] + N[l - 1];
     USF_CHECK_ARG((ldw[l] % 8) == 0 && (N[l] % 16) == 0 && (args.bn[l] % 16) == 0 && args.bn[l] <= TC_MAX_BN,
                   "tc_mlp_coupling: bad layer %d", l);
     rc = make_tmap(&maps.w[l], Wb[l], N[l], K[l], ldw[l], args.bn[l] / 2);
@@ -1306,7 +1325,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
   if (pairs > args.m_tiles) pairs = args.m_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(MLP_THREADS);
   cfg.dynamicSmemBytes = MLP_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -15,7 +15,7 @@ with torch.no_grad():
     for _ in range(3): flow.log_prob(x)
     torch.cuda.synchronize()
     # trace only a 1-block prefix: build a K=1 flow so that the LAST traced launch is the fused kernel
-    _lib.check(lib().usf_debug_tc_trace(2, None, 0))
+    _lib.check(lib().usf_debug_tc_trace(2 | (int(os.environ.get("CPL_DBG", "0")) << 16), None, 0))
     flow.log_prob(x)
     torch.cuda.synchronize()
 buf = (C.c_uint64 * (2 * 3 * CAP * 2))()
@@ -33,3 +33,9 @@ for cta in range(2):
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(roles, open("gpurun_out/mlp_trace.json", "w"))
 print({k: len(v) for k, v in roles.items()})
+t0 = min(v[2] for vs in roles.values() for v in vs)
+for name in ("cta0_role1", "cta0_role2", "cta1_role2"):
+    recs = roles[name]
+    tiles = sorted(set(r[0] >> 4 for r in recs))
+    for tl in tiles[1:3]:
+        print(name, "rowtile", tl, " ".join(f"g{t & 15}e{e}@{c - t0}" for t, e, c in recs if (t >> 4) == tl))
