@@ -783,10 +783,15 @@ constexpr int MLP_EPI_WARPS = 16;
 constexpr int MLP_EPI_PARTS = MLP_EPI_WARPS / 4;
 constexpr int MLP_EPI_THREADS = MLP_EPI_WARPS * 32;
 constexpr int MLP_THREADS = 64 + MLP_EPI_THREADS;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int MLP_STAGES = 4;
-constexpr uint32_t MLP_STAGE_BYTES = 2 * TC_A_BYTES;          // [A 16 KB | W half-tile <= 128 rows 16 KB]
-constexpr uint32_t MLP_H_BYTES = 4 * TC_A_BYTES;              // 128 rows x 256 cols bf16 = 4 k-blocks of 16 KB
-constexpr uint32_t MLP_SMEM_BYTES = MLP_STAGES * MLP_STAGE_BYTES + MLP_H_BYTES + TC_BAR_BYTES + TC_EPI_BYTES + 1024;
+// Operand ring: 9 slots of 16 KB, ONE TMA box per slot (128 activation rows, or this CTA's <= 128 weight rows, of one
+// 64-wide k-block).  Layers >= 2 stream only weights, so with [A|W] stage pairs half of the ring sat empty and only 4
+// k-blocks were in flight -- at the measured 2-3.5k-cycle loaded TMA latency that, not the MMA rate, set the pace of
+// the second and third layer (profiles/r2).  Layer 1 takes two slots per k-block, the others one.
+constexpr int MLP_SLOTS = 9;
+constexpr uint32_t MLP_SLOT_BYTES = TC_A_BYTES;
+constexpr int MLP_H_KB = 4;                                   // k-blocks of the hidden tile
+constexpr uint32_t MLP_H_BYTES = MLP_H_KB * TC_A_BYTES;       // 128 rows x 256 cols bf16 = 4 k-blocks of 16 KB
+constexpr uint32_t MLP_SMEM_BYTES = MLP_SLOTS * MLP_SLOT_BYTES + MLP_H_BYTES + TC_BAR_BYTES + TC_EPI_BYTES + 1024;
 
 struct MlpMaps {
   CUtensorMap w[MLP_MAX_LAYERS];
@@ -811,21 +816,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ MlpMaps maps, MlpArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t h_base = smem_base + MLP_STAGES * MLP_STAGE_BYTES;   // hidden activation tile (operand A of layers >= 2)
+  const uint32_t h_base = smem_base + MLP_SLOTS * MLP_SLOT_BYTES;   // hidden activation tile (operand A of layers >= 2)
   const uint32_t bar_base = h_base + MLP_H_BYTES;
   const uint32_t cta_rank = cluster_ctarank();
   const int unit = (int)(blockIdx.x >> 1), num_units = (int)(gridDim.x >> 1);
+  // barriers (8 bytes each): full[SLOTS], empty[SLOTS], tmem_full[2], tmem_empty[2], hready[H_KB]; then the tmem pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MLP_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MLP_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MLP_STAGES + 2 + a); };
-  const uint32_t hready_bar = bar_base + 8u * (2 * MLP_STAGES + 4);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * MLP_STAGES + 5);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MLP_SLOTS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MLP_SLOTS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MLP_SLOTS + 2 + a); };
+  auto hready_bar = [&](int kb) { return bar_base + 8u * (2 * MLP_SLOTS + 4 + kb); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * MLP_SLOTS + 4 + MLP_H_KB);
   const uint32_t epi_base = bar_base + TC_BAR_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < MLP_STAGES; ++s) {
+    for (int s = 0; s < MLP_SLOTS; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -833,7 +839,9 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * MLP_EPI_WARPS);
     }
-    mbar_init(hready_bar, 2 * MLP_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
+    // one per 64-column k-block of the hidden tile: the next layer's MMAs over k-block i start as soon as every
+    // epilogue warp of both CTAs has written its columns of that k-block
+    for (int kb = 0; kb < MLP_H_KB; ++kb) mbar_init(hready_bar(kb), 2 * MLP_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     for (int l = 0; l < args.L; ++l)
@@ -862,25 +870,28 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
+      // one box into the next free slot; the pair's bytes are accounted on the leader's barrier
+      auto load = [&](const CUtensorMap* tm, uint32_t bytes_per_cta, int c0, int c1) {
+        ok = mbar_wait(empty_bar(s), ph ^ 1u);
+        if (!ok) return;
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes_per_cta);
+          tma_load_2d_2sm(smem_base + s * MLP_SLOT_BYTES, tm, full_bar(s), c0, c1);
+        }
+        if (++s == MLP_SLOTS) { s = 0; ph ^= 1u; }
+      };
       for (int t = unit; t < args.m_tiles && ok; t += num_units) {
         const int a_row = (t * 2 + (int)cta_rank) * TC_BM;
         for (int l = 0; l < L && ok; ++l) {
           const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
-          const uint32_t tx = 2u * ((l == 0 ? TC_A_BYTES : 0u) + (uint32_t)(args.bn[l] >> 1) * TC_BK * 2);
+          const uint32_t w_bytes = (uint32_t)(args.bn[l] >> 1) * TC_BK * 2;
           for (int nt = 0; nt < args.ntile[l] && ok; ++nt) {
             int width = args.N[l] - nt * args.bn[l];
             if (width > args.bn[l]) width = args.bn[l];
             const int w_row = nt * args.bn[l] + (int)cta_rank * (width >> 1);
-            for (int kb = 0; kb < nkb; ++kb) {
-              ok = mbar_wait(empty_bar(s), ph ^ 1u);
-              if (!ok) break;
-              const uint32_t dst = smem_base + s * MLP_STAGE_BYTES;
-              if (elect_one()) {
-                if (cta_rank == 0) mbar_expect_tx(full_bar(s), tx);
-                if (l == 0) tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * TC_BK, a_row);
-                tma_load_2d_2sm(dst + TC_A_BYTES, &maps.w[l], full_bar(s), kb * TC_BK, w_row);
-              }
-              if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
+            for (int kb = 0; kb < nkb && ok; ++kb) {
+              if (l == 0) load(&tmA, TC_A_BYTES, kb * TC_BK, a_row);
+              if (ok) load(&maps.w[l], w_bytes, kb * TC_BK, w_row);
             }
           }
         }
@@ -892,6 +903,8 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0, hph = 0;
       bool ok = true;
+      const uint64_t desc_hi = make_smem_desc(0);
+      const uint32_t slot_lo0 = (smem_base & 0x3FFFFu) >> 4, h_lo0 = (h_base & 0x3FFFFu) >> 4;
       for (int t = unit; t < args.m_tiles && ok; t += num_units) {
         for (int l = 0; l < L && ok; ++l) {
           const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
@@ -904,29 +917,46 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             ok = mbar_wait(tempty_bar(a), aph ^ 1u);
             if (!ok) break;
             tc_trace<DBG>(trb, trn, gi, 1);
-            if (l > 0 && nt == 0) {      // operand A = the hidden tile written by the previous layer's epilogue (both CTAs)
-              ok = mbar_wait(hready_bar, hph);
-              if (!ok) break;
-              hph ^= 1u;
-            }
-            tc_trace<DBG>(trb, trn, gi, 2);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
             for (int kb = 0; kb < nkb; ++kb) {
+              uint32_t a_lo;
+              int sa = -1;
+              if (l == 0) {                 // operand A streams through the ring (its own slot)
+                ok = mbar_wait(full_bar(s), ph);
+                if (!ok) break;
+                sa = s;
+                a_lo = slot_lo0 + (uint32_t)s * (MLP_SLOT_BYTES >> 4);
+                if (++s == MLP_SLOTS) { s = 0; ph ^= 1u; }
+              } else {                      // operand A = k-block kb of the hidden tile (written by the previous epilogue)
+                if (nt == 0) {
+                  ok = mbar_wait(hready_bar(kb), hph);
+                  if (!ok) break;
+                  tc_fence_after();
+                }
+                a_lo = h_lo0 + (uint32_t)kb * (TC_A_BYTES >> 4);
+              }
               ok = mbar_wait(full_bar(s), ph);
               if (!ok) break;
-              const uint32_t slot = smem_base + s * MLP_STAGE_BYTES;
-              const uint32_t a_addr = l == 0 ? slot : h_base + (uint32_t)kb * TC_A_BYTES;
+              if (kb == 0) tc_trace<DBG>(trb, trn, gi, 2);
               int krem = args.K[l] - kb * TC_BK;
               if (krem > TC_BK) krem = TC_BK;
               const int ksteps = (krem + TC_UMMA_K - 1) / TC_UMMA_K;
               if (elect_one()) {
-                const uint64_t ad0 = make_smem_desc(a_addr), bd0 = make_smem_desc(slot + TC_A_BYTES);
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                const uint64_t ad0 = desc_hi | (uint64_t)a_lo;
+                const uint64_t bd0 = desc_hi | (uint64_t)(slot_lo0 + (uint32_t)s * (MLP_SLOT_BYTES >> 4));
+                if (ksteps == TC_BK / TC_UMMA_K) {
+#pragma unroll
+                  for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+                    umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                } else {
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16_2sm(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                if (sa >= 0) umma_commit_2sm(empty_bar(sa));
                 umma_commit_2sm(empty_bar(s));
               }
-              if (++s == MLP_STAGES) { s = 0; ph ^= 1u; }
+              if (++s == MLP_SLOTS) { s = 0; ph ^= 1u; }
             }
             if (!ok) break;
             if (elect_one()) umma_commit_2sm(tfull_bar(a));
@@ -934,6 +964,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             a ^= 1;
             if (a == 0) aph ^= 1u;
           }
+          if (l > 0) hph ^= 1u;   // every hready barrier completed exactly once for this layer
         }
       }
     }
@@ -972,10 +1003,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         if (lane == 0) {
           if (cta_rank == 0) mbar_arrive(tempty_bar(a));
           else mbar_arrive_cluster(tempty_bar(a), 0);
-          if (hidden) {            // this warp's part of the hidden tile is in place (in this CTA's smem)
-            if (cta_rank == 0) mbar_arrive(hready_bar);
-            else mbar_arrive_cluster(hready_bar, 0);
-          }
+          (void)hidden;
         }
         tc_trace<DBG>(trb, trn, gi, 3);
       };
@@ -994,31 +1022,50 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int gi = (t << 4) | (l * 4);
         if (acquire(gi)) {
           const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
-          for (int c = half * 16; c < width; c += 16 * MLP_EPI_PARTS) {
-            float v[16];
-            tmem_ld16(t_base + c, v);
-            tmem_ld_wait();
-            const float4* bv = reinterpret_cast<const float4*>(ev + c);
+          // chunk i of this warp = columns [16*part + 64*i, +16): one 16-byte-pair piece of k-block i of the next
+          // layer's operand A.  After each chunk the warp publishes its part of that k-block (hready[i]), so the MMA
+          // warp can start the next layer on k-block 0 while the later k-blocks are still being converted.
+          const int nkb_h = (width + TC_BK - 1) / TC_BK;
+          for (int i = 0; i < nkb_h; ++i) {
+            const int c = half * 16 + i * TC_BK;
+            if (c < width) {   // warp-uniform
+              float v[16];
+              tmem_ld16(t_base + c, v);
+              tmem_ld_wait();
+              const float4* bv = reinterpret_cast<const float4*>(ev + c);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 b4 = bv[j4];
-              v[4 * j4] = fmaxf(v[4 * j4] + b4.x, 0.f);
-              v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b4.y, 0.f);
-              v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b4.z, 0.f);
-              v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b4.w, 0.f);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = bv[j4];
+                v[4 * j4] = fmaxf(v[4 * j4] + b4.x, 0.f);
+                v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + b4.y, 0.f);
+                v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + b4.z, 0.f);
+                v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + b4.w, 0.f);
+              }
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              const int p = (c & 63) >> 3;    // 16-byte piece within the 128-byte row of k-block i
+              uint4* rowp = hp + (size_t)i * (TC_A_BYTES / 16) + rloc * 8;
+              rowp[p ^ (rloc & 7)] = q0;
+              rowp[(p + 1) ^ (rloc & 7)] = q1;
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             }
-            uint4 q0, q1;
-            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-            const int kb = c >> 6, p = (c & 63) >> 3;    // k-block of 64 columns, 16-byte piece within the 128-byte row
-            uint4* rowp = hp + (size_t)kb * (TC_A_BYTES / 16) + rloc * 8;
-            rowp[p ^ (rloc & 7)] = q0;
-            rowp[(p + 1) ^ (rloc & 7)] = q1;
+            __syncwarp();
+            if (lane == 0) {
+              if (cta_rank == 0) mbar_arrive(hready_bar(i));
+              else mbar_arrive_cluster(hready_bar(i), 0);
+            }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-          release(gi, true);
+          // k-blocks this layer does not have complete too (their phase must flip once per layer)
+          if (lane == 0) {
+            for (int i = nkb_h; i < MLP_H_KB; ++i) {
+              if (cta_rank == 0) mbar_arrive(hready_bar(i));
+              else mbar_arrive_cluster(hready_bar(i), 0);
+            }
+          }
+          release(gi, false);
         }
         advance();
       }
