@@ -129,6 +129,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtenso
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -261,23 +267,9 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4& lo, const ui
 //   both:              y = fma(u - sgn*tt, e, (1 - sgn)*tt)
 // A single copy of this code serves every mode (the epilogue warps walk it in a rolled loop): with the 16-way
 // unrolled per-mode variants the hot epilogue was ~32 KB of SASS and spent 40-50 % of its samples in instruction
-// fetch (ncu stall_no_inst, profiles/r2).  tanh / ex2 take f16 pairs (th in [-1,1], e in [2^-7.3, 2^7.3]: 11-bit
-// significands, finer than the bf16 activations they multiply); the log-det accumulates tanh in fp32.  Padded
-// coordinates have zero weight rows and zero bias, so s = 0 and tanh(0) = 0 adds nothing to the log-det.
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
-// +-clamp * log2(e) as a packed f16x2 constant
-__device__ __forceinline__ uint32_t coupling_k1(float clamp, bool inv) {
-  const float k = (inv ? -clamp : clamp) * 1.4426950408889634f;
-  return pack_f16x2(k, k);
-}
-
+// fetch (ncu stall_no_inst, profiles/r2).  tanh.approx / ex2.approx in fp32 (2 MUFU per coordinate; the MUFU pipe
+// delivers 16 results/clk/SM).  Padded coordinates have zero weight rows and zero bias, so s = 0 and tanh(0) = 0
+// adds nothing to the log-det.
 // request the 16 transformed coordinates of one chunk (32 bytes, one LDG.256); partial / invalid chunks load nothing
 __device__ __forceinline__ void cpl_load_u(const EpiParams& ep, int64_t row, bool rvalid, int coord0, uint4& q0, uint4& q1) {
   if (rvalid && coord0 + 16 <= ep.Db)
@@ -290,7 +282,7 @@ __device__ __forceinline__ void cpl_load_u(const EpiParams& ep, int64_t row, boo
 // -> FFMA links); AFFINE / INV are compile-time so the executed path carries no selects (only one instantiation runs
 // in any launch, so the instruction-cache footprint stays one chunk body).
 template <bool AFFINE, bool INV>
-__device__ __forceinline__ void cpl_chunk(uint32_t t_tile, int c, const float* ev, const EpiParams& ep, uint32_t k1h2,
+__device__ __forceinline__ void cpl_chunk(uint32_t t_tile, int c, const float* ev, const EpiParams& ep, float k1,
                                           int64_t row, bool rvalid, int coord0, const uint4& q0, const uint4& q1, float& lsum) {
   const int C = ep.C;
   float sv[16], tv[16];
@@ -325,35 +317,19 @@ __device__ __forceinline__ void cpl_chunk(uint32_t t_tile, int c, const float* e
       const float4 b = bs4[j4];
       sv[4 * j4] += b.x; sv[4 * j4 + 1] += b.y; sv[4 * j4 + 2] += b.z; sv[4 * j4 + 3] += b.w;
     }
-    uint32_t th2[8], e2[8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p) th2[p] = pack_f16x2(sv[2 * p], sv[2 * p + 1]);
-#pragma unroll
-    for (int p = 0; p < 8; ++p) asm("tanh.approx.f16x2 %0, %1;" : "=r"(th2[p]) : "r"(th2[p]));
-#pragma unroll
-    for (int p = 0; p < 8; ++p) asm("mul.f16x2 %0, %1, %2;" : "=r"(e2[p]) : "r"(th2[p]), "r"(k1h2));
-#pragma unroll
-    for (int p = 0; p < 8; ++p) asm("ex2.approx.f16x2 %0, %1;" : "=r"(e2[p]) : "r"(e2[p]));
-    // log-det: tanh values are summed in pairs in f16 (|sum| <= 2: absolute rounding error <= 2^-11), then in fp32
+    // fp32 MUFU throughout: the packed f16x2 forms issue one MUFU.F16 per half (measured 16 results/clk/SM either
+    // way, scripts/ubench/pipe_rates.cu), so they save nothing and cost 2x in log_prob error.
     float part = 0.f;
 #pragma unroll
-    for (int p = 0; p < 8; p += 2) {
-      uint32_t pr;
-      asm("add.f16x2 %0, %1, %2;" : "=r"(pr) : "r"(th2[p]), "r"(th2[p + 1]));
-      const float2 f = unpack_f16x2(pr);
-      part += f.x + f.y;
-    }
+    for (int j = 0; j < 16; ++j) sv[j] = fast_tanh(sv[j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) part += sv[j];
     lsum += part;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const float2 e = unpack_f16x2(e2[p]);
-      if (INV) {
-        u[2 * p] = (u[2 * p] - tv[2 * p]) * e.x;
-        u[2 * p + 1] = (u[2 * p + 1] - tv[2 * p + 1]) * e.y;
-      } else {
-        u[2 * p] = fmaf(u[2 * p], e.x, tv[2 * p]);
-        u[2 * p + 1] = fmaf(u[2 * p + 1], e.y, tv[2 * p + 1]);
-      }
+    for (int j = 0; j < 16; ++j) {
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(k1 * sv[j]));
+      u[j] = INV ? (u[j] - tv[j]) * e : fmaf(u[j], e, tv[j]);
     }
   } else {
 #pragma unroll
@@ -375,12 +351,12 @@ __device__ __forceinline__ void cpl_chunk(uint32_t t_tile, int c, const float* e
 
 // runtime mode -> the one compile-time instantiation this launch executes
 __device__ __forceinline__ void cpl_chunk_dispatch(int mode, uint32_t t_tile, int c, const float* ev, const EpiParams& ep,
-                                                   uint32_t k1h2, int64_t row, bool rvalid, int coord0, const uint4& q0,
+                                                   float k1, int64_t row, bool rvalid, int coord0, const uint4& q0,
                                                    const uint4& q1, float& lsum) {
-  if (mode == EPI_COUPLING_INV) cpl_chunk<true, true>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
-  else if (mode == EPI_COUPLING_FWD) cpl_chunk<true, false>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
-  else if (mode == EPI_ADD_INV) cpl_chunk<false, true>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
-  else cpl_chunk<false, false>(t_tile, c, ev, ep, k1h2, row, rvalid, coord0, q0, q1, lsum);
+  if (mode == EPI_COUPLING_INV) cpl_chunk<true, true>(t_tile, c, ev, ep, k1, row, rvalid, coord0, q0, q1, lsum);
+  else if (mode == EPI_COUPLING_FWD) cpl_chunk<true, false>(t_tile, c, ev, ep, k1, row, rvalid, coord0, q0, q1, lsum);
+  else if (mode == EPI_ADD_INV) cpl_chunk<false, true>(t_tile, c, ev, ep, k1, row, rvalid, coord0, q0, q1, lsum);
+  else cpl_chunk<false, false>(t_tile, c, ev, ep, k1, row, rvalid, coord0, q0, q1, lsum);
 }
 
 struct TcArgs {
@@ -595,7 +571,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
     const bool is_add = ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD;
     const bool is_base = ep.mode == EPI_BASE_NORMAL || ep.mode == EPI_BASE_LAPLACE;
-    const uint32_t k1h2 = coupling_k1(ep.clamp, ep.mode == EPI_COUPLING_INV);
+    const float k1 = (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * 1.4426950408889634f;   // +-clamp * log2(e)
     // per-column vectors: staged once for the whole kernel when they fit, else re-staged per tile
     const bool resident = args.N <= TC_EPI_COLS;
     if (resident) {
@@ -714,7 +690,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int c = half * 16; c < ep.C; c += 32) {
             uint4 nq0 = make_uint4(0, 0, 0, 0), nq1 = nq0;
             if (c + 32 < ep.C) cpl_load_u(ep, row, rvalid, nt * ep.C + c + 32, nq0, nq1);
-            cpl_chunk_dispatch(ep.mode, t_base, c, ev, ep, k1h2, row, rvalid, nt * ep.C + c, cq0, cq1, lsum);
+            cpl_chunk_dispatch(ep.mode, t_base, c, ev, ep, k1, row, rvalid, nt * ep.C + c, cq0, cq1, lsum);
             cq0 = nq0;
             cq1 = nq1;
           }
@@ -880,8 +856,14 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
         if (++s == MLP_SLOTS) { s = 0; ph ^= 1u; }
       };
+      const int nkb0 = (args.K[0] + TC_BK - 1) / TC_BK;
       for (int t = unit; t < args.m_tiles && ok; t += num_units) {
         const int a_row = (t * 2 + (int)cta_rank) * TC_BM;
+        // All CTAs run their first layer at about the same time, and its activation rows come from HBM: that phase
+        // was HBM-bound (~5.4 TB/s) while HBM idled through the rest of the row tile.  The NEXT row tile's rows are
+        // therefore requested into L2 while this tile's last layer streams its (L2-resident) weights.
+        int pf_kb = 0;
+        const int pf_row = t + num_units < args.m_tiles ? ((t + num_units) * 2 + (int)cta_rank) * TC_BM : -1;
         for (int l = 0; l < L && ok; ++l) {
           const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
           const uint32_t w_bytes = (uint32_t)(args.bn[l] >> 1) * TC_BK * 2;
@@ -892,6 +874,10 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             for (int kb = 0; kb < nkb && ok; ++kb) {
               if (l == 0) load(&tmA, TC_A_BYTES, kb * TC_BK, a_row);
               if (ok) load(&maps.w[l], w_bytes, kb * TC_BK, w_row);
+              if (l == L - 1 && pf_row >= 0 && pf_kb < nkb0) {
+                if (elect_one()) tma_prefetch_2d(&tmA, pf_kb * TC_BK, pf_row);
+                ++pf_kb;
+              }
             }
           }
         }
@@ -978,7 +964,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint4* hp = reinterpret_cast<uint4*>(smem_raw + (h_base - smem_u32(smem_raw)));   // H as uint4[kb][128 rows][8 pieces]
     const bool is_cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;   // else: additive
     const int rloc = lane_grp * 32 + lane;           // row within this CTA's 128-row tile
-    const uint32_t k1h2 = coupling_k1(ep.clamp, ep.mode == EPI_COUPLING_INV);
+    const float k1 = (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * 1.4426950408889634f;   // +-clamp * log2(e)
     // every layer's bias vector stays in shared memory for the whole kernel (sum of N <= 3 * TC_EPI_COLS, host-checked)
     for (int l = 0; l < L; ++l)
       for (int i = et; i < args.N[l]; i += MLP_EPI_THREADS) epi[args.boff[l] + i] = args.bias[l][i];
@@ -1097,7 +1083,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             ok = acquire(gi);
             t_tile = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
           }
-          if (ok) cpl_chunk_dispatch(ep.mode, t_tile, c, evl + nt * bnl, ep, k1h2, row, rvalid, nt * C + c, cq0, cq1, lsum);
+          if (ok) cpl_chunk_dispatch(ep.mode, t_tile, c, evl + nt * bnl, ep, k1, row, rvalid, nt * C + c, cq0, cq1, lsum);
           if (nnt != nt) {        // last chunk of the tile
             if (ok) release(gi, false);
             advance();
