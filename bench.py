@@ -353,15 +353,15 @@ def main():
             flow.precision = args.precision
 
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
-    train_ms, train_B, train_steps = float("nan"), args.train_rows, args.train_steps
+    train_ms, train_B, train_steps, train_graph = float("nan"), args.train_rows, args.train_steps, False
     if train_steps > 0:
         from nf4ad_b200.parallel import DataParallelTrainer
         tflow = build_flow(P, dev).train()
-        opt = torch.optim.Adam(tflow.parameters(), lr=1e-4)
+        opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True)   # the step replays as one CUDA graph
         trainer = DataParallelTrainer(tflow, opt)
         trainer.broadcast_parameters()
         xb = x[:train_B]
-        for _ in range(3):
+        for _ in range(5):          # 3 eager steps + capture + first replay (single rank), all untimed
             trainer.step(xb)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,6 +372,7 @@ def main():
         barrier()
         train_ms = g0.elapsed_time(g1)
         assert bool(torch.isfinite(loss))
+        train_graph = trainer.graph_replays > 0
         del tflow, opt, trainer
     t = torch.tensor([ms_total, e2e_ms, train_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -414,7 +415,7 @@ def main():
         if sweep:
             line["sweep"] = sweep
         if train_steps > 0:
-            line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam, fp32 path)",
+            line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam, fp32 path)", "graph_replay": bool(train_graph),
                              "value": train_B * world * train_steps / (train_ms * 1e-3), "unit": "samples/s",
                              "batch_per_gpu": train_B, "steps": train_steps, "ms_per_step": train_ms / train_steps}
         if world == 1 and not args.no_cpu_baseline:

@@ -9,9 +9,11 @@ mirror adds is the B200-specific plumbing around the same semantics:
   * `predict_score` streams pinned host rows in chunks whose H2D copies overlap the fused launch chain
     (`ShardedScorer.predict_score_host`) instead of one blocking copy of the whole test set
     (`adbench_wrapper.py:419`), and shards rows over the GPUs of a `torch.distributed` job;
-  * `fit` keeps the training set on the device (one H2D copy), draws the shuffled mini-batches there, and
-    reads the loss back once per epoch instead of once per step (`adbench_wrapper.py:392` syncs every
-    step); under `torch.distributed` it runs data parallel with one gradient all-reduce per step.
+  * `fit` keeps the training set on the device (one H2D copy), draws the shuffled mini-batches there, reads
+    the loss back once per epoch instead of once per step (`adbench_wrapper.py:392` syncs every step), and
+    replays the whole step (forward, backward kernels, Adam) as ONE CUDA graph per batch shape after a few
+    eager steps (`DataParallelTrainer`); under `torch.distributed` it runs data parallel with one gradient
+    all-reduce per step.
 """
 from typing import Optional
 
@@ -47,7 +49,7 @@ class ADBenchFlow:
             print(f"Device: {self.device}")
         X = X.to(self.device)
         n = X.shape[0]
-        opt = torch.optim.Adam(self.flow_model.parameters(), lr=self.lr)
+        opt = torch.optim.Adam(self.flow_model.parameters(), lr=self.lr, capturable=True)   # device-side step counters: the step can replay as a CUDA graph
         trainer = DataParallelTrainer(self.flow_model, opt, gradient_clip=self.gradient_clip)
         trainer.broadcast_parameters()
         self.flow_model.train()

@@ -5,6 +5,8 @@ replicated, so there is NO collective on the data path -- only one all-gather of
 scores.  Training is data parallel: one flat all-reduce (sum) of the gradients per step, then the same
 optimizer step on every rank.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -102,13 +104,31 @@ class ShardedScorer:
 class DataParallelTrainer:
     """Data-parallel NLL training step (`adbench_wrapper.py:375-392`): per-rank micro-batch,
     gradients summed with ONE flat all-reduce and divided by the world size (loss is a per-rank mean),
-    global-norm clipping after the reduction, identical optimizer step on every rank."""
+    global-norm clipping after the reduction, identical optimizer step on every rank.
 
-    def __init__(self, flow, optimizer, group=None, gradient_clip=None, loss_fn=None):
+    CUDA-graph replay.  At the reference's own batch sizes (32-64) the step is bound by the
+    host: ~300 autograd nodes and kernel launches cost 5-16 ms per step while the kernels need a fraction of
+    that.  After `graph_warmup` eager steps with a given batch shape the whole step -- forward, the hand-written
+    backward kernels, clipping, the optimizer update -- is captured once into a CUDA graph and every later step
+    with that shape is one `cudaGraphLaunch` on a static input buffer.  Used when there is a single rank, the
+    parameters live on a CUDA device and the optimizer was built with `capturable=True` (its step counters live
+    on the device); anything else, and any shape seen fewer than `graph_warmup` times, runs eagerly."""
+
+    def __init__(self, flow, optimizer, group=None, gradient_clip=None, loss_fn=None, use_graph=None,
+                 graph_warmup=3):
         self.flow, self.opt, self.group, self.clip = flow, optimizer, group, gradient_clip
         self.loss_fn = loss_fn or (lambda batch: -flow.log_prob(batch).mean())
         self.rank, self.world = _world(group)
         self.params = [p for p in flow.parameters() if p.requires_grad]
+        capturable = all(g.get("capturable", False) for g in getattr(optimizer, "param_groups", [])) \
+            if getattr(optimizer, "param_groups", None) else False
+        on_cuda = bool(self.params) and all(p.is_cuda for p in self.params)
+        if use_graph is None:
+            use_graph = os.environ.get("USF_TRAIN_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph) and self.world == 1 and capturable and on_cuda
+        self.graph_warmup = int(graph_warmup)
+        self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss]
+        self.graph_replays = 0
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -127,7 +147,7 @@ class DataParallelTrainer:
         for g, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
             g.copy_(new)
 
-    def step(self, batch):
+    def _eager_step(self, batch):
         self.opt.zero_grad(set_to_none=True)
         loss = self.loss_fn(batch)
         loss.backward()
@@ -136,3 +156,36 @@ class DataParallelTrainer:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip)
         self.opt.step()
         return loss.detach()
+
+    def _capture(self, batch):
+        static_x = batch.detach().clone()
+        graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss = self.loss_fn(static_x)
+            loss.backward()
+            if self.clip is not None:
+                torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+            self.opt.step()
+            static_loss = loss.detach()
+        return graph, static_x, static_loss
+
+    def step(self, batch):
+        if not self.use_graph or not batch.is_cuda:
+            return self._eager_step(batch)
+        key = (tuple(batch.shape), batch.dtype, batch.device.index)
+        slot = self._graphs.setdefault(key, [0, None, None, None])
+        if slot[1] is None:
+            slot[0] += 1
+            if slot[0] <= self.graph_warmup:          # real (eager) steps; they also initialise the optimizer state
+                return self._eager_step(batch)
+            try:
+                slot[1], slot[2], slot[3] = self._capture(batch)     # records the step, does not run it
+            except Exception:
+                self.use_graph = False                 # e.g. a conditioner that is not capture-safe
+                torch.cuda.synchronize()
+                return self._eager_step(batch)
+        slot[2].copy_(batch)
+        slot[1].replay()
+        self.graph_replays += 1
+        return slot[3].clone()
