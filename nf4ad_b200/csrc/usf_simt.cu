@@ -291,10 +291,13 @@ int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, in
                     cudaStream_t stream) {
   if (M <= 0 || N <= 0) return USF_OK;
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  // Few output tiles (small batches, weight gradients of narrow layers): one 128x128 tile walks K serially at ~1 us
+  // per 16-wide step with most SMs idle, so K is split over up to ~one CTA per SM (>= 32 columns each) and the
+  // partial sums meet in atomics.
   int split = 1;
-  if (K >= 512 && tiles < num_sms()) {
-    split = (int)((2 * num_sms()) / tiles);
-    const int64_t max_split = ceil_div(K, 128);
+  if (K >= 64 && tiles * 2 <= num_sms()) {
+    split = (int)(num_sms() / tiles);
+    const int64_t max_split = ceil_div(K, 32);
     if (split > max_split) split = (int)max_split;
     if (split < 1) split = 1;
   }
@@ -864,10 +867,32 @@ extern "C" int usf_lu_pack(const float* L_raw, const float* U_raw, int64_t D, fl
   return USF_OK;
 }
 
+namespace usf {
+namespace {
+// y[r, c] = act(y[r, c] + bias[c]) in place: second phase of the split-K form of usf_linear
+__global__ void usf_bias_act_kernel(float* y, int64_t ldy, const float* __restrict__ bias, int relu, int64_t B, int64_t N) {
+  const int64_t total = B * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / N, c = i - r * N;
+    float v = y[r * ldy + c] + (bias != nullptr ? bias[c] : 0.f);
+    y[r * ldy + c] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+}  // namespace
+}  // namespace usf
+
 extern "C" int usf_linear(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, int relu,
                           float* y, int64_t ldy, int64_t B, int64_t N, int64_t K, usf_stream_t stream) {
   USF_CHECK_ARG(x && W && y, "usf_linear: null pointer");
   USF_CHECK_ARG(B >= 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N, "usf_linear: bad sizes");
+  if (B > 0 && K >= 64 && ceil_div(B, BM) * ceil_div(N, BN) * 2 <= num_sms()) {
+    // small problem: split-K GEMM (atomic partial sums) + a bias/activation pass, instead of a few serial tiles
+    int rc = simt_gemm_plain(x, ldx, 0, W, ldw, 0, B, N, K, y, ldy, 0, as_stream(stream));
+    if (rc) return rc;
+    usf_bias_act_kernel<<<ew_grid(B * N), 256, 0, as_stream(stream)>>>(y, ldy, bias, relu, B, N);
+    USF_LAUNCH_CHECK("usf_bias_act_kernel");
+    return USF_OK;
+  }
   EpiParams ep{};
   ep.mode = relu ? EPI_BIAS_RELU : EPI_BIAS;
   ep.bias = bias;

@@ -54,6 +54,7 @@ class Flow(torch.nn.Module):
         self.precision = _default_precision()   # "fp32" (<=1e-4 tier) or "bf16" (tcgen05, <=1e-2 tier)
         self.last_launches = 0                  # kernels enqueued by the last fused call
         self._compiled = {}
+        self._key_slots = None
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -69,14 +70,39 @@ class Flow(torch.nn.Module):
                 return l.mask.numel()
         raise ValueError("cannot infer the event dimension")
 
+    def _scan_key_slots(self):
+        """(owner dict, name) of every parameter / buffer / base-distribution tensor.  Walking the module tree costs
+        ~0.2 ms, comparable to a whole small-batch scoring call, so it is done once (and again whenever the module
+        is moved, re-moded or `invalidate_cache()`d) and `_weights_key` only looks the slots up."""
+        slots = []
+        for m in self.modules():
+            slots += [(m._parameters, k) for k, v in m._parameters.items() if v is not None]
+            slots += [(m._buffers, k) for k, v in m._buffers.items() if v is not None]
+        base, seen = self.base_distribution, set()
+        while base is not None and id(base) not in seen and not isinstance(base, torch.nn.Module):
+            seen.add(id(base))
+            slots += [(base.__dict__, k) for k, v in base.__dict__.items() if isinstance(v, torch.Tensor)]
+            base = getattr(base, "base_dist", None)
+        self._key_slots = slots
+        return slots
+
+    def invalidate_cache(self):
+        """Forget the packed weights and the parameter scan (call after replacing sub-modules of a built flow)."""
+        self._compiled = {}
+        self._key_slots = None
+
     def _weights_key(self):
-        key = [(p.data_ptr(), p._version) for p in self.parameters()]
-        key += [(b.data_ptr(), b._version) for b in self.buffers()]
-        base = self.base_distribution
-        for v in getattr(base, "__dict__", {}).values():
-            if isinstance(v, torch.Tensor):
-                key.append((v.data_ptr(), v._version))
+        slots = self.__dict__.get("_key_slots") or self._scan_key_slots()
+        key = []
+        for d, k in slots:
+            t = d.get(k)
+            key.append((id(t), t._version if t is not None else -1))
         return tuple(key)
+
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self._key_slots = None
+        return super().train(mode)
 
     def _stack(self, inverse, device):
         """Compiled (packed) stack for this direction / precision / weight version, or None."""
@@ -235,6 +261,7 @@ class Flow(torch.nn.Module):
                         base.__dict__[k] = fn(v)
                 base = getattr(base, "base_dist", None)
         self._compiled = {}
+        self._key_slots = None
         return out
 
     def to(self, *args, **kwargs):
