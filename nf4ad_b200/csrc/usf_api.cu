@@ -66,10 +66,12 @@ struct StackPlan {
   size_t act_bytes;   // one activation buffer for `rows` rows
   size_t hid_bytes;
   size_t acc_bytes;
+  size_t small_bytes;  // fp32 path: split-K accumulator for small batches (rows <= kSmallRows)
   size_t total;
 };
 
 constexpr int64_t kChunkRows = 131072;  // rows pushed through the stack per pass (bounds the workspace)
+constexpr int64_t kSmallRows = 2048;    // fp32 path: batches up to this size may use the split-K + epilogue-kernel GEMM form
 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -77,14 +79,17 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
   USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0, "stack: bad descriptor");
   USF_CHECK_ARG(st->n_blocks == 0 || st->blocks != nullptr, "stack: blocks pointer is null");
   USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16, "stack: unknown precision %d", precision);
-  int64_t wmax = st->D, hmax = 16;
+  int64_t wmax = st->D, hmax = 16, nmax = st->G_final.N;
   for (int b = 0; b < st->n_blocks; ++b) {
     const usf_block_desc& blk = st->blocks[b];
     USF_CHECK_ARG(blk.n_mlp >= 1 && blk.n_mlp <= USF_MAX_MLP, "stack: block %d has %d conditioner layers", b, blk.n_mlp);
     if (blk.G.N > wmax) wmax = blk.G.N;
     if (blk.G.K > wmax) wmax = blk.G.K;
-    for (int l = 0; l + 1 < blk.n_mlp; ++l)
-      if (blk.mlp[l].N > hmax) hmax = blk.mlp[l].N;
+    if (blk.G.N > nmax) nmax = blk.G.N;
+    for (int l = 0; l < blk.n_mlp; ++l) {
+      if (l + 1 < blk.n_mlp && blk.mlp[l].N > hmax) hmax = blk.mlp[l].N;
+      if (blk.mlp[l].N > nmax) nmax = blk.mlp[l].N;
+    }
   }
   if (st->G_final.K > wmax) wmax = st->G_final.K;
   const size_t esz = precision == USF_PREC_BF16 ? 2 : 4;
@@ -93,7 +98,8 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
   p->act_bytes = align256((size_t)rows * p->ld_act * esz);
   p->hid_bytes = align256((size_t)rows * p->ld_hid * esz);
   p->acc_bytes = align256((size_t)rows * sizeof(float));
-  p->total = 2 * p->act_bytes + 2 * p->hid_bytes + p->acc_bytes + 256;
+  p->small_bytes = (precision == USF_PREC_FP32 && rows <= kSmallRows) ? align256((size_t)rows * (size_t)nmax * sizeof(float)) : 0;
+  p->total = 2 * p->act_bytes + 2 * p->hid_bytes + p->acc_bytes + p->small_bytes + 256;
   return USF_OK;
 }
 
@@ -202,6 +208,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   uint8_t* act[2] = {base, base + p.act_bytes};
   uint8_t* hid[2] = {base + 2 * p.act_bytes, base + 2 * p.act_bytes + p.hid_bytes};
+  float* small = p.small_bytes ? reinterpret_cast<float*>(base + 2 * p.act_bytes + 2 * p.hid_bytes + p.acc_bytes) : nullptr;
 
   int launches = 0;
 
@@ -212,7 +219,8 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       return tc_gemm(reinterpret_cast<const uint16_t*>(A), lda, L.Wb, L.ldw, rows, L.N, L.K, bn, ep, s);
     }
     USF_CHECK_ARG(L.W != nullptr, "usf_stack_run: fp32 weights missing in descriptor");
-    return simt_gemm(reinterpret_cast<const float*>(A), lda, 0, L.W, L.ldw, 0, rows, L.N, L.K, ep, s);
+    return simt_gemm(reinterpret_cast<const float*>(A), lda, 0, L.W, L.ldw, 0, rows, L.N, L.K, ep, s, small,
+                     p.small_bytes / sizeof(float));
   };
 
   for (int64_t r0 = 0; r0 < B; r0 += kChunkRows) {

@@ -75,8 +75,10 @@ struct EpiParams {
 // ---- SIMT fp32 GEMM (usf_simt.cu) -------------------------------------------------------------
 // acc = A(MxK, lda) * W(NxK, ldw)^T with the epilogue above.  a_trans / w_trans select the
 // storage order: a_trans=0: A[m*lda+k]; a_trans=1: A[k*lda+m]; w_trans=0: W[n*ldw+k]; 1: W[k*ldw+n].
+// scratch (optional, scratch_floats >= M*N): enables the split-K + epilogue-kernel form for small batches.
 int simt_gemm(const float* A, int64_t lda, int a_trans, const float* W, int64_t ldw, int w_trans,
-              int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t stream);
+              int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t stream, float* scratch = nullptr,
+              size_t scratch_floats = 0);
 // Plain C (+)= alpha * A*W^T style GEMM used by the backward pass (no bias), fp32 out with ldc.
 int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, int64_t ldw, int w_trans,
                     int64_t M, int64_t N, int64_t K, float* Cout, int64_t ldc, int accumulate,

@@ -270,14 +270,76 @@ usf_simt_gemm_kernel(const float* __restrict__ A, int64_t lda, int a_trans, cons
 
 }  // namespace
 
+// Second phase of the small-batch form of the fused GEMM: the layer epilogue of usf_simt_gemm_kernel<true> applied to
+// an accumulator that a split-K launch left in global memory (acc: M x N, leading dimension N).  One warp per row.
+__global__ void usf_simt_epilogue_kernel(const float* __restrict__ acc, int64_t M, int64_t N, EpiParams ep) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const float* a = acc + r * N;
+  const int mode = ep.mode;
+  if (mode == EPI_BIAS || mode == EPI_BIAS_RELU) {
+    for (int64_t c = lane; c < N; c += 32) {
+      float v = a[c] + (ep.bias != nullptr ? ep.bias[c] : 0.f);
+      if (mode == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      st_act(ep.out, r * ep.ldo + c, ep.out_bf16, v);
+    }
+  } else if (mode == EPI_COUPLING_INV || mode == EPI_COUPLING_FWD) {
+    float lsum = 0.f;
+    for (int coord = lane; coord < ep.Db; coord += 32) {
+      const int64_t cs = (int64_t)(coord >> 6) * 128 + (coord & 63);   // tile = [s(64) | t(64)]
+      const float s = a[cs] + ep.bias[cs];
+      const float t = a[cs + 64] + ep.bias[cs + 64];
+      const float ls = ep.clamp * tanhf(s);
+      const int64_t idx = r * ep.ldub + coord;
+      const float u = ld_act(ep.ub, idx, ep.ub_bf16);
+      st_act(ep.ub, idx, ep.ub_bf16, (mode == EPI_COUPLING_INV) ? (u - t) * expf(-ls) : fmaf(u, expf(ls), t));
+      lsum += ls;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0 && ep.row_acc != nullptr) atomicAdd(ep.row_acc + r, mode == EPI_COUPLING_INV ? -lsum : lsum);
+  } else if (mode == EPI_ADD_INV || mode == EPI_ADD_FWD) {
+    for (int c = lane; c < ep.Db; c += 32) {
+      const float t = a[c] + ep.bias[c];
+      const int64_t idx = r * ep.ldub + c;
+      const float u = ld_act(ep.ub, idx, ep.ub_bf16);
+      st_act(ep.ub, idx, ep.ub_bf16, mode == EPI_ADD_INV ? u - t : u + t);
+    }
+  } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE
+    float lsum = 0.f;
+    for (int64_t c = lane; c < N; c += 32) {
+      const float z = a[c] + ep.bias[c];
+      if (ep.out != nullptr) st_act(ep.out, r * ep.ldo + c, ep.out_bf16, z);
+      if (ep.loc != nullptr) {
+        const float d = (z - ep.loc[c]) * ep.inv_scale[c];
+        lsum += (mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+      }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0 && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + r, lsum);
+  }
+}
+
 const char* const kSimtGemmKernelName = "usf_simt_gemm_kernel";
 
 int simt_gemm(const float* A, int64_t lda, int a_trans, const float* W, int64_t ldw, int w_trans,
-              int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t stream) {
+              int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t stream, float* scratch,
+              size_t scratch_floats) {
   if (M <= 0 || N <= 0) return USF_OK;
   if ((ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD) && ep.C != 64) {
     set_error("simt_gemm: coupling epilogue needs C == 64 (got %d)", ep.C);
     return USF_E_ARG;
+  }
+  if (scratch != nullptr && (size_t)M * (size_t)N <= scratch_floats && K >= 64 &&
+      ceil_div(M, BM) * ceil_div(N, BN) * 2 <= num_sms()) {
+    // small batch: a handful of 128x128 tiles would walk K serially on a few SMs.  Split K across the SMs into the
+    // caller's scratch accumulator, then apply the same epilogue from there (2 short launches instead of 1 long).
+    int rc = simt_gemm_plain(A, lda, a_trans, W, ldw, w_trans, M, N, K, scratch, N, 0, stream);
+    if (rc) return rc;
+    const int warps = 8;
+    usf_simt_epilogue_kernel<<<(unsigned)ceil_div(M, warps), warps * 32, 0, stream>>>(scratch, M, N, ep);
+    USF_LAUNCH_CHECK("usf_simt_epilogue_kernel");
+    return USF_OK;
   }
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN), 1);
   PlainOut po{nullptr, 0, 0, 1};
