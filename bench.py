@@ -31,8 +31,10 @@ ALG_FLOP_PER_SAMPLE = 26.84e6      # mask-pruned, conditioner counted once (SURV
 ALG_BYTES_PER_SAMPLE = 4 * D + 4
 LAST_LAYER_GAIN = 0.25             # trained-flow-like activations (see DESIGN.md "Synthetic weights")
 CPU_SAMPLE_ROWS = 4096
-# DRAM bytes per GEMM launch at 65536 rows from the committed ncu capture (8*(160.3+69.2+34.0+103.6) MB / 33)
-NCU_DRAM_BYTES_PER_LAUNCH = 89.0e6
+EXEC_FLOP_PER_SAMPLE = 17.7e6      # what the launch chain executes: 9 merged dense maps + 8 pruned MLPs
+# DRAM bytes per tensor-core launch at 65536 rows from the committed ncu capture: 9 GEMM launches at 174.4 MB
+# (106.2 read + 68.2 written) and 8 fused conditioner launches at 120.3 MB (106.0 + 14.3), profiles/r1b_final
+NCU_DRAM_BYTES_PER_LAUNCH = (9 * 174.4e6 + 8 * 120.3e6) / 17
 
 
 def build_flow(ns, device, dtype=torch.float32):
@@ -405,8 +407,10 @@ def main():
                              _lib.USF_PREC_BF16 if args.precision == "bf16" else _lib.USF_PREC_FP32).decode(),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 GEMM kinds "
-                                           "weighted by launches/step, profiles/r1_run2/tc_gemm_full_raw.csv",
+                         "traffic_source": "ncu --set full dram__bytes_read+write per launch, mean over the 9 GEMM + 8 fused "
+                                           "conditioner launches of a step, profiles/r1b_final/tc_kernels_full_raw.csv",
+                         "executed_flop_per_sample": EXEC_FLOP_PER_SAMPLE,
+                         "frac_executed": achieved / peak * EXEC_FLOP_PER_SAMPLE / ALG_FLOP_PER_SAMPLE,
                          "alg_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_ms,
                          "gemm_share_of_step": gemm_ms_per_step / (ms_total / args.steps),
                          "launch_ms_by_kind": {names[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},

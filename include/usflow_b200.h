@@ -244,9 +244,13 @@ int usf_profile_end(float* ms, int* tags, int* n_out);
  * GEMM expired (a pipeline protocol bug); synchronises the device. */
 int usf_debug_tc_timeout(int* flag, int reset);
 
-/* Debug: in-kernel pipeline trace of the tcgen05 GEMM.  on != 0 enables recording for subsequent launches
- * (CTAs 0 and 1; roles 0 TMA producer, 1 MMA issuer, 2 first epilogue warp; 2048 records of
- * {tile<<8 | event, SM clock} per (CTA, role)); out != NULL copies the last launch's 12288 records. */
+/* Debug: in-kernel pipeline trace of the tcgen05 GEMM.  Bits 0-7 of `on`: 1 = record the plain GEMM, 2 = the
+ * fused conditioner kernel, for subsequent launches (CTAs 0 and 1; roles 0 TMA producer, 1 MMA issuer, 2 first
+ * epilogue warp; 2048 records of {tile<<8 | event, SM clock} per (CTA, role)); out != NULL copies the last
+ * launch's 12288 records.  Bits 8-15 of `on` (with out == NULL): ablation switches of the plain GEMM's
+ * instrumented variant (1 no global stores, 2 no epilogue, 4 no A loads, 8 no W loads, 16 no MMAs, 32 back-off
+ * waits, 64 single-lane polling, 128 nothing: just select the instrumented variant) -- results are then wrong by
+ * construction, only times matter (scripts/tc_ablate.py).  Production launches run an uninstrumented variant. */
 int usf_debug_tc_trace(int on, unsigned long long* out, int max_records);
 
 /* Standalone bf16 tensor-core GEMM y = act(x W^T + bias) (testing / conditioner layers):
