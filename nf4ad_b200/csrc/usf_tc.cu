@@ -450,7 +450,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // bytes landing per stage on the (leader's) full barrier: every CTA loads 128 rows of A and bn/CG rows of W
   // debug ablations (usf_debug_tc_trace, bits 8+ of `on`): 1 = epilogue without global stores, 2 = epilogue only
   // hands the accumulator back, 4 = producer skips the A loads, 8 = producer skips the W loads, 16 = no MMAs issued
-  const int dbg = DBG ? args.dbg : 0;
+  // the uninstrumented variant honours only the producer-side load ablations (4, 8), requested with bit 0x200
+  const int dbg = DBG ? args.dbg : ((args.dbg & 0x200) ? (args.dbg & 12) : 0);
   const uint32_t stage_tx = CG * (((dbg & 4) ? 0u : TC_A_BYTES) + ((dbg & 8) ? 0u : (uint32_t)(args.bn / CG) * TC_BK * 2));
 
   if (warp == 0) {
@@ -1283,7 +1284,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (args.trace != nullptr || args.dbg != 0) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
+  if (args.trace != nullptr || (args.dbg != 0 && !(args.dbg & 0x200))) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
   else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, args));
   return USF_OK;
 }
@@ -1376,7 +1377,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
 // Debug: enable tracing for subsequent launches (on != 0) / read back the records of the LAST launch.
 int tc_trace_ctl(int on, unsigned long long* out, int max_records) {
   g_trace_on = on & 0xFF;
-  if (out == nullptr) g_tc_dbg = (on >> 8) & 0xFF;   // bits 8+: ablation switches for subsequent plain-GEMM launches
+  if (out == nullptr) g_tc_dbg = (on >> 8) & 0x3FF;   // bits 8+: ablation switches for subsequent plain-GEMM launches
   if (out != nullptr) {
     const size_t n = (size_t)2 * 3 * TC_TRACE_CAP * 2;
     const size_t want = (size_t)max_records * 2 < n ? (size_t)max_records * 2 : n;

@@ -19,7 +19,7 @@ for (B, N, K, relu) in [(65536, 800, 784, 0), (65536, 256, 392, 1), (65536, 832,
     b = torch.zeros(N, device="cuda")
     y = torch.empty(B, N, device="cuda", dtype=torch.bfloat16)
     res = {}
-    for dbg in (0, 128, 64, 2, 12):
+    for dbg in (0, 0x200 | 4, 0x200 | 8, 0x200 | 12, 128, 12):
         _lib.check(lib().usf_debug_tc_trace(dbg << 8, None, 0))
         for _ in range(3):
             _lib.check(lib().usf_linear_bf16(ptr(x), ldx, ptr(W), ldx, ptr(b), relu, ptr(y), N, 1, B, N, K, stream()))
