@@ -137,6 +137,10 @@ class NvmlSampler:
         nv = self.nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
         try:
+            self.rows.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        try:
             self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
         except Exception:
             self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -161,9 +165,10 @@ class NvmlSampler:
         self.stop_flag = True
         self.t.join(timeout=2)
         sm = sorted(self.sm)
+        pw = sorted(self.rows)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "samples": len(sm),
-                "source": "nvml"}
+                "power_w": pw[len(pw) // 2] if pw else None, "source": "nvml"}
 
 
 def make_sampler(index):

@@ -74,11 +74,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: returns false (and raises the global flag) if the barrier never completes.  The hot spin is
 // try_wait only; the clock and the global abort flag (an L2 round trip) are looked at once per 1024 failed polls.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return true;
   uint32_t spins = 0;
   long long t0 = 0;
   for (;;) {
+    if (backoff_ns != 0) __nanosleep(backoff_ns);   // waits off the critical path: do not burn issue slots / power
     if (mbar_try_wait(bar, parity)) return true;
     if ((++spins & 1023u) == 0u) {
       if (*reinterpret_cast<volatile int*>(&g_tc_timeout) != 0) return false;
@@ -367,6 +368,7 @@ struct TcArgs {
   int n_valid;   // valid output columns for fp32 stores / base density (<= N)
   int stages;                 // smem ring depth (<= TC_MAX_STAGES)
   uint32_t stage_bytes;       // bytes per stage (A tile + this CTA's W rows), multiple of 1024
+  uint32_t backoff_ns;        // sleep between polls of the epilogue / producer waits (0 = spin)
   int dbg;                    // debug experiments (env USF_TC_DBG): 1 = copy-out without the global store, 2 = no copy-out
   unsigned long long* trace;  // debug: per-role timestamp records of CTA 0/1 (NULL = off), see usf_debug_tc_trace
   EpiParams ep;
@@ -469,7 +471,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int a_row = (mt * CG + (int)cta_rank) * TC_BM;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (kb == 0) tc_trace<DBG>(trb, trn, t, 0);
-          ok = (dbg & 32) ? mbar_wait_relaxed(empty_bar(s), ph ^ 1u, 40) : mbar_wait(empty_bar(s), ph ^ 1u);
+          ok = (dbg & 32) ? mbar_wait_relaxed(empty_bar(s), ph ^ 1u, 40) : mbar_wait(empty_bar(s), ph ^ 1u, args.backoff_ns);
           if (!ok) break;
           if (kb == 0) tc_trace<DBG>(trb, trn, t, 1);
           if (kb == num_kb - 1) tc_trace<DBG>(trb, trn, t, 2);
@@ -618,7 +620,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (!resident) asm volatile("bar.sync 1, 256;" ::: "memory");
       tc_trace<DBG>(trb, trn, t, 1);
 
-      const bool ok = (dbg & 32) ? mbar_wait_relaxed(tfull_bar(a), aph, 100) : mbar_wait(tfull_bar(a), aph);
+      const bool ok = (dbg & 32) ? mbar_wait_relaxed(tfull_bar(a), aph, 100) : mbar_wait(tfull_bar(a), aph, args.backoff_ns);
       tc_trace<DBG>(trb, trn, t, 2);
       if (ok) {
         tc_fence_after();
@@ -785,6 +787,7 @@ struct MlpArgs {
   int boff[MLP_MAX_LAYERS];      // offset of layer l's bias vector in the resident smem copy (prefix sums of N)
   const float* bias[MLP_MAX_LAYERS];
   EpiParams ep;                  // coupling epilogue of the last layer
+  uint32_t backoff_ns;           // sleep between polls of the epilogue / producer waits (0 = spin)
   unsigned long long* trace;     // debug timeline (see usf_debug_tc_trace); events use tile = (m_tile << 4) | gemm index
 };
 
@@ -849,7 +852,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       bool ok = true;
       // one box into the next free slot; the pair's bytes are accounted on the leader's barrier
       auto load = [&](const CUtensorMap* tm, uint32_t bytes_per_cta, int c0, int c1) {
-        ok = mbar_wait(empty_bar(s), ph ^ 1u);
+        ok = mbar_wait(empty_bar(s), ph ^ 1u, args.backoff_ns);
         if (!ok) return;
         if (elect_one()) {
           if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes_per_cta);
@@ -979,7 +982,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       // accumulator hand-over: wait until the MMAs of the next GEMM of the chain are complete / give the buffer back
       auto acquire = [&](int gi) -> bool {
         tc_trace<DBG>(trb, trn, gi, 0);
-        const bool ok = mbar_wait(tfull_bar(a), aph);
+        const bool ok = mbar_wait(tfull_bar(a), aph, args.backoff_ns);
         tc_trace<DBG>(trb, trn, gi, 2);
         if (ok) tc_fence_after();
         return ok;
@@ -1194,6 +1197,14 @@ int tc_cta_group() {
   return cg;
 }
 
+// USF_TC_BACKOFF_NS: sleep between polls of the waits that are off the critical path (epilogue warps waiting for a
+// tile of MMAs, producers waiting for a ring slot).
+static uint32_t tc_backoff_ns() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("USF_TC_BACKOFF_NS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  return (uint32_t)v;
+}
+
 int tc_pick_bn(int64_t N) {
   // balanced N tiles: as few tiles as possible, equal width, multiple of 16, <= 256
   const int64_t nt = ceil_div(N, TC_MAX_BN);
@@ -1255,6 +1266,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if (args.stages < 2) { set_error("tc_gemm: tile does not fit in shared memory"); return USF_E_ARG; }
   if (g_tc_dbg < 0) { const char* e = getenv("USF_TC_DBG"); g_tc_dbg = e ? atoi(e) : 0; }
   args.dbg = g_tc_dbg;
+  args.backoff_ns = tc_backoff_ns();
   args.trace = nullptr;
   if (g_trace_on == 1) {
     void* p = nullptr;
@@ -1348,6 +1360,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
                       (N[n_layers - 1] % bn_last) == 0 && (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 && (ep.ldub % 16) == 0,
                   "tc_mlp_coupling: bad additive tile");
   args.ep = ep;
+  args.backoff_ns = tc_backoff_ns();
   args.trace = nullptr;
   if (g_trace_on == 2) {
     void* tp = nullptr;
