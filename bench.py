@@ -361,30 +361,38 @@ def main():
 
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
     train_ms, train_B, train_steps, train_graph = float("nan"), args.train_rows, args.train_steps, False
+    train32_ms = float("nan")
     if train_steps > 0:
         from nf4ad_b200.parallel import DataParallelTrainer
-        tflow = build_flow(P, dev).train()
-        opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True)   # the step replays as one CUDA graph
-        trainer = DataParallelTrainer(tflow, opt)
-        trainer.broadcast_parameters()
         xb = x[:train_B]
-        for _ in range(5):          # 3 eager steps + capture + first replay (single rank), all untimed
-            trainer.step(xb)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(train_steps):
-            loss = trainer.step(xb)
-        g1.record()
-        barrier()
-        train_ms = g0.elapsed_time(g1)
-        assert bool(torch.isfinite(loss))
-        train_graph = trainer.graph_replays > 0
-        del tflow, opt, trainer
-    t = torch.tensor([ms_total, e2e_ms, train_ms], device=dev, dtype=torch.float64)
+        for prec in ("bf16", "fp32"):
+            # "bf16" = mixed precision: bf16 tensor-core GEMMs with fp32 accumulation, fp32 parameters / gradients /
+            # Adam state, LU layers applied through their per-step dense inverse; "fp32" = the all-fp32 kernels
+            tflow = build_flow(P, dev).train()
+            tflow.precision = prec
+            opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True)   # the step replays as one CUDA graph
+            trainer = DataParallelTrainer(tflow, opt)
+            trainer.broadcast_parameters()
+            for _ in range(5):          # 3 eager steps + capture + first replay (single rank), all untimed
+                trainer.step(xb)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(train_steps):
+                loss = trainer.step(xb)
+            g1.record()
+            barrier()
+            if prec == "bf16":
+                train_ms = g0.elapsed_time(g1)
+                train_graph = trainer.graph_replays > 0
+            else:
+                train32_ms = g0.elapsed_time(g1)
+            assert bool(torch.isfinite(loss))
+            del tflow, opt, trainer
+    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
+    ms_total, e2e_ms, train_ms, train32_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         n_gemm = sum(len(v) for k, v in per_tag.items() if k != 0)
@@ -424,9 +432,12 @@ def main():
         if sweep:
             line["sweep"] = sweep
         if train_steps > 0:
-            line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam, fp32 path)", "graph_replay": bool(train_graph),
+            line["train"] = {"metric": "train samples/sec (fwd + bwd + Adam; bf16 tensor-core GEMMs, fp32 accumulate / "
+                                       "parameters / optimizer state)", "graph_replay": bool(train_graph),
                              "value": train_B * world * train_steps / (train_ms * 1e-3), "unit": "samples/s",
-                             "batch_per_gpu": train_B, "steps": train_steps, "ms_per_step": train_ms / train_steps}
+                             "batch_per_gpu": train_B, "steps": train_steps, "ms_per_step": train_ms / train_steps,
+                             "fp32_path": {"value": train_B * world * train_steps / (train32_ms * 1e-3),
+                                           "ms_per_step": train32_ms / train_steps}}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, cms = cpu_reference_run(3, 1, CPU_SAMPLE_ROWS)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",

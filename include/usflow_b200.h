@@ -137,6 +137,13 @@ int usf_scale_bwd(const float* dy, int64_t lddy, const float* xy, int64_t ldxy, 
                   int inverse, float* dx, int64_t lddx, float* dscale, int64_t B, int64_t D,
                   usf_stream_t stream);
 
+/* Operand preparation of the tensor-core (bf16) training GEMMs: one pass over the fp32 (B x N) matrix x, optionally
+ * gated by a ReLU output (v = relu_mask[r,c] > 0 ? x[r,c] : 0), writes any of: `rows` (B x ldr bf16, pad columns
+ * zero), `transposed` (N x ldt bf16, pad columns zero: the weight-gradient GEMM reduces over the batch) and
+ * `colsum` (fp32, += column sums of v: the bias gradient; the caller zeroes it).  NULL outputs are skipped. */
+int usf_to_bf16(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, uint16_t* rows, int64_t ldr,
+                uint16_t* transposed, int64_t ldt, float* colsum, int64_t B, int64_t N, usf_stream_t stream);
+
 /* out[c] (+)= coef * sum_b a[b,c]  (bias gradients). */
 int usf_colsum(const float* a, int64_t lda, float coef, int accumulate, float* out, int64_t B, int64_t N,
                usf_stream_t stream);

@@ -136,7 +136,7 @@ extern "C" int usf_debug_tc_trace(int on, unsigned long long* out, int max_recor
 extern "C" int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias,
                                int relu, void* y, int64_t ldy, int y_is_bf16, int64_t B, int64_t N, int64_t K,
                                usf_stream_t stream) {
-  USF_CHECK_ARG(x && W && y && bias, "usf_linear_bf16: null pointer");
+  USF_CHECK_ARG(x && W && y, "usf_linear_bf16: null pointer");   // bias may be NULL (plain GEMM)
   EpiParams ep{};
   ep.mode = relu ? EPI_BIAS_RELU : EPI_BIAS;
   ep.bias = bias;

@@ -931,6 +931,50 @@ extern "C" int usf_lu_pack(const float* L_raw, const float* U_raw, int64_t D, fl
 
 namespace usf {
 namespace {
+// Operand preparation of the tensor-core training GEMMs.  One pass over an fp32 (B x N) matrix x (optionally gated by
+// a ReLU output: v = mask[r,c] > 0 ? x[r,c] : 0) writes any of: a bf16 row-major copy (B x ldr, pad columns zero), a
+// bf16 TRANSPOSED copy (N x ldt, pad columns zero: operand of the weight-gradient GEMM, which reduces over the
+// batch), and the fp32 column sums (bias gradient; atomically accumulated, caller zeroes).  32x32 tiles through smem.
+__global__ void usf_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
+                                   __nv_bfloat16* rows, int64_t ldr, __nv_bfloat16* tr, int64_t ldt, float* colsum,
+                                   int64_t B, int64_t N, int64_t Bp, int64_t Np) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  float cs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < B && c < N) {
+      v = x[r * ldx + c];
+      if (mask != nullptr && !(mask[r * ldm + c] > 0.f)) v = 0.f;
+    }
+    tile[ty + 8 * i][tx] = v;
+    cs += v;
+    if (rows != nullptr && r < B && c < Np) rows[r * ldr + c] = __float2bfloat16_rn(v);
+  }
+  if (colsum != nullptr) {
+    __shared__ float part[8][32];
+    part[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += part[i][tx];
+      atomicAdd(colsum + c0 + tx, t);
+    }
+  }
+  if (tr != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t c = c0 + ty + 8 * i, r = r0 + tx;     // tr[c, r] = x[r, c]
+      if (c < N && r < Bp) tr[c * ldt + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+  }
+}
+
 // y[r, c] = act(y[r, c] + bias[c]) in place: second phase of the split-K form of usf_linear
 __global__ void usf_bias_act_kernel(float* y, int64_t ldy, const float* __restrict__ bias, int relu, int64_t B, int64_t N) {
   const int64_t total = B * N;
@@ -942,6 +986,22 @@ __global__ void usf_bias_act_kernel(float* y, int64_t ldy, const float* __restri
 }
 }  // namespace
 }  // namespace usf
+
+extern "C" int usf_to_bf16(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, uint16_t* rows, int64_t ldr,
+                           uint16_t* transposed, int64_t ldt, float* colsum, int64_t B, int64_t N, usf_stream_t stream) {
+  USF_CHECK_ARG(x != nullptr && B >= 0 && N > 0 && ldx >= N, "usf_to_bf16: bad arguments");
+  USF_CHECK_ARG(rows == nullptr || ldr >= N, "usf_to_bf16: ldr < N");
+  USF_CHECK_ARG(transposed == nullptr || ldt >= B, "usf_to_bf16: ldt < B");
+  if (B == 0) return USF_OK;
+  // pad columns up to the leading dimension are written as zeros (B x ldr and N x ldt are fully defined)
+  const int64_t Np = rows != nullptr ? ldr : N, Bp = transposed != nullptr ? ldt : B;
+  dim3 grid((unsigned)ceil_div(Np > N ? Np : N, 32), (unsigned)ceil_div(Bp > B ? Bp : B, 32));
+  usf_to_bf16_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
+      x, ldx, relu_mask, ldm, reinterpret_cast<__nv_bfloat16*>(rows), ldr, reinterpret_cast<__nv_bfloat16*>(transposed), ldt,
+      colsum, B, N, Bp, Np);
+  USF_LAUNCH_CHECK("usf_to_bf16_kernel");
+  return USF_OK;
+}
 
 extern "C" int usf_linear(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, int relu,
                           float* y, int64_t ldy, int64_t B, int64_t N, int64_t K, usf_stream_t stream) {

@@ -143,8 +143,10 @@ class Flow(torch.nn.Module):
                 lp, _, _, n = cs.run(x2, want_logprob=True)
                 self.last_launches = n
                 return lp[0] if squeeze else lp
-        z, neg_ladj = self._inverse_layers(x2, context)
-        lp = self._base_log_prob(z) + neg_ladj
+        # autograd (training) pass; `precision == "bf16"` selects the mixed-precision form (ops.tc_training)
+        with ops.tc_training(self.precision == "bf16" and torch.is_grad_enabled()):
+            z, neg_ladj = self._inverse_layers(x2, context)
+            lp = self._base_log_prob(z) + neg_ladj
         return lp[0] if squeeze else lp
 
     def _inverse_layers(self, y, context=None):

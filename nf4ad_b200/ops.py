@@ -124,6 +124,71 @@ def pack_matrix(src, row_idx, col_idx, n_rows, n_cols, ldo, sub_row0=False, tran
     return out, outb
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def to_bf16(x, relu_mask=None, want_rows=True, want_transposed=False, want_colsum=False):
+    """One pass over fp32 x (B,N): bf16 copy (B, pad8(N)), bf16 transposed copy (N, pad8(B)), column sums (N,).
+    usf_to_bf16 (pads are zero so the buffers are valid TMA sources)."""
+    require_cuda(x)
+    x, ldx = _rows(x)
+    B, N = x.shape
+    dev = x.device
+    rows = torch.empty(B, _pad8(N), device=dev, dtype=torch.bfloat16) if want_rows else None
+    tr = torch.empty(N, _pad8(B), device=dev, dtype=torch.bfloat16) if want_transposed else None
+    cs = torch.zeros(N, device=dev, dtype=torch.float32) if want_colsum else None
+    m, ldm = (_rows(relu_mask) if relu_mask is not None else (None, 0))
+    check(lib().usf_to_bf16(ptr(x), ldx, ptr(m), ldm, ptr(rows), _pad8(N), ptr(tr), _pad8(B), ptr(cs), B, N, stream()),
+          "usf_to_bf16")
+    return rows, tr, cs
+
+
+def gemm_bf16(a, w, M, N, K, bias=None, relu=False):
+    """fp32 (M,N) = act(a w^T + bias) on the tcgen05 GEMM; a: (M, ld>=K) bf16, w: (N, ld>=K) bf16, N % 16 == 0."""
+    y = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    b = f32c(bias) if bias is not None else None
+    check(lib().usf_linear_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(b), int(relu), ptr(y), N, 0, M, N, K,
+                                stream()), "usf_linear_bf16")
+    return y
+
+
+# Mixed-precision training (flow.precision == "bf16" under autograd): the batch-sized GEMMs of the step run on the
+# tcgen05 kernel with bf16 operands and fp32 accumulation, parameters / gradients / optimizer state stay fp32, and an
+# LU layer is inverted once per step (weight space) so that no triangular solve ever sees the batch.
+_TC_TRAIN = False
+
+
+class tc_training:
+    """Context manager set by `Flow` around the autograd-recording forward pass."""
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _TC_TRAIN
+        self.prev, _TC_TRAIN = _TC_TRAIN, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _TC_TRAIN
+        _TC_TRAIN = self.prev
+        return False
+
+
+def tc_train_enabled():
+    return _TC_TRAIN
+
+
+def linear_fn(x, W, bias, relu=False):
+    """Autograd linear layer: tensor-core (bf16) GEMMs in mixed-precision training when the shapes allow TMA operands
+    (N, K multiples of 16, batch multiple of 8), else the fp32 kernels."""
+    if _TC_TRAIN and x.is_cuda and x.dim() == 2 and x.shape[0] % 8 == 0 and x.shape[0] >= 8 \
+            and W.shape[0] % 16 == 0 and W.shape[1] % 16 == 0:
+        return LinearTCFn.apply(x, W, bias, relu)
+    return LinearFn.apply(x, W, bias, relu)
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd Functions (training path; fp32)
 # ------------------------------------------------------------------------------------------------
@@ -156,6 +221,70 @@ class LinearFn(torch.autograd.Function):
         check(lib().usf_linear_bwd(ptr(dy), lddy, ptr(x), ldx, ptr(W), ldw, ptr(yr), ldyr, ptr(dx), K, ptr(dW), K,
                                    ptr(db), 0, ptr(scratch), B, N, K, stream()), "usf_linear_bwd")
         return dx, dW, db, None
+
+
+class LinearTCFn(torch.autograd.Function):
+    """y = relu?(x W^T + b) with bf16 tensor-core GEMMs (fp32 accumulate) forward and backward:
+        y  = x  W^T        A = x   (B,K),  W-operand = W   (N,K)
+        dx = dy W          A = dy  (B,N),  W-operand = W^T (K,N)
+        dW = dy^T x        A = dy^T (N,B), W-operand = x^T (K,B)     (reduces over the batch)
+    One `usf_to_bf16` pass per fp32 matrix produces the bf16 row-major / transposed operands (and, for dy, the ReLU
+    gating and the bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, relu):
+        B, K = x.shape
+        N = W.shape[0]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        xb, xT, _ = to_bf16(x, want_rows=True, want_transposed=need_w)
+        Wb, WT, _ = to_bf16(W, want_rows=True, want_transposed=need_x)
+        y = gemm_bf16(xb, Wb, B, N, K, bias, relu)
+        ctx.relu, ctx.has_bias, ctx.shape = bool(relu), bias is not None, (B, N, K)
+        ctx.save_for_backward(xT, WT, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xT, WT, y = ctx.saved_tensors
+        B, N, K = ctx.shape
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dyb, dyT, db = to_bf16(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
+                               want_colsum=need_b)
+        dx = gemm_bf16(dyb, WT, B, K, N) if need_x else None
+        dW = gemm_bf16(dyT, xT, N, K, B) if need_w else None
+        return dx, dW, db, None
+
+
+class LUInverseFn(torch.autograd.Function):
+    """A = (L U)^{-1} as a dense matrix, once per step (weight space): the triangular-solve kernel applied to the
+    identity.  Backward: dW = -A^T dA A^T, then the factor gradients through usf_lu_pack_bwd."""
+
+    @staticmethod
+    def forward(ctx, L_raw, U_raw):
+        D = L_raw.shape[0]
+        eye = torch.eye(D, device=L_raw.device, dtype=torch.float32)
+        A = lu_solve(eye, L_raw, U_raw, None, transpose=True)      # row i = e_i^T (LU)^{-1}
+        ctx.save_for_backward(A, L_raw, U_raw)
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        A, L_raw, U_raw = ctx.saved_tensors
+        D = A.shape[0]
+        dev = A.device
+        dA = f32c(dA).contiguous()
+        P = torch.empty(D, D, device=dev, dtype=torch.float32)
+        dW = torch.empty(D, D, device=dev, dtype=torch.float32)
+        # P = A^T dA ;  dW = -(P A^T)
+        check(lib().usf_gemm(ptr(A), D, 1, ptr(dA), D, 1, ptr(P), D, 0, D, D, D, stream()), "usf_gemm")
+        check(lib().usf_gemm(ptr(P), D, 0, ptr(A), D, 0, ptr(dW), D, 0, D, D, D, stream()), "usf_gemm")
+        Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+        dL = torch.zeros(D, D, device=dev, dtype=torch.float32)
+        dU = torch.zeros(D, D, device=dev, dtype=torch.float32)
+        scratch = torch.empty(3 * D * D, device=dev, dtype=torch.float32)
+        check(lib().usf_lu_pack_bwd(ptr(dW), ptr(Lc), ptr(Uc), 0.0, D, ptr(dL), ptr(dU), ptr(scratch), stream()),
+              "usf_lu_pack_bwd")
+        return dL.neg_(), dU.neg_()
 
 
 class LUPackFn(torch.autograd.Function):

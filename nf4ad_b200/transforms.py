@@ -120,12 +120,18 @@ class LUTransform(BaseTransform):
 
     def forward(self, x, context=None):
         x2, squeeze = _as2d(x)
-        y = ops.LinearFn.apply(x2, self.weight, self.bias, False)
+        y = ops.linear_fn(x2, self.weight, self.bias, False)
         return y[0] if squeeze else y
 
     def backward(self, y, context=None):
         y2, squeeze = _as2d(y)
-        x = ops.LUSolveFn.apply(y2, self.L_raw, self.U_raw, self.bias)
+        if ops.tc_train_enabled() and y2.is_cuda and self.dim % 16 == 0 and y2.shape[0] % 8 == 0 and y2.shape[0] >= 8:
+            # mixed-precision training: x = A (y - b) with the dense inverse A = (LU)^{-1} (one weight-space solve per
+            # step) applied by a tensor-core GEMM; the shift -A b is a weight-space matrix-vector product
+            A = ops.LUInverseFn.apply(self.L_raw, self.U_raw)
+            x = ops.linear_fn(y2, A, -(A @ self.bias), False)
+        else:
+            x = ops.LUSolveFn.apply(y2, self.L_raw, self.U_raw, self.bias)
         return x[0] if squeeze else x
 
     def log_abs_det_jacobian(self, x, y, context=None):
@@ -353,7 +359,7 @@ def run_conditioner(cond, xm, context=None):
         return cond(xm)
     h = xm
     for i, lin in enumerate(linears):
-        h = ops.LinearFn.apply(h, lin.weight, lin.bias, i + 1 < len(linears))
+        h = ops.linear_fn(h, lin.weight, lin.bias, i + 1 < len(linears))
     pd = getattr(cond, "param_dims", None)
     if pd is not None and len(pd) > 1:           # DenseNN tuple output
         outs, o = [], 0

@@ -10,6 +10,7 @@ P = nf4ad_b200.namespace()
 for name, D, K, hid in (("C2 D=784 K=8 [256,256]", 784, 8, [256, 256]), ("test D=32 K=3 [128]", 32, 3, [128]), ("C5 D=128 K=10 [512,256]", 128, 10, [512, 256])):
     torch.manual_seed(0)
     flow = build_flow(P, "NonUSFlow", D, K, ("mlp", hid), base="normal", affine_conjugation=True, prior_scale=1.0).to("cuda").train()
+    flow.precision = os.environ.get("TRAIN_PREC", "fp32")
     opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True)
     tr = DataParallelTrainer(flow, opt)
     for B in (32, 64, 4096):
@@ -25,8 +26,9 @@ for name, D, K, hid in (("C2 D=784 K=8 [256,256]", 784, 8, [256, 256]), ("test D
 from torch.profiler import profile, ProfilerActivity
 torch.manual_seed(0)
 flow = build_flow(P, "NonUSFlow", 784, 8, ("mlp", [256, 256]), base="normal", affine_conjugation=True, prior_scale=1.0).to("cuda").train()
+flow.precision = os.environ.get("TRAIN_PREC", "fp32")
 opt = torch.optim.Adam(flow.parameters(), lr=1e-4); tr = DataParallelTrainer(flow, opt)
-x = torch.randn(64, 784, device="cuda")
+x = torch.randn(int(os.environ.get("PROF_B", "64")), 784, device="cuda")
 for _ in range(5): tr.step(x)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

@@ -419,3 +419,46 @@ def test_training_step_graph_replay_matches_eager(P):
     assert np.allclose(l0, l1, rtol=2e-3, atol=1e-3), (l0, l1)
     for a, b in zip(p0, p1):
         assert float((a - b).abs().max()) <= 2e-3 * max(1.0, float(a.abs().max()))
+
+
+def test_mixed_precision_training_gradients_follow_fp32(P):
+    """`flow.precision = "bf16"` under autograd: the batch-sized GEMMs of the training step run on the tcgen05 kernel
+    (bf16 operands, fp32 accumulate), LU layers are applied through their dense inverse (`LUInverseFn`).  Loss within
+    the bf16 tier of the fp32 path, every parameter gradient pointing the same way."""
+    D, B = 64, 256
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", D, 3, ("mlp", [128, 128]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    flow = flow.to("cuda").train()
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(5)).cuda()
+    grads, losses = {}, {}
+    for prec in ("fp32", "bf16"):
+        flow.precision = prec
+        flow.zero_grad(set_to_none=True)
+        loss = -flow.log_prob(x).mean()
+        loss.backward()
+        losses[prec] = float(loss.detach())
+        grads[prec] = {n: p.grad.detach().clone() for n, p in flow.named_parameters() if p.grad is not None}
+    assert abs(losses["bf16"] - losses["fp32"]) <= 1e-2 * max(1.0, abs(losses["fp32"])), losses
+    assert set(grads["bf16"]) == set(grads["fp32"])
+    worst = 1.0
+    for n, g32 in grads["fp32"].items():
+        g16 = grads["bf16"][n]
+        assert torch.isfinite(g16).all(), n
+        if float(g32.norm()) < 1e-6:
+            continue
+        cos = float((g32 * g16).sum() / (g32.norm() * g16.norm()).clamp_min(1e-30))
+        worst = min(worst, cos)
+        assert cos > 0.98, (n, cos)
+        assert 0.9 < float(g16.norm() / g32.norm()) < 1.1, n
+    # and a few optimizer steps lower the loss
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-3)
+    flow.precision = "bf16"
+    first = None
+    for _ in range(10):
+        opt.zero_grad(set_to_none=True)
+        loss = -flow.log_prob(x).mean()
+        loss.backward()
+        opt.step()
+        first = float(loss) if first is None else first
+    assert float(loss) < first
