@@ -680,9 +680,16 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 dst[1] = q1;
               } else {
                 float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
+                if (n0 + c + 16 <= args.n_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                  // full, 16-byte aligned chunk (the training GEMMs: fp32 gradients / activations): 4 x 128-bit stores
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (n0 + c + j < args.n_valid) dst[j] = v[j];
+                  for (int j4 = 0; j4 < 4; ++j4)
+                    reinterpret_cast<float4*>(dst)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (n0 + c + j < args.n_valid) dst[j] = v[j];
+                }
               }
             }
           }

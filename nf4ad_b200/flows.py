@@ -149,8 +149,44 @@ class Flow(torch.nn.Module):
             lp = self._base_log_prob(z) + neg_ladj
         return lp[0] if squeeze else lp
 
+    def _prefetch_lu_inverses(self, y):
+        """Mixed-precision training: the dense inverses of all LU layers this pass will apply are independent of the
+        data and of each other, and one inversion (two 25-CTA triangular solves on the identity) cannot fill the GPU.
+        They are therefore issued up front on a few side streams (fork / join from the current stream; their backward
+        nodes run on the same streams), and `LUTransform.backward` picks its matrix up from `_A_pre`."""
+        B = y.shape[0]
+        if not y.is_cuda or B < 8 or B % 8:
+            return
+        mods, seen = [], set()
+        for layer in self.layers:
+            if isinstance(layer, InverseTransform) or not isinstance(layer, torch.nn.Module):
+                continue                      # applied through its forward map: no inverse needed
+            for m in layer.modules():
+                if isinstance(m, LUTransform) and id(m) not in seen and m.dim % 16 == 0:
+                    seen.add(id(m))
+                    mods.append(m)
+        if len(mods) < 2:
+            return
+        cur = torch.cuda.current_stream(y.device)
+        streams = self.__dict__.get("_side_streams")
+        if streams is None or streams[0].device != y.device:
+            streams = [torch.cuda.Stream(device=y.device) for _ in range(8)]
+            self.__dict__["_side_streams"] = streams
+        used = streams[:min(len(streams), len(mods))]
+        for s in used:
+            s.wait_stream(cur)
+        for i, lu in enumerate(mods):
+            with torch.cuda.stream(used[i % len(used)]):
+                A = ops.LUInverseFn.apply(lu.L_raw, lu.U_raw)
+            A.record_stream(cur)
+            lu.__dict__["_A_pre"] = A
+        for s in used:
+            cur.wait_stream(s)
+
     def _inverse_layers(self, y, context=None):
         """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""
+        if ops.tc_train_enabled():
+            self._prefetch_lu_inverses(y)
         total = torch.zeros(y.shape[0], device=y.device, dtype=torch.float32)
         for layer in reversed(self.layers):
             if hasattr(layer, "inverse_and_ladj"):

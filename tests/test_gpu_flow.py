@@ -460,5 +460,23 @@ def test_mixed_precision_training_gradients_follow_fp32(P):
         loss = -flow.log_prob(x).mean()
         loss.backward()
         opt.step()
-        first = float(loss) if first is None else first
-    assert float(loss) < first
+        first = float(loss.detach()) if first is None else first
+    assert float(loss.detach()) < first
+
+
+def test_mixed_precision_training_step_replays_as_graph(P):
+    """The mixed-precision step (side-stream LU inversions, bf16 tensor-core GEMMs) must survive CUDA-graph capture
+    and keep training."""
+    from nf4ad_b200.parallel import DataParallelTrainer
+    D, B = 64, 64
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", D, 3, ("mlp", [128]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    flow = flow.to("cuda").train()
+    flow.precision = "bf16"
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-3, capturable=True)
+    tr = DataParallelTrainer(flow, opt)
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(1)).cuda()
+    losses = [float(tr.step(x)) for _ in range(20)]
+    assert tr.graph_replays == 17
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0]
