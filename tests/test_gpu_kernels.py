@@ -133,3 +133,39 @@ def test_tcgen05_linear_bf16(ops, B, N, K, relu, f32out):
     assert torch.isfinite(y.float()).all()
     tol = 1e-5 if f32out else 6e-3
     assert relerr(y.float(), ref) < tol
+
+
+@pytest.mark.parametrize("B,N,relu", [(8, 16, False), (64, 784, True), (257, 100, True), (4096, 256, False)])
+def test_to_bf16_operand_pass(ops, B, N, relu):
+    """usf_to_bf16: bf16 row-major copy, bf16 transposed copy (both zero padded to a multiple of 8 columns) and
+    fp32 column sums of the (ReLU-gated) input, in one pass -- bit-exact against torch's round-to-nearest-even."""
+    g = torch.Generator().manual_seed(B + N)
+    x = torch.randn(B, N, generator=g).cuda()
+    mask = torch.randn(B, N, generator=g).cuda() if relu else None
+    rows, tr, cs = ops.to_bf16(x, relu_mask=mask, want_rows=True, want_transposed=True, want_colsum=True)
+    v = torch.where(mask > 0, x, torch.zeros_like(x)) if relu else x
+    ref = v.to(torch.bfloat16)
+    assert rows.shape == (B, (N + 7) // 8 * 8) and tr.shape == (N, (B + 7) // 8 * 8)
+    assert torch.equal(rows[:, :N], ref) and torch.equal(tr[:, :B], ref.t())
+    assert float(rows[:, N:].float().abs().sum()) == 0.0 and float(tr[:, B:].float().abs().sum()) == 0.0
+    assert relerr(cs, v.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,K", [(64, 256, 784), (4096, 784, 784), (256, 1568, 256)])
+def test_linear_tc_autograd_function(ops, B, N, K):
+    """LinearTCFn (bf16 tensor-core forward / dgrad / wgrad) against fp64 autograd of the same layer."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, K, generator=g).cuda().requires_grad_()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_()
+    b = torch.randn(N, generator=g).cuda().requires_grad_()
+    dy = torch.randn(B, N, generator=g).cuda()
+    y = ops.LinearTCFn.apply(x, W, b, True)
+    y.backward(dy)
+    xr, Wr, br = (t.detach().double().cpu().requires_grad_() for t in (x, W, b))
+    # same ReLU gate as the GPU result: pre-activations within bf16 rounding of zero may legitimately gate differently
+    gate = (y.detach().cpu() > 0).double()
+    yr = (xr @ Wr.t() + br) * gate
+    yr.backward(dy.double().cpu())
+    assert relerr(y, yr) < 2e-2
+    for got, ref in ((x.grad, xr.grad), (W.grad, Wr.grad), (b.grad, br.grad)):
+        assert relerr(got, ref) < 3e-2
