@@ -172,6 +172,11 @@ class Flow(torch.nn.Module):
         if streams is None or streams[0].device != y.device:
             streams = [torch.cuda.Stream(device=y.device) for _ in range(8)]
             self.__dict__["_side_streams"] = streams
+            # the factor gradients are produced on the side streams on purpose; autograd syncs them with the
+            # accumulation stream, it only warns that this costs a synchronisation
+            warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if warn_off is not None:
+                warn_off(False)
         used = streams[:min(len(streams), len(mods))]
         for s in used:
             s.wait_stream(cur)

@@ -110,9 +110,10 @@ class DataParallelTrainer:
     host: ~300 autograd nodes and kernel launches cost 5-16 ms per step while the kernels need a fraction of
     that.  After `graph_warmup` eager steps with a given batch shape the whole step -- forward, the hand-written
     backward kernels, clipping, the optimizer update -- is captured once into a CUDA graph and every later step
-    with that shape is one `cudaGraphLaunch` on a static input buffer.  Used when there is a single rank, the
-    parameters live on a CUDA device and the optimizer was built with `capturable=True` (its step counters live
-    on the device); anything else, and any shape seen fewer than `graph_warmup` times, runs eagerly."""
+    with that shape is one `cudaGraphLaunch` on a static input buffer (multi-rank NCCL jobs capture the gradient
+    all-reduce with it).  Used when the parameters live on a CUDA device and the optimizer was built with
+    `capturable=True` (its step counters live on the device); anything else, and any shape seen fewer than
+    `graph_warmup` times, runs eagerly."""
 
     def __init__(self, flow, optimizer, group=None, gradient_clip=None, loss_fn=None, use_graph=None,
                  graph_warmup=3):
@@ -125,7 +126,12 @@ class DataParallelTrainer:
         on_cuda = bool(self.params) and all(p.is_cuda for p in self.params)
         if use_graph is None:
             use_graph = os.environ.get("USF_TRAIN_GRAPH", "1") != "0"
-        self.use_graph = bool(use_graph) and self.world == 1 and capturable and on_cuda
+        # multi-rank: the gradient all-reduce is captured with the step (NCCL collectives are graph-capturable); other
+        # backends (gloo in the CPU tests) run eagerly
+        nccl = self.world == 1 or (dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl")
+        if self.world > 1 and os.environ.get("USF_TRAIN_GRAPH_MULTI", "1") == "0":
+            nccl = False
+        self.use_graph = bool(use_graph) and nccl and capturable and on_cuda
         self.graph_warmup = int(graph_warmup)
         self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss]
         self.graph_replays = 0
@@ -161,9 +167,11 @@ class DataParallelTrainer:
         static_x = batch.detach().clone()
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
+        # thread_local: NCCL's watchdog thread may query events while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             loss = self.loss_fn(static_x)
             loss.backward()
+            self.allreduce_gradients()
             if self.clip is not None:
                 torch.nn.utils.clip_grad_norm_(self.params, self.clip)
             self.opt.step()
