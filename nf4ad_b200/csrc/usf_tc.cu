@@ -395,6 +395,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int TC_STAGES = args.stages;
   const uint32_t TC_STAGE_BYTES = args.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the chain may start its prologue
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
@@ -439,6 +440,11 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  // Programmatic dependent launch: this grid may have been started while the previous kernel of the chain was still
+  // draining (its CTAs that ran out of tiles free their SMs early); everything above -- barrier init, TMEM
+  // allocation, tensor-map prefetch, cluster sync -- touched no data of that kernel.  From here on we read and write
+  // the activation buffers, so wait for it to complete (a no-op when the launch carried no such dependency).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int total_tiles = args.m_tiles * args.n_tiles;
   // trace region of this (CTA, role): only CTAs 0 and 1 record
@@ -802,6 +808,7 @@ template <bool DBG>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ MlpMaps maps, MlpArgs args) {
   extern __shared__ uint8_t smem_raw[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the chain may start its prologue
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t h_base = smem_base + MLP_SLOTS * MLP_SLOT_BYTES;   // hidden activation tile (operand A of layers >= 2)
   const uint32_t bar_base = h_base + MLP_H_BYTES;
@@ -843,6 +850,11 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  // Programmatic dependent launch: this grid may have been started while the previous kernel of the chain was still
+  // draining (its CTAs that ran out of tiles free their SMs early); everything above -- barrier init, TMEM
+  // allocation, tensor-map prefetch, cluster sync -- touched no data of that kernel.  From here on we read and write
+  // the activation buffers, so wait for it to complete (a no-op when the launch carried no such dependency).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int L = args.L;
   int trn = 0;
   unsigned long long* trb = nullptr;
@@ -1212,6 +1224,13 @@ static uint32_t tc_backoff_ns() {
   return (uint32_t)v;
 }
 
+// USF_PDL=0 disables programmatic dependent launch of the tensor-core kernels.
+static bool tc_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("USF_PDL"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 int tc_pick_bn(int64_t N) {
   // balanced N tiles: as few tiles as possible, equal width, multiple of 16, <= 256
   const int64_t nt = ceil_div(N, TC_MAX_BN);
@@ -1296,13 +1315,15 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tc_pdl() ? 2 : 1;
   if (args.trace != nullptr || (args.dbg != 0 && !(args.dbg & 0x200))) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
   else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, args));
   return USF_OK;
@@ -1382,13 +1403,15 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
   cfg.blockDim = dim3(MLP_THREADS);
   cfg.dynamicSmemBytes = MLP_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tc_pdl() ? 2 : 1;
   if (args.trace != nullptr) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel<true>, tmA, maps, args));
   else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_mlp_coupling_kernel<false>, tmA, maps, args));
   return USF_OK;
