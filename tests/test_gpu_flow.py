@@ -480,3 +480,35 @@ def test_mixed_precision_training_step_replays_as_graph(P):
     losses = [float(tr.step(x)) for _ in range(20)]
     assert tr.graph_replays == 17
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_full_size_properties_c2(O, P):
+    """BASELINE.json configs[1] at its full benchmark size (65536 x 784, K=8, MLP 784-256-256-1568), where the fp64
+    oracle cannot score every row: (1) 96 random rows against the oracle; (2) a row's score does not depend on the
+    batch it travels in (full batch vs a 4096-row slice; the fused kernels tile rows in 256-row pair tiles and chunks
+    of 131072); (3) data -> latent -> data round trip; (4) the scores are finite everywhere and replay identically."""
+    import bench
+    fo = bench.build_flow(O, "cpu").double()
+    fp = bench.build_flow(P, "cuda")
+    fp.load_state_dict({k: v.float() for k, v in fo.state_dict().items()})
+    fp.precision = "bf16"
+    x = torch.randn(65536, 784, generator=torch.Generator().manual_seed(42))
+    xc = x.cuda()
+    with torch.no_grad():
+        lp = fp.log_prob(xc)
+        assert lp.shape == (65536,) and bool(torch.isfinite(lp).all())
+        idx = torch.randperm(65536, generator=torch.Generator().manual_seed(1))[:96]
+        ref = fo.log_prob(x[idx].double())
+        check_bf16(lp_err(lp[idx.cuda()], ref), strict=True)
+        sl = slice(30000, 34096)
+        lp_slice = fp.log_prob(xc[sl].contiguous())
+        assert float(((lp[sl] - lp_slice).abs() / lp_slice.abs().clamp_min(1.0)).max()) < 1e-5
+        lp_again = fp.log_prob(xc)
+        assert float(((lp - lp_again).abs() / lp.abs().clamp_min(1.0)).max()) < 1e-5   # atomics: last-ulp order effects only
+        z = fp.backward(xc[:8192].contiguous())
+        rt = fp.latent_to_data(z)
+        assert float(row_err(rt, x[:8192]).median()) < 6e-2
+        # fp32 tier on a slice of the same batch
+        fp.precision = "fp32"
+        lp32 = fp.log_prob(xc[idx.cuda()].contiguous())
+        assert float(lp_err(lp32, ref).max()) < FP32_TOL
