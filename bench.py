@@ -116,10 +116,12 @@ class ClockSampler:
 class NvmlSampler:
     """In-process NVML sampling thread (same counters as the nvidia-smi query above: SM clock, max SM
     clock, clock-event reasons).  Preferred over spawning `nvidia-smi -lms`, which was measured to stall
-    kernel launches on this box (a 2 ms step became 12 ms while it polled)."""
+    kernel launches on this box (a 2 ms step became 12 ms while it polled).  NVML queries and CUDA launches share
+    a driver lock: with three queries every 50 ms some runs lost 30-50 % of the timed region to stalled graph
+    launches (host enqueue 1.2-2.6 ms per step instead of 0.04), so the thread asks for two values every 100 ms."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index, period_s=0.05):
+    def __init__(self, index, period_s=0.1):
         import pynvml
         self.nv = pynvml
         pynvml.nvmlInit()
@@ -136,10 +138,6 @@ class NvmlSampler:
     def _one(self):
         nv = self.nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-        try:
-            self.rows.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-        except Exception:
-            pass
         try:
             self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
         except Exception:
@@ -163,7 +161,12 @@ class NvmlSampler:
 
     def stop(self):
         self.stop_flag = True
-        self.t.join(timeout=2)
+        if hasattr(self, "t"):
+            self.t.join(timeout=2)
+        try:        # one power reading, AFTER the timed region: every NVML query takes the driver lock the launches need
+            self.rows.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
         sm = sorted(self.sm)
         pw = sorted(self.rows)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
@@ -171,7 +174,22 @@ class NvmlSampler:
                 "power_w": pw[len(pw) // 2] if pw else None, "source": "nvml"}
 
 
+class NullSampler:
+    sm = []
+
+    def start(self):
+        pass
+
+    def sample_once(self):
+        pass
+
+    def stop(self):
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampling disabled (USF_BENCH_SAMPLER=0)"], "samples": 0}
+
+
 def make_sampler(index):
+    if os.environ.get("USF_BENCH_SAMPLER", "1") == "0":
+        return NullSampler()
     try:
         return NvmlSampler(index)
     except Exception:
@@ -280,11 +298,25 @@ def main():
     with torch.no_grad():
         # pre-warm: a step is only ~2-3 ms, so run the same step for >= 1 s first to bring the GPU out of its
         # idle P-state to steady clocks (untimed), then the W warm-up steps the contract asks for
+        # (untimed) until the step time has settled: a fresh process can sit in a slow state for a second or more
+        # (idle clocks / power state; steps of 3-13 ms were seen), which must not leak into the timed region.  Batches
+        # of 20 steps are timed with events until two consecutive batches agree within 3 %, for at least
+        # `prewarm_s` and at most 8 s.
         t_pw = time.perf_counter()
-        while time.perf_counter() - t_pw < args.prewarm_s:
-            for _ in range(10):
+        prev_ms = None
+        while args.prewarm_s > 0:
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(20):
                 lp = scorer.score_local(x)
+            p1.record()
             torch.cuda.synchronize()
+            cur_ms = p0.elapsed_time(p1)
+            elapsed = time.perf_counter() - t_pw
+            settled = prev_ms is not None and abs(cur_ms - prev_ms) <= 0.03 * prev_ms
+            if (elapsed >= args.prewarm_s and settled) or elapsed > 8.0:
+                break
+            prev_ms = cur_ms
         for _ in range(args.warmup):
             lp = scorer.score_local(x)
         barrier()
@@ -303,6 +335,11 @@ def main():
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
+        gstats = (ctypes.c_longlong * 4)()
+        gfail = ctypes.create_string_buffer(160)
+        _lib.lib().usf_debug_graph_stats(gstats, gfail, 160)
+        graph_info = {"replays": int(gstats[0]), "captures": int(gstats[1]), "failed_captures": int(gstats[2]),
+                      "eager_runs": int(gstats[3]), "last_failure": gfail.value.decode()}
         clocks = sampler.stop() if rank == 0 else None
         launches_per_step = flow.last_launches
         assert launches_per_step > 0, "fused CUDA path did not run"
@@ -412,7 +449,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
-            "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms, "graph": graph_info,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,

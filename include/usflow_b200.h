@@ -247,6 +247,10 @@ int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t
 int usf_profile_begin(int max_launches);
 int usf_profile_end(float* ms, int* tags, int* n_out);
 
+/* Debug: counters of the calling thread's usf_stack_run calls -- stats4 = {graph replays, successful captures,
+ * failed captures, eager first sightings}; last_failure receives the reason of the last failed capture. */
+int usf_debug_graph_stats(long long* stats4, char* last_failure, int failure_bytes);
+
 /* Debug: reads (and optionally clears) the flag raised when a bounded mbarrier wait of the tcgen05
  * GEMM expired (a pipeline protocol bug); synchronises the device. */
 int usf_debug_tc_timeout(int* flag, int reset);

@@ -381,6 +381,9 @@ constexpr int kGraphSlots = 16;
 thread_local GraphEntry g_graphs[kGraphSlots];
 thread_local cudaStream_t g_capture_stream = nullptr;
 thread_local uint64_t g_graph_clock = 0;
+// counters of this thread's usf_stack_run calls: {graph replays, successful captures, failed captures, eager runs}
+thread_local long long g_graph_stats[4] = {0, 0, 0, 0};
+thread_local char g_graph_fail[160] = "";
 
 inline uint64_t fnv(uint64_t h, const void* data, size_t n) {
   const unsigned char* p = static_cast<const unsigned char*>(data);
@@ -395,6 +398,16 @@ bool graphs_enabled() {
 }
 
 }  // namespace
+
+extern "C" int usf_debug_graph_stats(long long* stats4, char* last_failure, int failure_bytes) {
+  if (stats4 != nullptr)
+    for (int i = 0; i < 4; ++i) stats4[i] = g_graph_stats[i];
+  if (last_failure != nullptr && failure_bytes > 0) {
+    strncpy(last_failure, g_graph_fail, (size_t)failure_bytes - 1);
+    last_failure[failure_bytes - 1] = 0;
+  }
+  return USF_OK;
+}
 
 extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
                              float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
@@ -420,6 +433,7 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
   cudaStream_t s = as_stream(stream);
   if (slot != nullptr && slot->exec != nullptr) {
     slot->stamp = ++g_graph_clock;
+    ++g_graph_stats[0];
     USF_CUDA(cudaGraphLaunch(slot->exec, s));
     if (gpu_launches) *gpu_launches = slot->launches;
     return USF_OK;
@@ -430,6 +444,7 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
     victim->key = key;
     victim->seen = 1;
     victim->stamp = ++g_graph_clock;
+    ++g_graph_stats[3];
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
                            gpu_launches, stream);
   }
@@ -452,8 +467,12 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
                                  &launches, g_capture_stream);
   const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
   cudaGraphExec_t exec = nullptr;
+  cudaError_t ie = cudaSuccess;
   if (rc != USF_OK || ce != cudaSuccess || graph == nullptr ||
-      cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      (ie = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) {
+    ++g_graph_stats[2];
+    snprintf(g_graph_fail, sizeof(g_graph_fail), "rc=%d endCapture=%s instantiate=%s", rc, cudaGetErrorName(ce),
+             cudaGetErrorName(ie));
     cudaGetLastError();
     if (graph != nullptr) cudaGraphDestroy(graph);
     slot->key = 0;   // do not try again with this key
@@ -461,6 +480,7 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
                            gpu_launches, stream);
   }
   cudaGraphDestroy(graph);
+  ++g_graph_stats[1];
   slot->exec = exec;
   slot->launches = launches;
   USF_CUDA(cudaGraphLaunch(exec, s));
