@@ -407,7 +407,7 @@ def main():
             # Adam state, LU layers applied through their per-step dense inverse; "fp32" = the all-fp32 kernels
             tflow = build_flow(P, dev).train()
             tflow.precision = prec
-            opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True)   # the step replays as one CUDA graph
+            opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True, fused=True)   # the step replays as one CUDA graph
             trainer = DataParallelTrainer(tflow, opt)
             trainer.broadcast_parameters()
             for _ in range(5):          # 3 eager steps + capture + first replay (single rank), all untimed

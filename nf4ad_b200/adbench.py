@@ -49,7 +49,7 @@ class ADBenchFlow:
             print(f"Device: {self.device}")
         X = X.to(self.device)
         n = X.shape[0]
-        opt = torch.optim.Adam(self.flow_model.parameters(), lr=self.lr, capturable=True)   # device-side step counters: the step can replay as a CUDA graph
+        opt = torch.optim.Adam(self.flow_model.parameters(), lr=self.lr, capturable=True, fused=True)   # device-side step counters: the step can replay as a CUDA graph
         trainer = DataParallelTrainer(self.flow_model, opt, gradient_clip=self.gradient_clip)
         trainer.broadcast_parameters()
         self.flow_model.train()

@@ -157,6 +157,7 @@ def gemm_bf16(a, w, M, N, K, bias=None, relu=False):
 # tcgen05 kernel with bf16 operands and fp32 accumulation, parameters / gradients / optimizer state stay fp32, and an
 # LU layer is inverted once per step (weight space) so that no triangular solve ever sees the batch.
 _TC_TRAIN = False
+_TC_WEIGHT_SPACE = True      # the D^3 products of LUInverseFn.backward also run on the tensor cores
 
 
 class tc_training:
@@ -276,8 +277,17 @@ class LUInverseFn(torch.autograd.Function):
         P = torch.empty(D, D, device=dev, dtype=torch.float32)
         dW = torch.empty(D, D, device=dev, dtype=torch.float32)
         # P = A^T dA ;  dW = -(P A^T)
-        check(lib().usf_gemm(ptr(A), D, 1, ptr(dA), D, 1, ptr(P), D, 0, D, D, D, stream()), "usf_gemm")
-        check(lib().usf_gemm(ptr(P), D, 0, ptr(A), D, 0, ptr(dW), D, 0, D, D, D, stream()), "usf_gemm")
+        if _TC_WEIGHT_SPACE and D % 16 == 0:
+            # mixed precision: the two D^3 products on the tensor cores as well (bf16 operands, fp32 accumulate)
+            _, At, _ = to_bf16(A, want_rows=False, want_transposed=True)      # A^T rows
+            Ab, _, _ = to_bf16(A, want_rows=True)
+            _, dAt, _ = to_bf16(dA, want_rows=False, want_transposed=True)    # dA^T rows: operand [n, k] = dA[k, n]
+            P = gemm_bf16(At, dAt, D, D, D)
+            Pb, _, _ = to_bf16(P, want_rows=True)
+            dW = gemm_bf16(Pb, Ab, D, D, D)
+        else:
+            check(lib().usf_gemm(ptr(A), D, 1, ptr(dA), D, 1, ptr(P), D, 0, D, D, D, stream()), "usf_gemm")
+            check(lib().usf_gemm(ptr(P), D, 0, ptr(A), D, 0, ptr(dW), D, 0, D, D, D, stream()), "usf_gemm")
         Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
         dL = torch.zeros(D, D, device=dev, dtype=torch.float32)
         dU = torch.zeros(D, D, device=dev, dtype=torch.float32)

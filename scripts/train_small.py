@@ -11,7 +11,7 @@ for name, D, K, hid in (("C2 D=784 K=8 [256,256]", 784, 8, [256, 256]), ("test D
     torch.manual_seed(0)
     flow = build_flow(P, "NonUSFlow", D, K, ("mlp", hid), base="normal", affine_conjugation=True, prior_scale=1.0).to("cuda").train()
     flow.precision = os.environ.get("TRAIN_PREC", "fp32")
-    opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True, fused=True)
     tr = DataParallelTrainer(flow, opt)
     for B in (32, 64, 4096):
         x = torch.randn(B, D, device="cuda")
