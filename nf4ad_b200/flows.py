@@ -155,17 +155,18 @@ class Flow(torch.nn.Module):
         They are therefore issued up front on a few side streams (fork / join from the current stream; their backward
         nodes run on the same streams), and `LUTransform.backward` picks its matrix up from `_A_pre`."""
         B = y.shape[0]
-        if not y.is_cuda or B < 8 or B % 8:
-            return
         mods, seen = [], set()
         for layer in self.layers:
-            if isinstance(layer, InverseTransform) or not isinstance(layer, torch.nn.Module):
-                continue                      # applied through its forward map: no inverse needed
+            if not isinstance(layer, torch.nn.Module):
+                continue
             for m in layer.modules():
-                if isinstance(m, LUTransform) and id(m) not in seen and m.dim % 16 == 0:
-                    seen.add(id(m))
-                    mods.append(m)
-        if len(mods) < 2:
+                if isinstance(m, LUTransform):
+                    m.__dict__.pop("_A_pre", None)          # never carry a matrix over from an interrupted pass
+                    # a layer wrapped in InverseTransform is applied through its forward map: no inverse needed
+                    if not isinstance(layer, InverseTransform) and id(m) not in seen and m.dim % 16 == 0:
+                        seen.add(id(m))
+                        mods.append(m)
+        if not y.is_cuda or B < 8 or B % 8 or len(mods) < 2:
             return
         cur = torch.cuda.current_stream(y.device)
         streams = self.__dict__.get("_side_streams")
@@ -180,13 +181,13 @@ class Flow(torch.nn.Module):
         used = streams[:min(len(streams), len(mods))]
         for s in used:
             s.wait_stream(cur)
-        for i, lu in enumerate(mods):
-            with torch.cuda.stream(used[i % len(used)]):
+        # in the order the pass will need them (it walks the layers backwards); each consumer joins only its own stream
+        for i, lu in enumerate(reversed(mods)):
+            st = used[i % len(used)]
+            with torch.cuda.stream(st):
                 A = ops.LUInverseFn.apply(lu.L_raw, lu.U_raw)
             A.record_stream(cur)
-            lu.__dict__["_A_pre"] = A
-        for s in used:
-            cur.wait_stream(s)
+            lu.__dict__["_A_pre"] = (A, st)
 
     def _inverse_layers(self, y, context=None):
         """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""

@@ -288,6 +288,16 @@ class LUInverseFn(torch.autograd.Function):
         else:
             check(lib().usf_gemm(ptr(A), D, 1, ptr(dA), D, 1, ptr(P), D, 0, D, D, D, stream()), "usf_gemm")
             check(lib().usf_gemm(ptr(P), D, 0, ptr(A), D, 0, ptr(dW), D, 0, D, D, D, stream()), "usf_gemm")
+        if _TC_WEIGHT_SPACE and D % 16 == 0:
+            Lt = torch.tril(L_raw.detach(), -1)
+            Lt.diagonal().fill_(1.0)
+            Ut = torch.triu(U_raw.detach())
+            dWb, dWT, _ = to_bf16(dW, want_rows=True, want_transposed=True)
+            Ub, _, _ = to_bf16(Ut, want_rows=True)
+            _, LtT, _ = to_bf16(Lt, want_rows=False, want_transposed=True)
+            dL = torch.tril(gemm_bf16(dWb, Ub, D, D, D), -1)
+            dU = torch.triu(gemm_bf16(LtT, dWT, D, D, D))
+            return dL.neg_(), dU.neg_()
         Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
         dL = torch.zeros(D, D, device=dev, dtype=torch.float32)
         dU = torch.zeros(D, D, device=dev, dtype=torch.float32)
@@ -298,18 +308,39 @@ class LUInverseFn(torch.autograd.Function):
 
 
 class LUPackFn(torch.autograd.Function):
-    """W = L U from the raw factors; backward masks the gradient onto the two triangles."""
+    """W = L U from the raw factors; backward masks the gradient onto the two triangles.  In mixed-precision training
+    the three D^3 products (W = Lt Ut, dLt = dW Ut^T, dUt = Lt^T dW) run on the tensor cores like every other GEMM of
+    the step (bf16 operands, fp32 accumulate); the triangle masks are weight-space tensor ops."""
 
     @staticmethod
     def forward(ctx, L_raw, U_raw):
+        D = L_raw.shape[0]
+        ctx.tc = bool(_TC_TRAIN and _TC_WEIGHT_SPACE and L_raw.is_cuda and D % 16 == 0)
         ctx.save_for_backward(L_raw, U_raw)
-        return lu_pack(L_raw, U_raw)
+        if not ctx.tc:
+            return lu_pack(L_raw, U_raw)
+        Lt = torch.tril(L_raw.detach(), -1)
+        Lt.diagonal().fill_(1.0)
+        Ut = torch.triu(U_raw.detach())
+        Lb, _, _ = to_bf16(Lt, want_rows=True)
+        _, UtT, _ = to_bf16(Ut, want_rows=False, want_transposed=True)      # operand [n, k] = Ut[k, n]
+        return gemm_bf16(Lb, UtT, D, D, D)
 
     @staticmethod
     def backward(ctx, dW):
         L_raw, U_raw = ctx.saved_tensors
         D = L_raw.shape[0]
         dW = f32c(dW).contiguous()
+        if ctx.tc:
+            Lt = torch.tril(L_raw.detach(), -1)
+            Lt.diagonal().fill_(1.0)
+            Ut = torch.triu(U_raw.detach())
+            dWb, dWT, _ = to_bf16(dW, want_rows=True, want_transposed=True)
+            Ub, _, _ = to_bf16(Ut, want_rows=True)
+            _, LtT, _ = to_bf16(Lt, want_rows=False, want_transposed=True)
+            dL = torch.tril(gemm_bf16(dWb, Ub, D, D, D), -1)               # dW Ut^T, strictly lower part
+            dU = torch.triu(gemm_bf16(LtT, dWT, D, D, D))                  # Lt^T dW, upper part
+            return dL, dU
         Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
         dL = torch.zeros(D, D, device=dW.device, dtype=torch.float32)
         dU = torch.zeros(D, D, device=dW.device, dtype=torch.float32)

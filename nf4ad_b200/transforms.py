@@ -128,8 +128,11 @@ class LUTransform(BaseTransform):
         if ops.tc_train_enabled() and y2.is_cuda and self.dim % 16 == 0 and y2.shape[0] % 8 == 0 and y2.shape[0] >= 8:
             # mixed-precision training: x = A (y - b) with the dense inverse A = (LU)^{-1} (one weight-space solve per
             # step) applied by a tensor-core GEMM; the shift -A b is a weight-space matrix-vector product
-            A = self.__dict__.pop("_A_pre", None)        # issued up front by Flow._prefetch_lu_inverses
-            if A is None:
+            pre = self.__dict__.pop("_A_pre", None)      # issued up front by Flow._prefetch_lu_inverses
+            if pre is not None:
+                A, side = pre
+                torch.cuda.current_stream(y2.device).wait_stream(side)
+            else:
                 A = ops.LUInverseFn.apply(self.L_raw, self.U_raw)
             x = ops.linear_fn(y2, A, -(A @ self.bias), False)
         else:
