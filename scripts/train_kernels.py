@@ -11,7 +11,8 @@ P = nf4ad_b200.namespace()
 for name, D, K, hid, B in (("C5 D=128 K=10 [512,256]", 128, 10, [512, 256], 64), ("C2 D=784 K=8 [256,256]", 784, 8, [256, 256], 64), ("test D=32 K=3 [128]", 32, 3, [128], 64)):
     torch.manual_seed(0)
     flow = build_flow(P, "NonUSFlow", D, K, ("mlp", hid), base="normal", affine_conjugation=True, prior_scale=1.0).to("cuda").train()
-    opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True)
+    flow.precision = os.environ.get("TRAIN_PREC", "fp32")
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True, fused=True)
     tr = DataParallelTrainer(flow, opt)
     x = torch.randn(B, D, device="cuda")
     for _ in range(6): tr.step(x)
