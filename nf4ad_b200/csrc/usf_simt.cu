@@ -542,6 +542,22 @@ __global__ void usf_householder_kernel(const float* __restrict__ x, int64_t ldx,
 
 __global__ void usf_scale_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
                                  int inverse, float* y, int64_t ldy, int64_t B, int64_t D) {
+  // HBM-bound (4*D read + 4*D written per row): 16-byte accesses when the rows allow it, 4 columns per thread
+  const bool vec = (D & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0;
+  if (vec) {
+    const int64_t D4 = D >> 2, total4 = B * D4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / D4, d4 = i - r * D4;
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * d4);
+      const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * d4);
+      float4 o;
+      if (inverse) { o.x = v.x / sc.x; o.y = v.y / sc.y; o.z = v.z / sc.z; o.w = v.w / sc.w; }
+      else { o.x = v.x * sc.x; o.y = v.y * sc.y; o.z = v.z * sc.z; o.w = v.w * sc.w; }
+      *reinterpret_cast<float4*>(y + r * ldy + 4 * d4) = o;
+    }
+    return;
+  }
   const int64_t total = B * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / D, d = i - r * D;
@@ -627,18 +643,76 @@ __global__ void usf_base_logprob_kernel(int kind, const float* __restrict__ z, i
                                         const float* __restrict__ loc, const float* __restrict__ scale,
                                         int64_t scale_numel, const float* __restrict__ add, float add_coef,
                                         float* out, int64_t B, int64_t D) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  // HBM-bound (4*D read per row).  The normalisation sum_d (-log sc_d - const) is the same for every row: each CTA
+  // computes it once (all 8 warps together) instead of one logf per element; the data term uses 16-byte loads.
+  __shared__ float s_part[ROWS_PER_CTA];
+  __shared__ float s_const;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  {
+    float c = 0.f;
+    for (int64_t d = threadIdx.x; d < D; d += ROWS_PER_CTA * 32) {
+      const float sc = scale[scale_numel == 1 ? 0 : d];
+      c += kind == 0 ? (-logf(sc) - 0.91893853320467274178f) : -logf(2.f * sc);
+    }
+    c = warp_sum(c);
+    if (lane == 0) s_part[w] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_CTA; ++i) t += s_part[i];
+      s_const = t;
+    }
+    __syncthreads();
+  }
+  // loc and 1/scale staged once per CTA (<= 2048 columns): the row loop is then one 16-byte load + 8 FMA-pipe ops per 4
+  // columns, fully unrolled in groups so several loads are in flight per lane
+  constexpr int SMAX = 2048;
+  __shared__ __align__(16) float s_loc[SMAX];
+  __shared__ __align__(16) float s_inv[SMAX];
+  const bool staged = D <= SMAX;
+  if (staged) {
+    for (int64_t d = threadIdx.x; d < D; d += ROWS_PER_CTA * 32) {
+      s_loc[d] = loc[d];
+      s_inv[d] = 1.f / scale[scale_numel == 1 ? 0 : d];
+    }
+    __syncthreads();
+  }
+  const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + w;
   if (r >= B) return;
+  const float* zr = z + r * ldz;
   float acc = 0.f;
-  for (int64_t d = lane; d < D; d += 32) {
-    const float sc = scale[scale_numel == 1 ? 0 : d];
-    const float u = (z[r * ldz + d] - loc[d]) / sc;
-    if (kind == 0) acc += -0.5f * u * u - logf(sc) - 0.91893853320467274178f;
-    else acc += -fabsf(u) - logf(2.f * sc);
+  const bool vec = staged && (D & 3) == 0 && (ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0;
+  if (vec) {
+    const int n4 = (int)(D >> 2);
+    for (int i0 = lane; i0 < n4; i0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 32 * j;
+        v[j] = i < n4 ? *reinterpret_cast<const float4*>(zr + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 32 * j;
+        if (i < n4) {
+          const float4 l = *reinterpret_cast<const float4*>(s_loc + 4 * i);
+          const float4 q = *reinterpret_cast<const float4*>(s_inv + 4 * i);
+          const float u0 = (v[j].x - l.x) * q.x, u1 = (v[j].y - l.y) * q.y, u2 = (v[j].z - l.z) * q.z, u3 = (v[j].w - l.w) * q.w;
+          if (kind == 0) acc += -0.5f * (u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3);
+          else acc += -(fabsf(u0) + fabsf(u1) + fabsf(u2) + fabsf(u3));
+        }
+      }
+    }
+  } else {
+    for (int64_t d = lane; d < D; d += 32) {
+      const float sc = scale[scale_numel == 1 ? 0 : d];
+      const float u = (zr[d] - loc[d]) / sc;
+      acc += kind == 0 ? -0.5f * u * u : -fabsf(u);
+    }
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[r] = acc + (add != nullptr ? add_coef * add[r] : 0.f);
+  if (lane == 0) out[r] = acc + s_const + (add != nullptr ? add_coef * add[r] : 0.f);
 }
 
 // dz = dout * dlogp/dz ; column sums for loc / scale grads via atomics (one partial per warp-row).
