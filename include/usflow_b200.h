@@ -264,6 +264,16 @@ int usf_debug_tc_timeout(int* flag, int reset);
  * construction, only times matter (scripts/tc_ablate.py).  Production launches run an uninstrumented variant. */
 int usf_debug_tc_trace(int on, unsigned long long* out, int max_records);
 
+/* 3xTF32: fp32-grade accuracy on the tensor cores.  Every fp32 operand travels as hi + lo, where hi is what the tensor
+ * core sees when it reads fp32 as tf32 (low 13 mantissa bits dropped) and lo = value - hi; usf_split_lo computes lo
+ * for a (rows x cols) matrix.  usf_linear_tf32x3: y = act(x W^T + bias) with three tcgen05.mma.kind::tf32 per K step
+ * (x_hi W_hi + x_hi W_lo + x_lo W_hi); x, x_lo: (B, ldx), W, W_lo: (N, ldw) (ld multiples of 4, N multiple of 16 and
+ * <= 1024); y fp32 and optionally its low part y_lo (NULL to skip), both with leading dimension ldy. */
+int usf_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols, usf_stream_t stream);
+int usf_linear_tf32x3(const float* x, const float* x_lo, int64_t ldx, const float* W, const float* W_lo, int64_t ldw,
+                      const float* bias, int relu, float* y, float* y_lo, int64_t ldy, int64_t B, int64_t N, int64_t K,
+                      usf_stream_t stream);
+
 /* Standalone bf16 tensor-core GEMM y = act(x W^T + bias) (testing / conditioner layers):
  * x:(B,K) bf16 ldx, W:(N,K) bf16 ldw (ld multiples of 8, N multiple of 16), y:(B,N) bf16 or fp32. */
 int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W, int64_t ldw, const float* bias, int relu,

@@ -146,6 +146,25 @@ extern "C" int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W
   return tc_gemm(x, ldx, W, ldw, B, N, K, tc_pick_bn(N), ep, as_stream(stream));
 }
 
+extern "C" int usf_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols,
+                            usf_stream_t stream) {
+  USF_CHECK_ARG(x && lo && ldx >= cols && ldl >= cols, "usf_split_lo: bad arguments");
+  return launch_split_lo(x, ldx, lo, ldl, rows, cols, as_stream(stream));
+}
+
+extern "C" int usf_linear_tf32x3(const float* x, const float* x_lo, int64_t ldx, const float* W, const float* W_lo,
+                                 int64_t ldw, const float* bias, int relu, float* y, float* y_lo, int64_t ldy, int64_t B,
+                                 int64_t N, int64_t K, usf_stream_t stream) {
+  USF_CHECK_ARG(x && x_lo && W && W_lo && y, "usf_linear_tf32x3: null pointer");
+  EpiParams ep{};
+  ep.mode = relu ? EPI_BIAS_RELU : EPI_BIAS;
+  ep.bias = bias;
+  ep.out = y;
+  ep.ldo = ldy;
+  ep.out_bf16 = 0;
+  return tc3_gemm(x, x_lo, ldx, W, W_lo, ldw, B, N, K, tc_pick_bn(N), ep, y_lo, nullptr, as_stream(stream));
+}
+
 extern "C" int usf_profile_begin(int max_launches) {
   USF_CHECK_ARG(max_launches > 0 && !g_prof.on, "usf_profile_begin: bad state");
   g_prof.ev = new cudaEvent_t[2 * (size_t)max_launches];

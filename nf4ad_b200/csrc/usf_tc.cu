@@ -1135,6 +1135,311 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
+
+// ================================================================================================
+// 3xTF32 GEMM: fp32-grade accuracy on the tensor cores (the <= 1e-4 tier without the FFMA pipe).
+// Every fp32 operand is used as hi + lo, hi = the value the tensor core sees when it reads fp32 as tf32 (it drops the
+// low 13 mantissa bits), lo = a - hi (exact in fp32, precomputed by the producing kernel / at weight-pack time):
+//     a w ~= a_hi w_hi + a_hi w_lo + a_lo w_hi            (the dropped a_lo w_lo term is ~2^-21 relative)
+// three tcgen05.mma.kind::tf32 per K=8 step into the same fp32 TMEM accumulator.  Same CTA-pair structure as
+// usf_tc_gemm_kernel; a k-block is 32 fp32 columns (128-byte rows), a stage holds [A_hi | A_lo | W_hi | W_lo].
+// Epilogues write the fp32 result AND its low part (the next GEMM's A_lo), the coupling uses precise tanhf / expf.
+// ================================================================================================
+constexpr int T3_BK = 32;
+constexpr int T3_UMMA_K = 8;
+
+struct Tc3Args {
+  int64_t M, N, K;
+  int bn, n_tiles, m_tiles, n_valid, stages;
+  uint32_t stage_bytes, w_bytes;   // w_bytes: this CTA's W rows of one k-block, rounded up to 1 KB
+  uint32_t backoff_ns;
+  EpiParams ep;
+  float* out_lo;    // EPI_BIAS*: low part of the output (same leading dimension as ep.out), may be NULL
+  float* ub_lo;     // coupling modes: low part of the transformed columns (same leading dimension as ep.ub)
+};
+
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32 (format 2), both K-major
+__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n, uint32_t m) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void st16_f32(float* dst, const float (&v)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4)
+    reinterpret_cast<float4*>(dst)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, Tc3Args args) {
+  const int STAGES = args.stages;
+  const uint32_t STAGE_BYTES = args.stage_bytes;
+  extern __shared__ uint8_t smem_raw[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), num_units = (int)(gridDim.x >> 1);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t epi_base = bar_base + TC_BAR_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int total_tiles = args.m_tiles * args.n_tiles;
+  const int num_kb = (int)((args.K + T3_BK - 1) / T3_BK);
+  const uint32_t w_rows_bytes = (uint32_t)(args.bn >> 1) * 128u;
+  const uint32_t stage_tx = 2u * (2u * TC_A_BYTES + 2u * w_rows_bytes);
+  const uint32_t off_alo = TC_A_BYTES, off_w = 2u * TC_A_BYTES, off_wlo = 2u * TC_A_BYTES + args.w_bytes;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int t = unit; t < total_tiles && ok; t += num_units) {
+      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      int width = (int)(args.N - (int64_t)nt * args.bn);
+      if (width > args.bn) width = args.bn;
+      const int w_row = nt * args.bn + (int)cta_rank * (width >> 1);
+      const int a_row = (mt * 2 + (int)cta_rank) * TC_BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ok = mbar_wait(empty_bar(s), ph ^ 1u, args.backoff_ns);
+        if (!ok) break;
+        const uint32_t dst = smem_base + s * STAGE_BYTES;
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+          tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * T3_BK, a_row);
+          tma_load_2d_2sm(dst + off_alo, &tmAlo, full_bar(s), kb * T3_BK, a_row);
+          tma_load_2d_2sm(dst + off_w, &tmW, full_bar(s), kb * T3_BK, w_row);
+          tma_load_2d_2sm(dst + off_wlo, &tmWlo, full_bar(s), kb * T3_BK, w_row);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta_rank == 0) {
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      bool ok = true;
+      const int tail_steps = ((int)args.K - (num_kb - 1) * T3_BK + T3_UMMA_K - 1) / T3_UMMA_K;
+      const uint64_t desc_hi = make_smem_desc(0);
+      const uint32_t lo0 = (smem_base & 0x3FFFFu) >> 4, stage16 = STAGE_BYTES >> 4;
+      for (int t = unit; t < total_tiles && ok; t += num_units) {
+        const int nt = t % args.n_tiles;
+        int width = (int)(args.N - (int64_t)nt * args.bn);
+        if (width > args.bn) width = args.bn;
+        const uint32_t idesc = make_idesc_tf32((uint32_t)width, 2 * TC_BM);
+        ok = mbar_wait(tempty_bar(a), aph ^ 1u);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ok = mbar_wait(full_bar(s), ph);
+          if (!ok) break;
+          if (elect_one()) {
+            const uint64_t ah = desc_hi | (uint64_t)(lo0 + (uint32_t)s * stage16);
+            const uint64_t al = ah + (off_alo >> 4), wh = ah + (off_w >> 4), wl = ah + (off_wlo >> 4);
+            const int ksteps = kb + 1 < num_kb ? T3_BK / T3_UMMA_K : tail_steps;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_tf32_2sm(d_tmem, ah + 2u * k, wh + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32_2sm(d_tmem, ah + 2u * k, wl + 2u * k, idesc, 1u);
+              umma_tf32_2sm(d_tmem, al + 2u * k, wh + 2u * k, idesc, 1u);
+            }
+            umma_commit_2sm(empty_bar(s));
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        if (elect_one()) umma_commit_2sm(tfull_bar(a));
+        a ^= 1;
+        if (a == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;
+    const EpiParams& ep = args.ep;
+    float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));
+    const int mode = ep.mode;
+    const bool is_cpl = mode == EPI_COUPLING_INV || mode == EPI_COUPLING_FWD;
+    const bool is_add = mode == EPI_ADD_INV || mode == EPI_ADD_FWD;
+    const bool is_base = mode == EPI_BASE_NORMAL || mode == EPI_BASE_LAPLACE;
+    // column vectors resident for the whole kernel (host guarantees N <= TC_EPI_COLS)
+    for (int i = et; i < (int)args.N; i += 256) {
+      epi[i] = ep.bias != nullptr ? ep.bias[i] : 0.f;
+      if (is_base) {
+        const bool v2 = i < args.n_valid && ep.loc != nullptr;
+        epi[TC_EPI_COLS + i] = v2 ? ep.loc[i] : 0.f;
+        epi[2 * TC_EPI_COLS + i] = v2 ? ep.inv_scale[i] : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int a = 0;
+    uint32_t aph = 0;
+    for (int t = unit; t < total_tiles; t += num_units) {
+      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      const int64_t row = (int64_t)(mt * 2 + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
+      const bool rvalid = row < args.M;
+      const int64_t n0 = (int64_t)nt * args.bn;
+      int width = (int)(args.N - n0);
+      if (width > args.bn) width = args.bn;
+      const float* ev = epi + n0;
+      const bool ok = mbar_wait(tfull_bar(a), aph, args.backoff_ns);
+      if (ok) {
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+        if (mode == EPI_BIAS || mode == EPI_BIAS_RELU) {
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                v[j] += ev[c + j];
+                if (mode == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
+              }
+              float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
+              if (n0 + c + 16 <= args.n_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                st16_f32(dst, v);
+                if (args.out_lo != nullptr) {
+                  float l[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) l[j] = tf32_lo(v[j]);
+                  st16_f32(args.out_lo + row * ep.ldo + n0 + c, l);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c + j < args.n_valid) {
+                    dst[j] = v[j];
+                    if (args.out_lo != nullptr) args.out_lo[row * ep.ldo + n0 + c + j] = tf32_lo(v[j]);
+                  }
+              }
+            }
+          }
+        } else if (is_cpl || is_add) {
+          const int C = ep.C;
+          float lsum = 0.f;
+          for (int c = half * 16; c < C; c += 32) {
+            float sv[16], tv[16];
+            if (is_cpl) {
+              tmem_ld16(t_base + c, sv);
+              tmem_ld16(t_base + C + c, tv);
+            } else {
+              tmem_ld16(t_base + c, tv);
+            }
+            tmem_ld_wait();
+            const int coord0 = nt * C + c;
+            if (rvalid && coord0 < ep.Db) {
+              float* up = reinterpret_cast<float*>(ep.ub) + row * ep.ldub + coord0;
+              float* ulo = args.ub_lo + row * ep.ldub + coord0;
+              const float* bt = is_cpl ? ev + C + c : ev + c;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (coord0 + j < ep.Db) {
+                  const float u = up[j];
+                  const float tt = tv[j] + bt[j];
+                  float y;
+                  if (is_cpl) {
+                    const float ls = ep.clamp * tanhf(sv[j] + ev[c + j]);
+                    y = mode == EPI_COUPLING_INV ? (u - tt) * expf(-ls) : fmaf(u, expf(ls), tt);
+                    lsum += ls;
+                  } else {
+                    y = mode == EPI_ADD_INV ? u - tt : u + tt;
+                  }
+                  up[j] = y;
+                  ulo[j] = tf32_lo(y);
+                }
+              }
+            }
+          }
+          if (is_cpl && rvalid && ep.row_acc != nullptr)
+            atomicAdd(ep.row_acc + row, mode == EPI_COUPLING_INV ? -lsum : lsum);
+        } else {   // base density
+          float lsum = 0.f;
+          const float* ev_loc = ev + TC_EPI_COLS;
+          const float* ev_isc = ev + 2 * TC_EPI_COLS;
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float z = v[j] + ev[c + j];
+                if (ep.out != nullptr && n0 + c + j < args.n_valid)
+                  reinterpret_cast<float*>(ep.out)[row * ep.ldo + n0 + c + j] = z;
+                const float d = (z - ev_loc[c + j]) * ev_isc[c + j];
+                lsum += (mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+              }
+            }
+          }
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(tempty_bar(a));
+          else mbar_arrive_cluster(tempty_bar(a), 0);
+        }
+      }
+      a ^= 1;
+      if (a == 0) aph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// lo[i] = x[i] - tf32(x[i]) over a (rows x cols) fp32 matrix (pads included by the caller's cols)
+__global__ void usf_split_lo_kernel(const float* __restrict__ x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    lo[r * ldl + c] = tf32_lo(x[r * ldx + c]);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1159,9 +1464,10 @@ EncodeTiledFn get_encode_fn() {
 struct TmapKey {
   const void* base;
   int64_t rows, cols, ld;
-  int box_rows;
+  int box_rows, elem_bytes;
   bool operator==(const TmapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           elem_bytes == o.elem_bytes;
   }
 };
 struct TmapSlot {
@@ -1171,11 +1477,12 @@ struct TmapSlot {
 };
 constexpr int TMAP_CACHE_SLOTS = 256;
 
-int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// elem_bytes = 2 (bf16, box of 64 columns) or 4 (fp32 read as tf32, box of 32 columns): one box row is always 128 bytes.
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int elem_bytes = 2) {
   static thread_local TmapSlot cache[TMAP_CACHE_SLOTS];
-  const TmapKey key{base, rows, cols, ld, box_rows};
+  const TmapKey key{base, rows, cols, ld, box_rows, elem_bytes};
   const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 4) * 0x9E3779B97F4A7C15ull ^ (uint64_t)rows * 0xC2B2AE3D27D4EB4Full ^
-                     (uint64_t)cols * 0x165667B19E3779F9ull ^ (uint64_t)ld * 31 ^ (uint64_t)box_rows;
+                     (uint64_t)cols * 0x165667B19E3779F9ull ^ (uint64_t)ld * 31 ^ (uint64_t)box_rows ^ ((uint64_t)elem_bytes << 40);
   TmapSlot& slot = cache[(h >> 20) % TMAP_CACHE_SLOTS];
   if (slot.used && slot.key == key) {
     *tm = slot.map;
@@ -1187,10 +1494,11 @@ int make_tmap(CUtensorMap* tm, const uint16_t* base, int64_t rows, int64_t cols,
     return USF_E_CUDA;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr,
+  const CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1331,6 +1639,79 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   cfg.numAttrs = tc_pdl() ? 2 : 1;
   if (args.trace != nullptr || (args.dbg != 0 && !(args.dbg & 0x200))) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
   else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, args));
+  return USF_OK;
+}
+
+
+// 3xTF32 GEMM launcher (see usf_tc3_gemm_kernel).  A, Alo: (M, lda) fp32; W, Wlo: (N, ldw) fp32; leading dimensions
+// multiples of 4 (16-byte pitches), N multiple of 16 and <= TC_EPI_COLS.
+int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, const float* Wlo, int64_t ldw, int64_t M,
+             int64_t N, int64_t K, int bn, const EpiParams& ep, float* out_lo, float* ub_lo, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return USF_OK;
+  USF_CHECK_ARG(A && Alo && W && Wlo, "tc3_gemm: null operand");
+  USF_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0, "tc3_gemm: leading dimensions must be multiples of 4");
+  USF_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Alo) | reinterpret_cast<uintptr_t>(W) |
+                  reinterpret_cast<uintptr_t>(Wlo)) & 15) == 0, "tc3_gemm: operands must be 16-byte aligned");
+  USF_CHECK_ARG(bn >= 16 && bn <= TC_MAX_BN && (bn % 16) == 0 && (N % 16) == 0 && K > 0 && N <= TC_EPI_COLS,
+                "tc3_gemm: bad tile/shape (bn=%d N=%lld K=%lld)", bn, (long long)N, (long long)K);
+  const bool cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+  const bool add = ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD;
+  if (cpl) USF_CHECK_ARG(bn == 2 * ep.C && (N % bn) == 0 && ub_lo != nullptr && !ep.ub_bf16, "tc3_gemm: bad coupling tile");
+  if (add) USF_CHECK_ARG(bn == ep.C && (N % bn) == 0 && ub_lo != nullptr && !ep.ub_bf16, "tc3_gemm: bad additive tile");
+  static bool attr_set = false;
+  if (!attr_set) {
+    USF_CUDA(cudaFuncSetAttribute(usf_tc3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmAlo, tmW, tmWlo;
+  int rc = make_tmap(&tmA, A, M, K, lda, TC_BM, 4);
+  if (!rc) rc = make_tmap(&tmAlo, Alo, M, K, lda, TC_BM, 4);
+  if (!rc) rc = make_tmap(&tmW, W, N, K, ldw, bn / 2, 4);
+  if (!rc) rc = make_tmap(&tmWlo, Wlo, N, K, ldw, bn / 2, 4);
+  if (rc) return rc;
+  Tc3Args args;
+  memset(&args, 0, sizeof(args));
+  args.M = M; args.N = N; args.K = K; args.bn = bn;
+  args.n_tiles = (int)ceil_div(N, bn);
+  args.m_tiles = (int)ceil_div(M, 2 * TC_BM);
+  args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
+  args.ep = ep;
+  args.out_lo = out_lo;
+  args.ub_lo = ub_lo;
+  args.w_bytes = (uint32_t)round_up((int64_t)(bn / 2) * 128, 1024);
+  args.stage_bytes = 2u * TC_A_BYTES + 2u * args.w_bytes;
+  args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES) / args.stage_bytes);
+  if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
+  if (args.stages < 2) { set_error("tc3_gemm: tile does not fit in shared memory"); return USF_E_ARG; }
+  args.backoff_ns = tc_backoff_ns();
+  const int64_t total = (int64_t)args.m_tiles * args.n_tiles;
+  int64_t pairs = num_sms() / 2;
+  if (pairs > total) pairs = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl() ? 2 : 1;
+  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc3_gemm_kernel, tmA, tmAlo, tmW, tmWlo, args));
+  return USF_OK;
+}
+
+int launch_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return USF_OK;
+  const int64_t total = rows * cols;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  usf_split_lo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, lo, ldl, rows, cols);
+  USF_LAUNCH_CHECK("usf_split_lo_kernel");
   return USF_OK;
 }
 
