@@ -192,6 +192,9 @@ int usf_pack_matrix(const float* src, int64_t lds, const int32_t* row_idx, const
 
 #define USF_PREC_FP32 0 /* SIMT FFMA GEMMs, fp32 activations: log_prob rel. err <= 1e-4 tier */
 #define USF_PREC_BF16 1 /* tcgen05 bf16 GEMMs (fp32 accumulate in TMEM), bf16 activations: <= 1e-2 tier */
+#define USF_PREC_TF32X3 2 /* tcgen05 3xTF32 GEMMs (fp32 operands as hi + lo parts), fp32 activations: the <= 1e-4 tier on
+                             tensor cores.  usf_linear_desc.W then holds 2N rows: the N fp32 rows followed by their N
+                             low-part rows (W - tf32(W)); tile geometry (C) as for USF_PREC_BF16; every N <= 1024 */
 
 #define USF_MAX_MLP 8
 

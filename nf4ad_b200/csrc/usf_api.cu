@@ -78,7 +78,8 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan* p) {
   USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0, "stack: bad descriptor");
   USF_CHECK_ARG(st->n_blocks == 0 || st->blocks != nullptr, "stack: blocks pointer is null");
-  USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16, "stack: unknown precision %d", precision);
+  USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16 || precision == USF_PREC_TF32X3,
+                "stack: unknown precision %d", precision);
   int64_t wmax = st->D, hmax = 16, nmax = st->G_final.N;
   for (int b = 0; b < st->n_blocks; ++b) {
     const usf_block_desc& blk = st->blocks[b];
@@ -99,7 +100,9 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
   p->hid_bytes = align256((size_t)rows * p->ld_hid * esz);
   p->acc_bytes = align256((size_t)rows * sizeof(float));
   p->small_bytes = (precision == USF_PREC_FP32 && rows <= kSmallRows) ? align256((size_t)rows * (size_t)nmax * sizeof(float)) : 0;
-  p->total = 2 * p->act_bytes + 2 * p->hid_bytes + p->acc_bytes + p->small_bytes + 256;
+  // 3xTF32: every activation buffer has a low-part twin
+  const size_t twins = precision == USF_PREC_TF32X3 ? 2 : 1;
+  p->total = twins * (2 * p->act_bytes + 2 * p->hid_bytes) + p->acc_bytes + p->small_bytes + 256;
   return USF_OK;
 }
 
@@ -149,7 +152,7 @@ extern "C" int usf_linear_bf16(const uint16_t* x, int64_t ldx, const uint16_t* W
 extern "C" int usf_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols,
                             usf_stream_t stream) {
   USF_CHECK_ARG(x && lo && ldx >= cols && ldl >= cols, "usf_split_lo: bad arguments");
-  return launch_split_lo(x, ldx, lo, ldl, rows, cols, as_stream(stream));
+  return launch_split_lo(x, ldx, nullptr, lo, ldl, rows, cols, as_stream(stream));
 }
 
 extern "C" int usf_linear_tf32x3(const float* x, const float* x_lo, int64_t ldx, const float* W, const float* W_lo,
@@ -228,6 +231,17 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   uint8_t* act[2] = {base, base + p.act_bytes};
   uint8_t* hid[2] = {base + 2 * p.act_bytes, base + 2 * p.act_bytes + p.hid_bytes};
   float* small = p.small_bytes ? reinterpret_cast<float*>(base + 2 * p.act_bytes + 2 * p.hid_bytes + p.acc_bytes) : nullptr;
+  const bool t3 = precision == USF_PREC_TF32X3;
+  // low-part twins of the activation / hidden buffers (3xTF32 only), placed after the accumulator region
+  uint8_t* lo_base = base + 2 * p.act_bytes + 2 * p.hid_bytes + p.acc_bytes + p.small_bytes;
+  uint8_t* act_lo[2] = {lo_base, lo_base + p.act_bytes};
+  uint8_t* hid_lo[2] = {lo_base + 2 * p.act_bytes, lo_base + 2 * p.act_bytes + p.hid_bytes};
+  auto lo_of = [&](const void* hi) -> float* {   // the twin of one of the four hi buffers (or of a pointer into it)
+    if (!t3) return nullptr;
+    const uint8_t* h = reinterpret_cast<const uint8_t*>(hi);
+    return reinterpret_cast<float*>(lo_base + (h - base));
+  };
+  (void)act_lo; (void)hid_lo;
 
   int launches = 0;
 
@@ -238,6 +252,15 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       return tc_gemm(reinterpret_cast<const uint16_t*>(A), lda, L.Wb, L.ldw, rows, L.N, L.K, bn, ep, s);
     }
     USF_CHECK_ARG(L.W != nullptr, "usf_stack_run: fp32 weights missing in descriptor");
+    if (t3) {
+      const float* Af = reinterpret_cast<const float*>(A);
+      float* ub_lo = ep.ub != nullptr ? lo_of(ep.ub) : nullptr;
+      float* out_lo = (ep.out != nullptr && (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) &&
+                       reinterpret_cast<uint8_t*>(ep.out) >= base && reinterpret_cast<uint8_t*>(ep.out) < lo_base)
+                          ? lo_of(ep.out) : nullptr;
+      return tc3_gemm(Af, lo_of(Af), lda, L.W, L.W + (size_t)L.N * (size_t)L.ldw, L.ldw, rows, L.N, L.K, bn, ep, out_lo,
+                      ub_lo, s);
+    }
     return simt_gemm(reinterpret_cast<const float*>(A), lda, 0, L.W, L.ldw, 0, rows, L.N, L.K, ep, s, small,
                      p.small_bytes / sizeof(float));
   };
@@ -258,6 +281,12 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
     }
     if (rc) return rc;
     ++launches;
+    if (t3) {
+      rc = launch_split_lo(reinterpret_cast<const float*>(act[0]), p.ld_act, reinterpret_cast<float*>(act[0]), lo_of(act[0]),
+                           p.ld_act, rows, p.ld_act, s);
+      if (rc) return rc;
+      ++launches;
+    }
 
     for (int b = 0; b < st->n_blocks; ++b) {
       const usf_block_desc& blk = st->blocks[b];
@@ -271,7 +300,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
         ep.out_bf16 = bf16;
         {
           ProfScope ps(s, 1);
-          rc = gemm(act[cur], p.ld_act, blk.G, bf16 ? tc_pick_bn(blk.G.N) : 0, ep, rows);
+          rc = gemm(act[cur], p.ld_act, blk.G, (bf16 || t3) ? tc_pick_bn(blk.G.N) : 0, ep, rows);
         }
         if (rc) return rc;
         ++launches;
@@ -323,7 +352,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.out = hid[l & 1];
           ep.ldo = p.ld_hid;
           ep.out_bf16 = bf16;
-          if (bf16) bn = tc_pick_bn(L.N);
+          if (bf16 || t3) bn = tc_pick_bn(L.N);
         } else {
           if (blk.affine) ep.mode = st->inverse ? EPI_COUPLING_INV : EPI_COUPLING_FWD;
           else ep.mode = st->inverse ? EPI_ADD_INV : EPI_ADD_FWD;
@@ -334,7 +363,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.C = blk.C;
           ep.clamp = blk.clamp;
           ep.row_acc = row_acc;
-          if (bf16) bn = blk.affine ? 2 * blk.C : blk.C;
+          if (bf16 || t3) bn = blk.affine ? 2 * blk.C : blk.C;
         }
         {
           ProfScope ps(s, l + 1 < blk.n_mlp ? 2 : 3);
@@ -365,10 +394,10 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       }
       // fp32 path: the SIMT kernel stores exactly N = D columns
       usf_linear_desc Lf = st->G_final;
-      if (!bf16) Lf.N = st->D;
+      if (!bf16 && !t3) Lf.N = st->D;
       {
         ProfScope ps(s, 4);
-        rc = gemm(act[cur], p.ld_act, Lf, bf16 ? tc_pick_bn(Lf.N) : 0, ep, rows);
+        rc = gemm(act[cur], p.ld_act, Lf, (bf16 || t3) ? tc_pick_bn(Lf.N) : 0, ep, rows);
       }
       if (rc) return rc;
       ++launches;

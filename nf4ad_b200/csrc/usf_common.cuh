@@ -93,7 +93,8 @@ int tc_pick_bn(int64_t N);
 // 3xTF32 GEMM (fp32 operands as hi + lo parts, fp32-grade accuracy on the tensor cores), see usf_tc3_gemm_kernel
 int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, const float* Wlo, int64_t ldw, int64_t M,
              int64_t N, int64_t K, int bn, const EpiParams& ep, float* out_lo, float* ub_lo, cudaStream_t stream);
-int launch_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream);
+// hi == NULL: lo against the truncated read of x; hi != NULL (may alias x): hi = x rounded to tf32, lo = x - hi
+int launch_split_lo(const float* x, int64_t ldx, float* hi, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream);
 bool tc_mlp_supported(int n_layers, const int* N, const int* K, int Da);
 int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, const uint16_t* const* Wb, const int* ldw,
                     const float* const* bias, const int* N, const int* K, int bn_last, const EpiParams& ep,

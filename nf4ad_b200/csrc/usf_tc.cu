@@ -1170,7 +1170,9 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, 
 __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n, uint32_t m) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// hi = v rounded to nearest tf32 (low 13 mantissa bits zero, so the tensor core's truncating read is exact);
+// lo = v - hi is exact in fp32 and at most 2^-12 |v|
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void st16_f32(float* dst, const float (&v)[16]) {
 #pragma unroll
@@ -1334,20 +1336,25 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (mode == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
               }
               float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
+              // with a low-part twin the output travels as (hi, lo), hi + lo = v; without one it is v itself
+              float l[16];
+              if (args.out_lo != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float h = tf32_hi(v[j]);
+                  l[j] = v[j] - h;
+                  v[j] = h;
+                }
+              }
               if (n0 + c + 16 <= args.n_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                 st16_f32(dst, v);
-                if (args.out_lo != nullptr) {
-                  float l[16];
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) l[j] = tf32_lo(v[j]);
-                  st16_f32(args.out_lo + row * ep.ldo + n0 + c, l);
-                }
+                if (args.out_lo != nullptr) st16_f32(args.out_lo + row * ep.ldo + n0 + c, l);
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                   if (n0 + c + j < args.n_valid) {
                     dst[j] = v[j];
-                    if (args.out_lo != nullptr) args.out_lo[row * ep.ldo + n0 + c + j] = tf32_lo(v[j]);
+                    if (args.out_lo != nullptr) args.out_lo[row * ep.ldo + n0 + c + j] = l[j];
                   }
               }
             }
@@ -1369,22 +1376,53 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float* up = reinterpret_cast<float*>(ep.ub) + row * ep.ldub + coord0;
               float* ulo = args.ub_lo + row * ep.ldub + coord0;
               const float* bt = is_cpl ? ev + C + c : ev + c;
+              const bool full = coord0 + 16 <= ep.Db && (reinterpret_cast<uintptr_t>(up) & 31) == 0;
+              float u[16];
+              if (full) {     // 64 contiguous bytes of this thread's row per array: two 256-bit loads each; u = hi + lo
+                uint4 q[4], ql[4];
+                ld_global_256(up, q[0], q[1]);
+                ld_global_256(up + 8, q[2], q[3]);
+                ld_global_256(ulo, ql[0], ql[1]);
+                ld_global_256(ulo + 8, ql[2], ql[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  u[4 * i] = __uint_as_float(q[i].x) + __uint_as_float(ql[i].x);
+                  u[4 * i + 1] = __uint_as_float(q[i].y) + __uint_as_float(ql[i].y);
+                  u[4 * i + 2] = __uint_as_float(q[i].z) + __uint_as_float(ql[i].z);
+                  u[4 * i + 3] = __uint_as_float(q[i].w) + __uint_as_float(ql[i].w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) u[j] = coord0 + j < ep.Db ? up[j] + ulo[j] : 0.f;
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (coord0 + j < ep.Db) {
-                  const float u = up[j];
-                  const float tt = tv[j] + bt[j];
-                  float y;
-                  if (is_cpl) {
-                    const float ls = ep.clamp * tanhf(sv[j] + ev[c + j]);
-                    y = mode == EPI_COUPLING_INV ? (u - tt) * expf(-ls) : fmaf(u, expf(ls), tt);
-                    lsum += ls;
-                  } else {
-                    y = mode == EPI_ADD_INV ? u - tt : u + tt;
-                  }
-                  up[j] = y;
-                  ulo[j] = tf32_lo(y);
+                const float tt = tv[j] + bt[j];
+                if (is_cpl) {
+                  const float ls = ep.clamp * tanhf(sv[j] + ev[c + j]);   // padded coordinates: s = 0 -> ls = 0
+                  u[j] = mode == EPI_COUPLING_INV ? (u[j] - tt) * expf(-ls) : fmaf(u[j], expf(ls), tt);
+                  lsum += ls;
+                } else {
+                  u[j] = mode == EPI_ADD_INV ? u[j] - tt : u[j] + tt;
                 }
+              }
+              float l[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float h = tf32_hi(u[j]);
+                l[j] = u[j] - h;
+                u[j] = h;
+              }
+              if (full) {
+                st16_f32(up, u);
+                st16_f32(ulo, l);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (coord0 + j < ep.Db) {
+                    up[j] = u[j];
+                    ulo[j] = l[j];
+                  }
               }
             }
           }
@@ -1431,12 +1469,16 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// lo[i] = x[i] - tf32(x[i]) over a (rows x cols) fp32 matrix (pads included by the caller's cols)
-__global__ void usf_split_lo_kernel(const float* __restrict__ x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols) {
+// (hi, lo) split of a (rows x cols) fp32 matrix: hi = x rounded to tf32 (written to `hi`, which may alias x, or skipped
+// when NULL -- then lo is taken against the truncated value the tensor core would read from x itself), lo = x - hi
+__global__ void usf_split_lo_kernel(const float* x, int64_t ldx, float* hi, float* lo, int64_t ldl, int64_t rows, int64_t cols) {
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
-    lo[r * ldl + c] = tf32_lo(x[r * ldx + c]);
+    const float v = x[r * ldx + c];
+    const float h = hi != nullptr ? tf32_hi(v) : __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    lo[r * ldl + c] = v - h;
+    if (hi != nullptr) hi[r * ldx + c] = h;
   }
 }
 
@@ -1705,12 +1747,12 @@ int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, cons
   return USF_OK;
 }
 
-int launch_split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream) {
+int launch_split_lo(const float* x, int64_t ldx, float* hi, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return USF_OK;
   const int64_t total = rows * cols;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  usf_split_lo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, lo, ldl, rows, cols);
+  usf_split_lo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, hi, lo, ldl, rows, cols);
   USF_LAUNCH_CHECK("usf_split_lo_kernel");
   return USF_OK;
 }

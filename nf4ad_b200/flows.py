@@ -23,7 +23,7 @@ from .transforms import (
     MaskedCoupling, ScaleTransform, SequentialAffineTransform, run_conditioner, split_params,
 )
 
-_PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16}
+_PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16, "tf32x3": _lib.USF_PREC_TF32X3}
 
 
 def _default_precision():

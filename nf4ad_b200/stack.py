@@ -88,6 +88,7 @@ class CompiledStack:
         self.device = device
         self._keep = []          # every tensor the descriptors point to
         bf16 = precision == _lib.USF_PREC_BF16
+        self._t3 = precision == _lib.USF_PREC_TF32X3      # fp32 weights travel as [W ; W - tf32(W)] (2N rows)
         runs, couplings = _classify(layers)
         n = len(couplings)
         if n > 0:
@@ -182,6 +183,11 @@ class CompiledStack:
 
     # -------------------------------------------------------------------------------------------
     def _fill_linear(self, desc, W32, Wb, bias, N, K, ldw):
+        if getattr(self, "_t3", False) and W32 is not None:
+            if N > 1024:
+                raise Unsupported("3xTF32 path keeps the per-column vectors resident: N <= 1024")
+            hi = ((W32.view(torch.int32) + 0x1000) & -8192).view(torch.float32)   # rounded to tf32 (exact under the
+            W32 = torch.cat([hi, W32 - hi], dim=0).contiguous()                   # tensor core's truncating read)
         self._keep += [t for t in (W32, Wb, bias) if t is not None]
         desc.W = W32.data_ptr() if W32 is not None else None
         desc.Wb = Wb.data_ptr() if Wb is not None else None
@@ -218,7 +224,7 @@ class CompiledStack:
         Da, Db, idx_a, idx_b = L["Da"], L["Db"], L["idx_a"], L["idx_b"]
         dev = self.device
         # tile geometry of the last layer
-        if bf16:
+        if bf16 or self._t3:
             cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
             nt = -(-Db // cap)
             Cc = _round_up(-(-Db // nt), 16)

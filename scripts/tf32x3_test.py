@@ -26,10 +26,11 @@ def run(B, N, K, relu):
     check(lib().usf_debug_tc_timeout(_lib.C.byref(flag), 1))
     ref = x[:, :K].double().cpu() @ W[:, :K].double().cpu().t() + b.double().cpu()
     if relu: ref = ref.clamp_min(0)
-    err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+    yy = y.double().cpu() + ylo.double().cpu()          # the output travels as (hi, lo)
+    err = float((yy - ref).abs().max() / ref.abs().max())
     y32 = ops.linear(x[:, :K].contiguous(), W[:, :K].contiguous(), b, relu)
     err32 = float((y32.double().cpu() - ref).abs().max() / ref.abs().max())
-    lo_ok = float((y.double() - (y.view(torch.int32) & -8192).view(torch.float32).double() - ylo.double()).abs().max())
+    lo_ok = float(((y.view(torch.int32) & 8191) != 0).sum())   # hi must be tf32-exact (low 13 bits zero)
     for _ in range(3): call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,7 +38,7 @@ def run(B, N, K, relu):
     for _ in range(10): call()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 10 * 1e3
-    print(f"{B}x{N}x{K} relu={relu}: timeout_flag={flag.value} max rel err 3xTF32 {err:.2e} (fp32 SIMT {err32:.2e}) lo residual {lo_ok:.1e} | {us:.1f} us = {2.0*B*N*K/us/1e6:.1f} TFLOP/s", flush=True)
+    print(f"{B}x{N}x{K} relu={relu}: timeout_flag={flag.value} max rel err 3xTF32 {err:.2e} (fp32 SIMT {err32:.2e}) hi not tf32-exact: {lo_ok:.0f} | {us:.1f} us = {2.0*B*N*K/us/1e6:.1f} TFLOP/s", flush=True)
 
 for cfg in [(256, 208, 64, False), (300, 256, 392, True), (4096, 800, 784, False), (65536, 800, 784, False), (65536, 256, 392, True), (65536, 896, 256, False)]:
     run(*cfg)

@@ -512,3 +512,26 @@ def test_full_size_properties_c2(O, P):
         fp.precision = "fp32"
         lp32 = fp.log_prob(xc[idx.cuda()].contiguous())
         assert float(lp_err(lp32, ref).max()) < FP32_TOL
+
+
+def test_tf32x3_tier(O, P):
+    """`flow.precision = "tf32x3"`: the fused stack on 3xTF32 tensor-core GEMMs (fp32 activations carried as hi + lo).
+    Sits between the tiers: log_prob within 2e-4 of the fp64 oracle on the headline shapes (measured 1e-5 ... 6e-5;
+    the tensor core's accumulate truncates, which FFMA does not), latents / samples within 2e-4 of the row scale."""
+    for kind, D, K, cond, base, kw in (
+            ("NonUSFlow", 784, 2, ("mlp", [256, 256]), "normal", dict(affine_conjugation=True)),
+            ("USFlow", 128, 4, ("densenn1", [512, 256]), "normal", dict(affine_conjugation=True, householder=0)),
+            ("NonUSFlow", 500, 3, ("mlp", [128]), "laplace", dict(affine_conjugation=True)),
+            ("NonUSFlow", 33, 2, ("densenn2", [40]), "normal", dict(affine_conjugation=False, lu_transform=2, householder=2))):
+        fo, fp = _pair(O, P, kind, D, K, cond, base, 0.25, seed=D + K, **kw)
+        x = torch.randn(300, D, generator=torch.Generator().manual_seed(42))
+        zs = torch.randn(300, D, generator=torch.Generator().manual_seed(43))
+        with torch.no_grad():
+            fp.precision = "tf32x3"
+            lp, z, xs = fp.log_prob(x.cuda()), fp.backward(x.cuda()), fp.latent_to_data(zs.cuda())
+            assert fp.last_launches > 0
+            assert float(lp_err(lp, fo.log_prob(x.double())).max()) < 2e-4
+            assert float(row_err(z, fo.backward(x.double())).max()) < 2e-4
+            assert float(row_err(xs, fo.latent_to_data(zs.double())).max()) < 2e-4
+            # small batch and more than one internal tile
+            assert float(lp_err(fp.log_prob(x[:5].cuda()), fo.log_prob(x[:5].double())).max()) < 2e-4

@@ -169,3 +169,30 @@ def test_linear_tc_autograd_function(ops, B, N, K):
     assert relerr(y, yr) < 2e-2
     for got, ref in ((x.grad, xr.grad), (W.grad, Wr.grad), (b.grad, br.grad)):
         assert relerr(got, ref) < 3e-2
+
+
+@pytest.mark.parametrize("B,N,K,relu", [(300, 256, 392, True), (4096, 800, 784, False), (129, 208, 70, False)])
+def test_tcgen05_linear_tf32x3(ops, B, N, K, relu):
+    """3xTF32 GEMM (usf_linear_tf32x3): fp32 operands as hi + lo, three kind::tf32 MMAs per K step.  Against fp64:
+    max-norm relative error <= 2e-5 (the fp32 SIMT GEMM sits at ~1e-6; a single-pass tf32 GEMM at ~1e-3)."""
+    from nf4ad_b200._lib import lib, ptr, stream, check
+    g = torch.Generator().manual_seed(B + N + K)
+    ld = (K + 3) // 4 * 4
+    x = torch.zeros(B, ld); x[:, :K] = torch.randn(B, K, generator=g); x = x.cuda()
+    W = torch.zeros(N, ld); W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5; W = W.cuda()
+    b = torch.randn(N, generator=g).cuda()
+    xlo, Wlo = torch.empty_like(x), torch.empty_like(W)
+    check(lib().usf_split_lo(ptr(x), ld, ptr(xlo), ld, B, ld, stream()))
+    check(lib().usf_split_lo(ptr(W), ld, ptr(Wlo), ld, N, ld, stream()))
+    y, ylo = torch.empty(B, N, device="cuda"), torch.empty(B, N, device="cuda")
+    check(lib().usf_linear_tf32x3(ptr(x), ptr(xlo), ld, ptr(W), ptr(Wlo), ld, ptr(b), int(relu), ptr(y), ptr(ylo), N, B, N, K,
+                                  stream()))
+    torch.cuda.synchronize()
+    flag = C.c_int(0)
+    check(lib().usf_debug_tc_timeout(C.byref(flag), 1))
+    assert flag.value == 0
+    ref = x[:, :K].double().cpu() @ W[:, :K].double().cpu().t() + b.double().cpu()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert int(((y.view(torch.int32) & 8191) != 0).sum()) == 0          # hi part is tf32-exact
+    assert relerr(y.double() + ylo.double(), ref) < 2e-5
