@@ -377,8 +377,8 @@ def main():
     if rank == 0 and args.sweep:
         with torch.no_grad():
             for rows_s in (64, 1024, 16384, 262144):
-                for prec in ("bf16", "fp32"):
-                    if prec == "fp32" and rows_s > 16384:
+                for prec in ("bf16", "tf32x3", "fp32"):
+                    if (prec == "fp32" and rows_s > 16384) or (prec == "tf32x3" and rows_s < 16384):
                         continue
                     flow.precision = prec
                     xs = torch.randn(rows_s, D, device=dev)
