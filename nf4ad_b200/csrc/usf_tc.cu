@@ -1174,6 +1174,16 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n, uint32_t m) {
 // lo = v - hi is exact in fp32 and at most 2^-12 |v|
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
+// tanh / exp for the fp32-grade tier from two MUFU ops each instead of the ~25-instruction libm paths:
+//   tanh(x) = 1 - 2 / (exp(2x) + 1)   (ex2.approx: 2^-22 relative; absolute error of the result ~1e-7, which is what
+//   the log-det sum sees; saturates correctly for |x| large: ex2 -> inf or 0)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float tanh_mufu(float x) { return 1.f - __fdividef(2.f, ex2_fast(x * 2.8853900817779268f) + 1.f); }
+
 __device__ __forceinline__ void st16_f32(float* dst, const float (&v)[16]) {
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4)
@@ -1399,8 +1409,9 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 16; ++j) {
                 const float tt = tv[j] + bt[j];
                 if (is_cpl) {
-                  const float ls = ep.clamp * tanhf(sv[j] + ev[c + j]);   // padded coordinates: s = 0 -> ls = 0
-                  u[j] = mode == EPI_COUPLING_INV ? (u[j] - tt) * expf(-ls) : fmaf(u[j], expf(ls), tt);
+                  const float ls = ep.clamp * tanh_mufu(sv[j] + ev[c + j]);   // padded coordinates: s = 0 -> ls = 0
+                  const float e = ex2_fast((mode == EPI_COUPLING_INV ? -ls : ls) * 1.4426950408889634f);
+                  u[j] = mode == EPI_COUPLING_INV ? (u[j] - tt) * e : fmaf(u[j], e, tt);
                   lsum += ls;
                 } else {
                   u[j] = mode == EPI_ADD_INV ? u[j] - tt : u[j] + tt;
