@@ -398,13 +398,14 @@ def main():
 
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
     train_ms, train_B, train_steps, train_graph = float("nan"), args.train_rows, args.train_steps, False
-    train32_ms = float("nan")
+    train32_ms = train3_ms = float("nan")
     if train_steps > 0:
         from nf4ad_b200.parallel import DataParallelTrainer
         xb = x[:train_B]
-        for prec in ("bf16", "fp32"):
+        for prec in ("bf16", "tf32x3", "fp32"):
             # "bf16" = mixed precision: bf16 tensor-core GEMMs with fp32 accumulation, fp32 parameters / gradients /
-            # Adam state, LU layers applied through their per-step dense inverse; "fp32" = the all-fp32 kernels
+            # Adam state, LU layers applied through their per-step dense inverse; "tf32x3" = the same step with
+            # 3xTF32 tensor-core GEMMs (fp32-grade); "fp32" = the all-fp32 kernels
             tflow = build_flow(P, dev).train()
             tflow.precision = prec
             opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True, fused=True)   # the step replays as one CUDA graph
@@ -422,14 +423,16 @@ def main():
             if prec == "bf16":
                 train_ms = g0.elapsed_time(g1)
                 train_graph = trainer.graph_replays > 0
+            elif prec == "tf32x3":
+                train3_ms = g0.elapsed_time(g1)
             else:
                 train32_ms = g0.elapsed_time(g1)
             assert bool(torch.isfinite(loss))
             del tflow, opt, trainer
-    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms, train32_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_total, e2e_ms, train_ms, train32_ms, train3_ms = (float(v) for v in t)
 
     if rank == 0:
         n_gemm = sum(len(v) for k, v in per_tag.items() if k != 0)
@@ -473,6 +476,8 @@ def main():
                                        "parameters / optimizer state)", "graph_replay": bool(train_graph),
                              "value": train_B * world * train_steps / (train_ms * 1e-3), "unit": "samples/s",
                              "batch_per_gpu": train_B, "steps": train_steps, "ms_per_step": train_ms / train_steps,
+                             "tf32x3_path": {"value": train_B * world * train_steps / (train3_ms * 1e-3),
+                                             "ms_per_step": train3_ms / train_steps},
                              "fp32_path": {"value": train_B * world * train_steps / (train32_ms * 1e-3),
                                            "ms_per_step": train32_ms / train_steps}}
         if world == 1 and not args.no_cpu_baseline:

@@ -144,6 +144,12 @@ int usf_scale_bwd(const float* dy, int64_t lddy, const float* xy, int64_t ldxy, 
 int usf_to_bf16(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, uint16_t* rows, int64_t ldr,
                 uint16_t* transposed, int64_t ldt, float* colsum, int64_t B, int64_t N, usf_stream_t stream);
 
+/* The same operand pass for the 3xTF32 training GEMMs: fp32 (hi, lo) pairs (hi rounded to tf32, lo = value - hi) in
+ * row-major (B x ldr) and transposed (N x ldt) form, pads zero; leading dimensions multiples of 4. */
+int usf_to_tf32x3(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, float* rows_hi, float* rows_lo,
+                  int64_t ldr, float* t_hi, float* t_lo, int64_t ldt, float* colsum, int64_t B, int64_t N,
+                  usf_stream_t stream);
+
 /* out[c] (+)= coef * sum_b a[b,c]  (bias gradients). */
 int usf_colsum(const float* a, int64_t lda, float coef, int accumulate, float* out, int64_t B, int64_t N,
                usf_stream_t stream);

@@ -1049,6 +1049,57 @@ __global__ void usf_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, con
   }
 }
 
+// Same pass for the 3xTF32 training GEMMs: every output is an fp32 (hi, lo) pair, hi = value rounded to tf32,
+// lo = value - hi (see usf_tc3_gemm_kernel).
+__global__ void usf_to_tf32x3_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
+                                     float* rows_hi, float* rows_lo, int64_t ldr, float* tr_hi, float* tr_lo, int64_t ldt,
+                                     float* colsum, int64_t B, int64_t N, int64_t Bp, int64_t Np) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  float cs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < B && c < N) {
+      v = x[r * ldx + c];
+      if (mask != nullptr && !(mask[r * ldm + c] > 0.f)) v = 0.f;
+    }
+    tile[ty + 8 * i][tx] = v;
+    cs += v;
+    if (rows_hi != nullptr && r < B && c < Np) {
+      const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+      rows_hi[r * ldr + c] = h;
+      rows_lo[r * ldr + c] = v - h;
+    }
+  }
+  if (colsum != nullptr) {
+    __shared__ float part[8][32];
+    part[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += part[i][tx];
+      atomicAdd(colsum + c0 + tx, t);
+    }
+  }
+  if (tr_hi != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t c = c0 + ty + 8 * i, r = r0 + tx;     // tr[c, r] = x[r, c]
+      if (c < N && r < Bp) {
+        const float v = tile[tx][ty + 8 * i];
+        const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        tr_hi[c * ldt + r] = h;
+        tr_lo[c * ldt + r] = v - h;
+      }
+    }
+  }
+}
+
 // y[r, c] = act(y[r, c] + bias[c]) in place: second phase of the split-K form of usf_linear
 __global__ void usf_bias_act_kernel(float* y, int64_t ldy, const float* __restrict__ bias, int relu, int64_t B, int64_t N) {
   const int64_t total = B * N;
@@ -1074,6 +1125,23 @@ extern "C" int usf_to_bf16(const float* x, int64_t ldx, const float* relu_mask, 
       x, ldx, relu_mask, ldm, reinterpret_cast<__nv_bfloat16*>(rows), ldr, reinterpret_cast<__nv_bfloat16*>(transposed), ldt,
       colsum, B, N, Bp, Np);
   USF_LAUNCH_CHECK("usf_to_bf16_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_to_tf32x3(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, float* rows_hi,
+                             float* rows_lo, int64_t ldr, float* t_hi, float* t_lo, int64_t ldt, float* colsum, int64_t B,
+                             int64_t N, usf_stream_t stream) {
+  USF_CHECK_ARG(x != nullptr && B >= 0 && N > 0 && ldx >= N, "usf_to_tf32x3: bad arguments");
+  USF_CHECK_ARG((rows_hi == nullptr) == (rows_lo == nullptr) && (t_hi == nullptr) == (t_lo == nullptr),
+                "usf_to_tf32x3: hi and lo outputs come in pairs");
+  USF_CHECK_ARG(rows_hi == nullptr || ldr >= N, "usf_to_tf32x3: ldr < N");
+  USF_CHECK_ARG(t_hi == nullptr || ldt >= B, "usf_to_tf32x3: ldt < B");
+  if (B == 0) return USF_OK;
+  const int64_t Np = rows_hi != nullptr ? ldr : N, Bp = t_hi != nullptr ? ldt : B;
+  dim3 grid((unsigned)ceil_div(Np > N ? Np : N, 32), (unsigned)ceil_div(Bp > B ? Bp : B, 32));
+  usf_to_tf32x3_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, ldx, relu_mask, ldm, rows_hi, rows_lo, ldr, t_hi, t_lo,
+                                                                   ldt, colsum, B, N, Bp, Np);
+  USF_LAUNCH_CHECK("usf_to_tf32x3_kernel");
   return USF_OK;
 }
 

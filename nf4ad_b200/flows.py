@@ -143,8 +143,9 @@ class Flow(torch.nn.Module):
                 lp, _, _, n = cs.run(x2, want_logprob=True)
                 self.last_launches = n
                 return lp[0] if squeeze else lp
-        # autograd (training) pass; `precision == "bf16"` selects the mixed-precision form (ops.tc_training)
-        with ops.tc_training(self.precision == "bf16" and torch.is_grad_enabled()):
+        # autograd (training) pass; "bf16" / "tf32x3" select the tensor-core forms of its GEMMs (ops.tc_training)
+        mode = {"bf16": 1, "tf32x3": 2}.get(self.precision, 0) if torch.is_grad_enabled() else 0
+        with ops.tc_training(mode):
             z, neg_ladj = self._inverse_layers(x2, context)
             lp = self._base_log_prob(z) + neg_ladj
         return lp[0] if squeeze else lp

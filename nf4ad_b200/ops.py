@@ -153,18 +153,54 @@ def gemm_bf16(a, w, M, N, K, bias=None, relu=False):
     return y
 
 
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def to_t3(x, relu_mask=None, want_rows=True, want_transposed=False, want_colsum=False):
+    """fp32 x (B,N) -> (hi, lo) pairs for the 3xTF32 GEMM: rows (B, pad4(N)) and / or transposed (N, pad4(B)), + column
+    sums.  usf_to_tf32x3."""
+    require_cuda(x)
+    x, ldx = _rows(x)
+    B, N = x.shape
+    dev = x.device
+    rh = torch.empty(B, _pad4(N), device=dev, dtype=torch.float32) if want_rows else None
+    rl = torch.empty_like(rh) if want_rows else None
+    th = torch.empty(N, _pad4(B), device=dev, dtype=torch.float32) if want_transposed else None
+    tl = torch.empty_like(th) if want_transposed else None
+    cs = torch.zeros(N, device=dev, dtype=torch.float32) if want_colsum else None
+    m, ldm = (_rows(relu_mask) if relu_mask is not None else (None, 0))
+    check(lib().usf_to_tf32x3(ptr(x), ldx, ptr(m), ldm, ptr(rh), ptr(rl), _pad4(N), ptr(th), ptr(tl), _pad4(B), ptr(cs), B, N,
+                              stream()), "usf_to_tf32x3")
+    return (rh, rl), (th, tl), cs
+
+
+def gemm_t3(a, w, M, N, K, bias=None, relu=False):
+    """fp32 (M,N) = act(a w^T + bias) on the 3xTF32 tensor-core GEMM; a = (hi, lo) of (M, ld>=K), w = (hi, lo) of
+    (N, ld>=K); N % 16 == 0.  Column blocks of <= 1024 (the kernel keeps its per-column vectors resident)."""
+    y = torch.empty(M, N, device=a[0].device, dtype=torch.float32)
+    b = f32c(bias) if bias is not None else None
+    for n0 in range(0, N, 1024):
+        n1 = min(N, n0 + 1024)
+        wh, wl = w[0][n0:n1], w[1][n0:n1]
+        check(lib().usf_linear_tf32x3(ptr(a[0]), ptr(a[1]), a[0].stride(0), ptr(wh), ptr(wl), w[0].stride(0),
+                                      ptr(b[n0:n1]) if b is not None else None, int(relu), ptr(y[:, n0:n1]), None, N, M,
+                                      n1 - n0, K, stream()), "usf_linear_tf32x3")
+    return y
+
+
 # Mixed-precision training (flow.precision == "bf16" under autograd): the batch-sized GEMMs of the step run on the
 # tcgen05 kernel with bf16 operands and fp32 accumulation, parameters / gradients / optimizer state stay fp32, and an
 # LU layer is inverted once per step (weight space) so that no triangular solve ever sees the batch.
-_TC_TRAIN = False
-_TC_WEIGHT_SPACE = True      # the D^3 products of LUInverseFn.backward also run on the tensor cores
+_TC_TRAIN = 0                 # 0: fp32 kernels, 1: bf16 tensor-core GEMMs, 2: 3xTF32 tensor-core GEMMs (fp32-grade)
+_TC_WEIGHT_SPACE = True       # bf16 mode: the D^3 weight-space products run on the tensor cores as well
 
 
 class tc_training:
     """Context manager set by `Flow` around the autograd-recording forward pass."""
 
     def __init__(self, on):
-        self.on = bool(on)
+        self.on = int(on)          # False / 0, True / 1 (bf16), 2 (3xTF32)
 
     def __enter__(self):
         global _TC_TRAIN
@@ -178,7 +214,7 @@ class tc_training:
 
 
 def tc_train_enabled():
-    return _TC_TRAIN
+    return _TC_TRAIN != 0
 
 
 def linear_fn(x, W, bias, relu=False):
@@ -186,6 +222,10 @@ def linear_fn(x, W, bias, relu=False):
     (N, K multiples of 16, batch multiple of 8), else the fp32 kernels."""
     if _TC_TRAIN and x.is_cuda and x.dim() == 2 and x.shape[0] % 8 == 0 and x.shape[0] >= 8 \
             and W.shape[0] % 16 == 0 and W.shape[1] % 16 == 0:
+        if _TC_TRAIN == 2:
+            if x.shape[0] >= 256:        # below that the fp32 split-K kernels are as fast
+                return LinearT3Fn.apply(x, W, bias, relu)
+            return LinearFn.apply(x, W, bias, relu)
         return LinearTCFn.apply(x, W, bias, relu)
     return LinearFn.apply(x, W, bias, relu)
 
@@ -256,6 +296,33 @@ class LinearTCFn(torch.autograd.Function):
         return dx, dW, db, None
 
 
+class LinearT3Fn(torch.autograd.Function):
+    """LinearTCFn with 3xTF32 GEMMs: fp32-grade forward / dgrad / wgrad on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, relu):
+        B, K = x.shape
+        N = W.shape[0]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        xr, xT, _ = to_t3(x, want_rows=True, want_transposed=need_w)
+        Wr, WT, _ = to_t3(W, want_rows=True, want_transposed=need_x)
+        y = gemm_t3(xr, Wr, B, N, K, bias, relu)
+        ctx.relu, ctx.has_bias, ctx.shape = bool(relu), bias is not None, (B, N, K)
+        ctx.save_for_backward(xT[0], xT[1], WT[0], WT[1], y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xTh, xTl, WTh, WTl, y = ctx.saved_tensors
+        B, N, K = ctx.shape
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dyr, dyT, db = to_t3(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
+                             want_colsum=need_b)
+        dx = gemm_t3(dyr, (WTh, WTl), B, K, N) if need_x else None
+        dW = gemm_t3(dyT, (xTh, xTl), N, K, B) if need_w else None
+        return dx, dW, db, None
+
+
 class LUInverseFn(torch.autograd.Function):
     """A = (L U)^{-1} as a dense matrix, once per step (weight space): the triangular-solve kernel applied to the
     identity.  Backward: dW = -A^T dA A^T, then the factor gradients through usf_lu_pack_bwd."""
@@ -265,6 +332,7 @@ class LUInverseFn(torch.autograd.Function):
         D = L_raw.shape[0]
         eye = torch.eye(D, device=L_raw.device, dtype=torch.float32)
         A = lu_solve(eye, L_raw, U_raw, None, transpose=True)      # row i = e_i^T (LU)^{-1}
+        ctx.tc = bool(_TC_TRAIN == 1 and _TC_WEIGHT_SPACE)
         ctx.save_for_backward(A, L_raw, U_raw)
         return A
 
@@ -277,7 +345,7 @@ class LUInverseFn(torch.autograd.Function):
         P = torch.empty(D, D, device=dev, dtype=torch.float32)
         dW = torch.empty(D, D, device=dev, dtype=torch.float32)
         # P = A^T dA ;  dW = -(P A^T)
-        if _TC_WEIGHT_SPACE and D % 16 == 0:
+        if ctx.tc and D % 16 == 0:
             # mixed precision: the two D^3 products on the tensor cores as well (bf16 operands, fp32 accumulate)
             _, At, _ = to_bf16(A, want_rows=False, want_transposed=True)      # A^T rows
             Ab, _, _ = to_bf16(A, want_rows=True)
@@ -288,7 +356,7 @@ class LUInverseFn(torch.autograd.Function):
         else:
             check(lib().usf_gemm(ptr(A), D, 1, ptr(dA), D, 1, ptr(P), D, 0, D, D, D, stream()), "usf_gemm")
             check(lib().usf_gemm(ptr(P), D, 0, ptr(A), D, 0, ptr(dW), D, 0, D, D, D, stream()), "usf_gemm")
-        if _TC_WEIGHT_SPACE and D % 16 == 0:
+        if ctx.tc and D % 16 == 0:
             Lt = torch.tril(L_raw.detach(), -1)
             Lt.diagonal().fill_(1.0)
             Ut = torch.triu(U_raw.detach())
@@ -315,7 +383,7 @@ class LUPackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, L_raw, U_raw):
         D = L_raw.shape[0]
-        ctx.tc = bool(_TC_TRAIN and _TC_WEIGHT_SPACE and L_raw.is_cuda and D % 16 == 0)
+        ctx.tc = bool(_TC_TRAIN == 1 and _TC_WEIGHT_SPACE and L_raw.is_cuda and D % 16 == 0)
         ctx.save_for_backward(L_raw, U_raw)
         if not ctx.tc:
             return lu_pack(L_raw, U_raw)

@@ -464,6 +464,34 @@ def test_mixed_precision_training_gradients_follow_fp32(P):
     assert float(loss.detach()) < first
 
 
+def test_tf32x3_training_gradients_match_fp32(P):
+    """`flow.precision = "tf32x3"` under autograd: the same tensor-core training path with 3xTF32 GEMMs (fp32 (hi, lo)
+    operands).  fp32-grade: loss within 1e-5 relative, every gradient within 1e-3 of the fp32 path's norm."""
+    D, B = 64, 512
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", D, 3, ("mlp", [128, 128]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    flow = flow.to("cuda").train()
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(5)).cuda()
+    grads, losses = {}, {}
+    for prec in ("fp32", "tf32x3"):
+        flow.precision = prec
+        flow.zero_grad(set_to_none=True)
+        loss = -flow.log_prob(x).mean()
+        loss.backward()
+        losses[prec] = float(loss.detach())
+        grads[prec] = {n: p.grad.detach().clone() for n, p in flow.named_parameters() if p.grad is not None}
+    assert abs(losses["tf32x3"] - losses["fp32"]) <= 1e-5 * max(1.0, abs(losses["fp32"])), losses
+    assert set(grads["tf32x3"]) == set(grads["fp32"])
+    for n, g32 in grads["fp32"].items():
+        g3 = grads["tf32x3"][n]
+        assert torch.isfinite(g3).all(), n
+        if float(g32.norm()) < 1e-6:
+            continue
+        rel = float((g3 - g32).norm() / g32.norm())
+        assert rel < 1e-3, (n, rel)
+
+
 def test_mixed_precision_training_step_replays_as_graph(P):
     """The mixed-precision step (side-stream LU inversions, bf16 tensor-core GEMMs) must survive CUDA-graph capture
     and keep training."""

@@ -151,6 +151,27 @@ def test_to_bf16_operand_pass(ops, B, N, relu):
     assert relerr(cs, v.double().sum(0)) < 1e-5
 
 
+def test_linear_t3_autograd_function():
+    """LinearT3Fn: forward, dgrad, wgrad and the bias gradient on the 3xTF32 GEMM against float64."""
+    from nf4ad_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for (B, K, N, relu) in ((512, 64, 1568, False), (1000, 80, 48, True), (256, 784, 256, True)):
+        x = torch.randn(B, K, generator=g).cuda().requires_grad_(True)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)
+        b = torch.randn(N, generator=g).cuda().requires_grad_(True)
+        dy = torch.randn(B, N, generator=g).cuda()
+        y = ops.LinearT3Fn.apply(x, W, b, relu)
+        y.backward(dy)
+        xd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+        pre = xd @ Wd.T + bd
+        gate = (y.detach() > 0).double() if relu else 1.0          # the kernel's own gate (ties at rounding of zero)
+        yd = pre * gate
+        yd.backward(dy.double())
+        for got, ref, name in ((y, yd, "y"), (x.grad, xd.grad, "dx"), (W.grad, Wd.grad, "dW"), (b.grad, bd.grad, "db")):
+            err = float((got.detach().double() - ref.detach()).abs().max() / ref.detach().abs().max().clamp_min(1e-30))
+            assert err < 2e-5, (B, K, N, relu, name, err)
+
+
 @pytest.mark.parametrize("B,N,K", [(64, 256, 784), (4096, 784, 784), (256, 1568, 256)])
 def test_linear_tc_autograd_function(ops, B, N, K):
     """LinearTCFn (bf16 tensor-core forward / dgrad / wgrad) against fp64 autograd of the same layer."""
