@@ -453,8 +453,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms, "graph": graph_info,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
-                    "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scorer.last_h2d_bytes),
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps,
+                    "host_input_bytes_per_step": B * D * 4,
+                    "host_narrowing": bool(scorer.host_bf16 and args.precision == "bf16"),
+                    "host_threads": int(scorer.host_threads)},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": _lib.lib().usf_gemm_kernel_name(
                              _lib.USF_PREC_BF16 if args.precision == "bf16" else _lib.USF_PREC_FP32).decode(),

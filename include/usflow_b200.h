@@ -247,6 +247,19 @@ int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t
                   float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
                   int precision, int* gpu_launches, usf_stream_t stream);
 
+/* usf_stack_run (precision USF_PREC_BF16) on rows that are bf16 already: x_bf16:(B,D) with ldx in bf16 elements.  The bf16
+ * tier rounds its fp32 input to bf16 (round-to-nearest-even) as its first device step, so rows narrowed the same way
+ * beforehand -- usf_host_f32_to_bf16 on the host, halving the PCIe copy of a scoring call -- give bit-identical results. */
+int usf_stack_run_bf16in(const usf_stack_desc* st, const uint16_t* x_bf16, int64_t ldx, int64_t B, float* out_logprob,
+                         float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                         int* gpu_launches, usf_stream_t stream);
+
+/* HOST function (no CUDA call): dst[r, c] = bf16(src[r, c]), round-to-nearest-even, NaN -> 0x7FFF -- the bit pattern the
+ * device conversion produces.  src/dst are host pointers (pinned or not), leading dimensions in elements; `threads`
+ * host threads of a persistent pool (<= 0: all hardware threads).  Calls are serialised. */
+int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
+                         int threads);
+
 /* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libusflow_b200.so")
-SOURCES = ["usf_api.cu", "usf_simt.cu", "usf_tc.cu", "usf_trsm.cu"]
+SOURCES = ["usf_api.cu", "usf_simt.cu", "usf_tc.cu", "usf_trsm.cu", "usf_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        o = os.path.join(LIBDIR, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or any(_newer(d, o) for d in deps):
             jobs.append([NVCC, *FLAGS, "-c", s, "-o", o])
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             with open(cmd[-1].replace(".o", ".ptxas.log"), "w") as f:
                 f.write(r.stderr)
     if force or jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -206,10 +206,12 @@ extern "C" size_t usf_stack_workspace_bytes(const usf_stack_desc* st, int64_t B,
   return p.total;
 }
 
+// x_bf16: x points to bf16 rows (ldx in bf16 elements) instead of fp32 ones -- usf_stack_run_bf16in
 static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
                            float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
-                           int precision, int* gpu_launches, usf_stream_t stream) {
+                           int precision, int* gpu_launches, usf_stream_t stream, int x_bf16) {
   USF_CHECK_ARG(st != nullptr && x != nullptr && B >= 0, "usf_stack_run: bad arguments");
+  USF_CHECK_ARG(!x_bf16 || precision == USF_PREC_BF16, "usf_stack_run_bf16in: bf16 rows need the bf16 precision tier");
   USF_CHECK_ARG(!(out_logprob && (st->base_kind < 0 || !st->inverse)),
                 "usf_stack_run: log_prob needs the inverse direction and a base distribution");
   USF_CHECK_ARG(!(out_logprob && out_ladj), "usf_stack_run: request log_prob or ladj, not both");
@@ -275,9 +277,13 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
     int cur = 0;
     {
       ProfScope ps(s, 0);
-      rc = launch_convert_rows(x + r0 * ldx, ldx, bf16 ? reinterpret_cast<uint16_t*>(act[0]) : nullptr,
-                               bf16 ? nullptr : reinterpret_cast<float*>(act[0]), p.ld_act, rows, st->D, row_acc,
-                               acc_init, s);
+      if (x_bf16)
+        rc = launch_copy_rows_bf16(reinterpret_cast<const uint16_t*>(x) + r0 * ldx, ldx, reinterpret_cast<uint16_t*>(act[0]),
+                                   p.ld_act, rows, st->D, row_acc, acc_init, s);
+      else
+        rc = launch_convert_rows(x + r0 * ldx, ldx, bf16 ? reinterpret_cast<uint16_t*>(act[0]) : nullptr,
+                                 bf16 ? nullptr : reinterpret_cast<float*>(act[0]), p.ld_act, rows, st->D, row_acc,
+                                 acc_init, s);
     }
     if (rc) return rc;
     ++launches;
@@ -457,19 +463,20 @@ extern "C" int usf_debug_graph_stats(long long* stats4, char* last_failure, int 
   return USF_OK;
 }
 
-extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
-                             float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
-                             int precision, int* gpu_launches, usf_stream_t stream) {
+static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                            float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                            int precision, int* gpu_launches, usf_stream_t stream, int x_bf16) {
   if (st == nullptr || !graphs_enabled() || g_prof.on || B <= 0 || st->n_blocks < 0 ||
       (st->n_blocks > 0 && st->blocks == nullptr))
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                           gpu_launches, stream);
+                           gpu_launches, stream, x_bf16);
   uint64_t key = 1469598103934665603ull;
   key = fnv(key, st, sizeof(*st));
   if (st->n_blocks > 0) key = fnv(key, st->blocks, sizeof(usf_block_desc) * (size_t)st->n_blocks);
   const uint64_t extra[9] = {(uint64_t)(uintptr_t)x, (uint64_t)ldx, (uint64_t)B, (uint64_t)(uintptr_t)out_logprob,
                              (uint64_t)(uintptr_t)out_y, (uint64_t)ldy, (uint64_t)(uintptr_t)out_ladj,
-                             (uint64_t)(uintptr_t)workspace, (uint64_t)workspace_bytes * 4u + (uint64_t)precision};
+                             (uint64_t)(uintptr_t)workspace,
+                             (uint64_t)workspace_bytes * 8u + (uint64_t)precision + (x_bf16 ? 4u : 0u)};
   key = fnv(key, extra, sizeof(extra));
   if (key == 0) key = 1;
   GraphEntry* slot = nullptr;
@@ -494,7 +501,7 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
     victim->stamp = ++g_graph_clock;
     ++g_graph_stats[3];
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                           gpu_launches, stream);
+                           gpu_launches, stream, x_bf16);
   }
   // second identical call: capture the chain, instantiate, replay
   slot->stamp = ++g_graph_clock;
@@ -502,17 +509,17 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
       cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                           gpu_launches, stream);
+                           gpu_launches, stream, x_bf16);
   }
   int launches = 0;
   cudaGraph_t graph = nullptr;
   if (cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                           gpu_launches, stream);
+                           gpu_launches, stream, x_bf16);
   }
   const int rc = stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                                 &launches, g_capture_stream);
+                                 &launches, g_capture_stream, x_bf16);
   const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
   cudaGraphExec_t exec = nullptr;
   cudaError_t ie = cudaSuccess;
@@ -525,7 +532,7 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
     if (graph != nullptr) cudaGraphDestroy(graph);
     slot->key = 0;   // do not try again with this key
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
-                           gpu_launches, stream);
+                           gpu_launches, stream, x_bf16);
   }
   cudaGraphDestroy(graph);
   ++g_graph_stats[1];
@@ -534,4 +541,18 @@ extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t l
   USF_CUDA(cudaGraphLaunch(exec, s));
   if (gpu_launches) *gpu_launches = launches;
   return USF_OK;
+}
+
+extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,
+                             float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
+                             int precision, int* gpu_launches, usf_stream_t stream) {
+  return stack_run_cached(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
+                          gpu_launches, stream, 0);
+}
+
+extern "C" int usf_stack_run_bf16in(const usf_stack_desc* st, const uint16_t* x_bf16, int64_t ldx, int64_t B,
+                                    float* out_logprob, float* out_y, int64_t ldy, float* out_ladj, void* workspace,
+                                    size_t workspace_bytes, int* gpu_launches, usf_stream_t stream) {
+  return stack_run_cached(st, reinterpret_cast<const float*>(x_bf16), ldx, B, out_logprob, out_y, ldy, out_ladj, workspace,
+                          workspace_bytes, USF_PREC_BF16, gpu_launches, stream, 1);
 }

@@ -113,6 +113,8 @@ int trsm_rows(const float* T, int64_t D, bool lower, bool unit, bool trans, cons
 // ---- small helpers launched by the stack runner ---------------------------------------------
 int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_f32, int64_t ldy,
                         int64_t B, int64_t D, float* row_init, float init_value, cudaStream_t stream);
+int launch_copy_rows_bf16(const uint16_t* x, int64_t ldx, uint16_t* y, int64_t ldy, int64_t B, int64_t D, float* row_init,
+                          float init_value, cudaStream_t stream);
 int launch_bf16_to_f32(const uint16_t* x, int64_t ldx, float* y, int64_t ldy, int64_t B, int64_t D,
                        cudaStream_t stream);
 

@@ -924,6 +924,31 @@ __global__ void usf_convert_rows_kernel(const float* __restrict__ x, int64_t ldx
   }
 }
 
+// The same stage for rows that arrive as bf16 already (usf_stack_run_bf16in: the host narrowed them before the
+// PCIe copy): a padded copy, 8 columns per thread.
+__global__ void usf_copy_rows_bf16_kernel(const uint16_t* __restrict__ x, int64_t ldx, uint16_t* y, int64_t ldy, int64_t B,
+                                          int64_t D, float* row_init, float init_value) {
+  const int64_t groups = ldy >> 3;
+  const int64_t total = B * groups;
+  const bool vec_ok = ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups, c = (i - r * groups) << 3;
+    const uint16_t* src = x + r * ldx + c;
+    uint4 q;
+    if (vec_ok && c + 8 <= D) {
+      q = __ldg(reinterpret_cast<const uint4*>(src));
+    } else {
+      uint16_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c + j < D ? src[j] : (uint16_t)0;
+      q.x = v[0] | ((uint32_t)v[1] << 16); q.y = v[2] | ((uint32_t)v[3] << 16);
+      q.z = v[4] | ((uint32_t)v[5] << 16); q.w = v[6] | ((uint32_t)v[7] << 16);
+    }
+    *reinterpret_cast<uint4*>(y + r * ldy + c) = q;
+    if (c == 0 && row_init) row_init[r] = init_value;
+  }
+}
+
 __global__ void usf_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* y, int64_t ldy,
                                        int64_t B, int64_t D) {
   const int64_t total = B * D;
@@ -966,6 +991,18 @@ int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_
   usf_convert_rows_kernel<<<ew_grid(B * (ldy >> 3)), 256, 0, stream>>>(
       x, ldx, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy, B, D, row_init, init_value);
   USF_LAUNCH_CHECK("usf_convert_rows_kernel");
+  return USF_OK;
+}
+
+int launch_copy_rows_bf16(const uint16_t* x, int64_t ldx, uint16_t* y, int64_t ldy, int64_t B, int64_t D, float* row_init,
+                          float init_value, cudaStream_t stream) {
+  if (B <= 0) return USF_OK;
+  if ((ldy & 7) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) {
+    set_error("copy_rows_bf16: destination must be 16-byte aligned with ld %% 8 == 0");
+    return USF_E_ARG;
+  }
+  usf_copy_rows_bf16_kernel<<<ew_grid(B * (ldy >> 3)), 256, 0, stream>>>(x, ldx, y, ldy, B, D, row_init, init_value);
+  USF_LAUNCH_CHECK("usf_copy_rows_bf16_kernel");
   return USF_OK;
 }
 

@@ -281,9 +281,16 @@ class CompiledStack:
 
     # -------------------------------------------------------------------------------------------
     def run(self, x, want_logprob=False, want_y=False, want_ladj=False):
-        """x: (B, D) fp32 CUDA.  Returns (logprob | None, y | None, ladj | None, n_launches)."""
+        """x: (B, D) fp32 CUDA -- or bf16 rows for the bf16 tier (usf_stack_run_bf16in: bit-identical to fp32 rows that
+        round to them).  Returns (logprob | None, y | None, ladj | None, n_launches)."""
         _lib.require_cuda(x)
-        x, ldx = ops._rows(x)
+        x_bf16 = x.dtype == torch.bfloat16 and self.precision == _lib.USF_PREC_BF16 and x.dim() == 2
+        if x_bf16:
+            if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+                x = x.contiguous()
+            ldx = x.stride(0) if x.shape[0] > 1 else max(x.shape[1], 1)
+        else:
+            x, ldx = ops._rows(x)
         B = x.shape[0]
         dev = x.device
         lp = torch.empty(B, device=dev, dtype=torch.float32) if want_logprob else None
@@ -298,6 +305,10 @@ class CompiledStack:
             raise _lib.USFError("usf_stack_workspace_bytes failed: " + lib().usf_last_error().decode())
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         n = C.c_int(0)
-        check(lib().usf_stack_run(C.byref(self.desc), ptr(x), ldx, B, ptr(lp), ptr(y), self.D, ptr(ladj), ptr(ws),
-                                  nbytes, self.precision, C.byref(n), stream()), "usf_stack_run")
+        if x_bf16:
+            check(lib().usf_stack_run_bf16in(C.byref(self.desc), ptr(x), ldx, B, ptr(lp), ptr(y), self.D, ptr(ladj), ptr(ws),
+                                             nbytes, C.byref(n), stream()), "usf_stack_run_bf16in")
+        else:
+            check(lib().usf_stack_run(C.byref(self.desc), ptr(x), ldx, B, ptr(lp), ptr(y), self.D, ptr(ladj), ptr(ws),
+                                      nbytes, self.precision, C.byref(n), stream()), "usf_stack_run")
         return lp, y, ladj, n.value

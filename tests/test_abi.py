@@ -66,3 +66,38 @@ def test_state_dict_keys_match_oracle(O):
         b = build_flow(ns, kind, 6, 3, cond, **kw)
         assert list(a.state_dict().keys()) == list(b.state_dict().keys())
         b.load_state_dict(a.state_dict())
+
+
+def test_host_narrowing_is_round_to_nearest_even():
+    """usf_host_f32_to_bf16 (host cores, no CUDA): the bit pattern of a round-to-nearest-even fp32 -> bf16 conversion, for
+    contiguous and strided rows, any thread count, specials included -- what the device's first step would produce, so that
+    narrowing before the PCIe copy cannot change a score."""
+    import ctypes as C
+    import torch
+    from nf4ad_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1237, 83, generator=g) * torch.logspace(-30, 30, 83)
+    x[0, :8] = torch.tensor([float("inf"), -float("inf"), 0.0, -0.0, 1e-40, -1e-45, 3.3895e38, 3.4e38])
+    x[1, 0] = float("nan")
+    # ties: exactly half way between two bf16 values, both parities
+    x[2, 0] = torch.tensor([0x3F808000], dtype=torch.int32).view(torch.float32)[0]
+    x[2, 1] = torch.tensor([0x3F818000], dtype=torch.int32).view(torch.float32)[0]
+    ref = x.to(torch.bfloat16)
+    for threads in (1, 3, 8, 0):
+        for ldd in (83, 96):
+            out = torch.full((1237, ldd), 7.0, dtype=torch.bfloat16)
+            assert L.usf_host_f32_to_bf16(C.c_void_p(x.data_ptr()), 83, C.c_void_p(out.data_ptr()), ldd, 1237, 83, threads) == 0
+            got = out[:, :83]
+            nan = torch.isnan(ref)
+            assert torch.equal(torch.isnan(got), nan)
+            assert torch.equal(got.view(torch.int16)[~nan], ref.view(torch.int16)[~nan])
+            assert bool((out[:, 83:] == 7.0).all())            # pad columns untouched
+    # strided source rows, empty inputs, bad arguments
+    xs = x[:, :40]
+    out = torch.empty(1237, 40, dtype=torch.bfloat16)
+    assert L.usf_host_f32_to_bf16(C.c_void_p(xs.data_ptr()), 83, C.c_void_p(out.data_ptr()), 40, 1237, 40, 2) == 0
+    nan = torch.isnan(ref[:, :40])
+    assert torch.equal(out.view(torch.int16)[~nan], ref[:, :40].contiguous().view(torch.int16)[~nan])
+    assert L.usf_host_f32_to_bf16(None, 83, None, 83, 0, 83, 1) == 0
+    assert L.usf_host_f32_to_bf16(C.c_void_p(x.data_ptr()), 10, C.c_void_p(out.data_ptr()), 40, 5, 40, 1) != 0

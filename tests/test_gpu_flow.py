@@ -464,6 +464,39 @@ def test_mixed_precision_training_gradients_follow_fp32(P):
     assert float(loss.detach()) < first
 
 
+def test_bf16_rows_and_host_narrowing_are_bit_identical(P):
+    """bf16 tier: rows narrowed to bf16 beforehand (`usf_stack_run_bf16in`) -- on the device, or on the host cores inside
+    `ShardedScorer.predict_score_host` (half the PCIe bytes) -- give exactly the scores of the fp32 rows."""
+    from nf4ad_b200.parallel import ShardedScorer
+    D = 80
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", D, 3, ("mlp", [64, 64]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    flow = flow.to("cuda").eval()
+    flow.precision = "bf16"
+    x_host = torch.randn(40000, D, generator=torch.Generator().manual_seed(2))
+    x = x_host.cuda()
+    with torch.no_grad():
+        ref = flow.log_prob(x)
+        # the transformed points carry no atomics: exact; the per-row sums are accumulated with fp32 atomics whose order
+        # varies from run to run (the same call twice differs by an ulp of the sum), so those get an ulp-level tolerance
+        assert torch.equal(flow.backward(x.to(torch.bfloat16)), flow.backward(x))
+        same = lambda a, b: torch.allclose(a, b, rtol=1e-6, atol=1e-4)
+        assert same(flow.log_prob(x.to(torch.bfloat16)), ref)
+        assert torch.equal(flow.log_prob(x[:5].to(torch.bfloat16)), flow.log_prob(x[:5]))
+    sc = ShardedScorer(flow)
+    sc.host_bf16 = True             # (auto: only with >= 12 host threads per rank)
+    for xh in (x_host, x_host.pin_memory(), x_host[:16384], x_host[:33000].pin_memory()):
+        got = sc.predict_score_host(xh)
+        assert same(got, -ref[:xh.shape[0]].cpu())
+    sc.host_bf16 = False
+    assert same(sc.predict_score_host(x_host), -ref.cpu())
+    # other tiers take bf16 rows as values (widened), never through the narrowed entry
+    flow.precision = "fp32"
+    with torch.no_grad():
+        assert same(flow.log_prob(x[:64].to(torch.bfloat16)), flow.log_prob(x[:64].to(torch.bfloat16).float()))
+
+
 def test_tf32x3_training_gradients_match_fp32(P):
     """`flow.precision = "tf32x3"` under autograd: the same tensor-core training path with 3xTF32 GEMMs (fp32 (hi, lo)
     operands).  fp32-grade: loss within 1e-5 relative, every gradient within 1e-3 of the fp32 path's norm."""
