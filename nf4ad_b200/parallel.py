@@ -36,17 +36,18 @@ class ShardedScorer:
         self._copy_stream = None
         # bf16 tier: narrow the rows to bf16 on the host cores before the PCIe copy (half the bytes; the tier rounds its
         # input to bf16 as its first device step, so the scores are bit-identical).  Only with the default score function.
-        # Measured on the pool's 16-thread hosts (scripts/host_narrow.py): 16 threads narrow at 103 GB/s of fp32, twice the
-        # PCIe rate, and the call gets 1.35x faster; with 8 threads the conversion is the bottleneck and the plain copy
-        # wins -- so it is on only with >= 12 host threads for this rank (USF_HOST_BF16=1/0 forces it).
+        # Measured (scripts/host_narrow.py): one rank with the host's 16 threads narrows at 103 GB/s of
+        # fp32, twice the PCIe rate, and the call gets 1.35x faster; with 8 threads the conversion is the bottleneck, and
+        # two ranks with 12 threads each contend for host DRAM (5.3 vs 4.3 ms) -- so it is on by default only for a single
+        # rank per host with >= 16 host threads (USF_HOST_BF16=1/0 forces it).
         try:
             avail = len(os.sched_getaffinity(0))
         except AttributeError:
             avail = os.cpu_count() or 1
-        per_rank = max(1, avail // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-        self.host_threads = int(os.environ.get("USF_HOST_THREADS", "0")) or per_rank
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self.host_threads = int(os.environ.get("USF_HOST_THREADS", "0")) or max(1, avail // local_world)
         want = os.environ.get("USF_HOST_BF16")
-        self.host_bf16 = score_fn is None and (want == "1" or (want is None and self.host_threads >= 12))
+        self.host_bf16 = score_fn is None and (want == "1" or (want is None and local_world == 1 and self.host_threads >= 16))
         self.last_h2d_bytes = 0
         self.raw_rows = int(os.environ.get("USF_HOST_RAW_ROWS", "16384"))    # leading rows sent as fp32 (pinned input)
         self._ring = None
