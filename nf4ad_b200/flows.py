@@ -319,32 +319,55 @@ class Flow(torch.nn.Module):
 
     def fit(self, data_train, optim=torch.optim.Adam, optim_params=None, batch_size=32, shuffle=True,
             gradient_clip=None, device=None, jitter=1e-6, epochs=1):
-        """Feasibility check + jitter, then minimise -mean log_prob (- log_prior / N)."""
+        """Feasibility check + jitter, then minimise -mean log_prob (- log_prior / N): USFlows `Flow.fit` as nf4ad's runner
+        calls it (`explib/hyperopt.py:71-77`).  Returns the per-epoch mean loss.
+
+        The data set is gathered once and kept on the device; batches are drawn there, the step -- forward, hand-written
+        backward kernels, clipping, optimizer update -- runs through `DataParallelTrainer` (one CUDA-graph replay per step
+        for torch's Adam / AdamW, which are built `capturable`), and the host reads the loss once per epoch.  The
+        feasibility check (a host read of the LU diagonals) runs at the start of every epoch instead of every step."""
+        from .parallel import DataParallelTrainer
         if device is not None:
             self.to(device)
-        opt = optim(self.parameters(), **(optim_params or {}))
-        n = len(data_train)
+        dev = next(self.parameters()).device
+        if isinstance(data_train, torch.Tensor):
+            X = data_train
+        elif isinstance(data_train, torch.utils.data.TensorDataset):
+            X = data_train.tensors[0]
+        elif hasattr(data_train, "__array__"):
+            X = torch.as_tensor(data_train.__array__())
+        else:                                        # a map-style dataset of rows or (row, label, ...) tuples
+            rows = [data_train[j] for j in range(len(data_train))]
+            X = torch.stack([torch.as_tensor(r[0] if isinstance(r, (tuple, list)) else r) for r in rows])
+        X = X.to(device=dev, dtype=torch.float32)
+        n = X.shape[0]
+        params = dict(optim_params or {})
+        if dev.type == "cuda" and optim in (torch.optim.Adam, torch.optim.AdamW):
+            params.setdefault("capturable", True)
+            params.setdefault("fused", True)
+        opt = optim(self.parameters(), **params)
+        with_prior = getattr(self, "prior_scale", None) is not None
+
+        def loss_fn(batch):
+            loss = -self.log_prob(batch).mean()
+            if with_prior:
+                loss = loss - self.log_prior() / n
+            return loss
+
+        trainer = DataParallelTrainer(self, opt, gradient_clip=gradient_clip, loss_fn=loss_fn)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(torch.initial_seed()) & 0x7FFFFFFF)
         losses = []
         for _ in range(epochs):
-            perm = torch.randperm(n) if shuffle else torch.arange(n)
-            total = 0.0
+            while not self.is_feasible():
+                self.add_jitter(jitter)
+            perm = torch.randperm(n, device=dev, generator=gen) if shuffle else torch.arange(n, device=dev)
+            total = torch.zeros((), device=dev)
             for i in range(0, n, batch_size):
-                idx = perm[i:i + batch_size]
-                rows = [data_train[int(j)] for j in idx]
-                rows = [r[0] if isinstance(r, (tuple, list)) else r for r in rows]
-                batch = torch.stack(rows).to(self.device)
-                while not self.is_feasible():
-                    self.add_jitter(jitter)
-                opt.zero_grad()
-                loss = -self.log_prob(batch).mean()
-                if getattr(self, "prior_scale", None) is not None:
-                    loss = loss - self.log_prior() / n
-                loss.backward()
-                if gradient_clip is not None:
-                    torch.nn.utils.clip_grad_norm_(self.parameters(), gradient_clip)
-                opt.step()
-                total += float(loss.detach()) * len(idx)
-            losses.append(total / n)
+                batch = X.index_select(0, perm[i:i + batch_size])
+                total += trainer.step(batch) * batch.shape[0]
+            losses.append(float(total.cpu()) / max(n, 1))         # one device -> host read per epoch
+        self.fit_graph_replays = trainer.graph_replays
         return losses
 
 

@@ -155,13 +155,12 @@ class LUTransform(BaseTransform):
     def log_prior(self):
         if self.prior_scale is None:
             return 0.0
+        # Gaussian prior N(0, s) over the active entries (strict lower triangle of L, upper triangle of U, bias): fixed-shape
+        # tensor ops only (no boolean indexing), so that a training step with the MAP term replays as a CUDA graph
         s = float(self.prior_scale)
-        active = torch.cat([
-            self.L_raw[torch.tril(torch.ones_like(self.L_raw), -1) > 0],
-            self.U_raw[torch.triu(torch.ones_like(self.U_raw), 0) > 0],
-            self.bias,
-        ])
-        return (-0.5 * (active / s) ** 2 - math.log(s) - 0.5 * math.log(2 * math.pi)).sum()
+        D = self.L_raw.shape[0]
+        sq = (torch.tril(self.L_raw, -1) ** 2).sum() + (torch.triu(self.U_raw) ** 2).sum() + (self.bias ** 2).sum()
+        return -0.5 * sq / (s * s) - (D * D + D) * (math.log(s) + 0.5 * math.log(2 * math.pi))
 
 
 class HouseholderTransform(BaseTransform):

@@ -101,3 +101,19 @@ def test_host_narrowing_is_round_to_nearest_even():
     assert torch.equal(out.view(torch.int16)[~nan], ref[:, :40].contiguous().view(torch.int16)[~nan])
     assert L.usf_host_f32_to_bf16(None, 83, None, 83, 0, 83, 1) == 0
     assert L.usf_host_f32_to_bf16(C.c_void_p(x.data_ptr()), 10, C.c_void_p(out.data_ptr()), 40, 5, 40, 1) != 0
+
+
+def test_lu_log_prior_matches_the_oracle_formula():
+    """`LUTransform.log_prior` is written with fixed-shape ops (graph-capturable); same value as the oracle's
+    boolean-indexed form (oracle/shim/src/usflows/transforms.py)."""
+    import torch
+    import oracle
+    from nf4ad_b200.transforms import LUTransform
+    ns = oracle.load()
+    torch.manual_seed(3)
+    ours = LUTransform(9, prior_scale=0.7).double()
+    theirs = ns.transforms.LUTransform(9, prior_scale=0.7).double()
+    theirs.load_state_dict(ours.state_dict())
+    a, b = ours.log_prior(), theirs.log_prior()
+    assert abs(float(a) - float(b)) <= 1e-12 * abs(float(b))
+    assert LUTransform(4, prior_scale=None).log_prior() == 0.0

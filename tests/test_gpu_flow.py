@@ -464,6 +464,25 @@ def test_mixed_precision_training_gradients_follow_fp32(P):
     assert float(loss.detach()) < first
 
 
+def test_flow_fit_runs_on_the_graph_trainer(P):
+    """USFlows `Flow.fit` (the call `explib/hyperopt.py:71-77` makes): MAP loss with the LU prior, device-resident data,
+    CUDA-graph replay of the step, one loss per epoch -- and the loss goes down."""
+    D = 32
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", D, 3, ("mlp", [64]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    flow = flow.to("cuda")
+    g = torch.Generator().manual_seed(4)
+    data = torch.randn(512, D, generator=g) * 0.5 + 0.3
+    ds = torch.utils.data.TensorDataset(data, torch.zeros(512))
+    losses = flow.fit(ds, torch.optim.Adam, {"lr": 2e-3}, batch_size=64, gradient_clip=5.0, epochs=6)
+    assert len(losses) == 6 and np.all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert flow.fit_graph_replays >= 8 * 6 - 4          # all but the warm-up steps of the first epoch
+    # a ragged data set (last batch smaller) and a plain tensor work the same way
+    losses2 = flow.fit(data[:200], batch_size=64, epochs=2, optim_params={"lr": 1e-3})
+    assert len(losses2) == 2 and np.all(np.isfinite(losses2))
+
+
 def test_bf16_rows_and_host_narrowing_are_bit_identical(P):
     """bf16 tier: rows narrowed to bf16 beforehand (`usf_stack_run_bf16in`) -- on the device, or on the host cores inside
     `ShardedScorer.predict_score_host` (half the PCIe bytes) -- give exactly the scores of the fp32 rows."""
