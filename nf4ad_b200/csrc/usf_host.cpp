@@ -4,6 +4,7 @@
 // the copy gives bit-identical scores.
 #include <stdint.h>
 #include <string.h>
+#include <pthread.h>
 #include <immintrin.h>
 
 #include <atomic>
@@ -79,9 +80,15 @@ struct Job {
 // counter during one.  One job at a time (calls are serialised by `call_mu`).
 class Pool {
  public:
+  // Leaked on purpose (workers may outlive static destruction order).  A forked child has none of the parent's worker
+  // threads and possibly a locked mutex: it gets a fresh pool.
   static Pool& get() {
-    static Pool* p = new Pool();   // leaked on purpose: workers may outlive static destruction order
-    return *p;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      instance() = new Pool();
+      pthread_atfork(nullptr, nullptr, [] { instance() = new Pool(); });
+    });
+    return *instance();
   }
 
   void run(const Job& job, int threads) {
@@ -112,6 +119,10 @@ class Pool {
 
  private:
   Pool() : fn_(pick_narrow()) {}
+  static Pool*& instance() {
+    static Pool* p = nullptr;
+    return p;
+  }
 
   static int64_t block_rows(const Job& j) {
     int64_t r = (int64_t)(1 << 16) / (j.cols > 0 ? j.cols : 1);   // ~64K elements per block

@@ -100,6 +100,38 @@ def test_host_narrowing_is_round_to_nearest_even():
     nan = torch.isnan(ref[:, :40])
     assert torch.equal(out.view(torch.int16)[~nan], ref[:, :40].contiguous().view(torch.int16)[~nan])
     assert L.usf_host_f32_to_bf16(None, 83, None, 83, 0, 83, 1) == 0
+    # a forked child (e.g. a data-loader worker) has none of the parent's pool threads: it must get its own pool.
+    # No torch calls in the child (its OpenMP pool does not survive a fork either); the parent waits with a deadline.
+    import os
+    import signal
+    import time
+    import warnings
+    x2 = torch.randn(500, 64, generator=g)
+    want = bytes(x2.to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+    src_ptr = C.c_void_p(x2.data_ptr())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        pid = os.fork()
+    if pid == 0:
+        try:
+            buf = (C.c_uint16 * (500 * 64))()
+            rc = L.usf_host_f32_to_bf16(src_ptr, 64, buf, 64, 500, 64, 4)
+            os._exit(0 if rc == 0 and bytes(buf) == want else 1)
+        finally:
+            os._exit(2)
+    deadline = time.time() + 30
+    status = None
+    while time.time() < deadline:
+        done, st = os.waitpid(pid, os.WNOHANG)
+        if done == pid:
+            status = st
+            break
+        time.sleep(0.05)
+    if status is None:
+        os.kill(pid, signal.SIGKILL)
+        os.waitpid(pid, 0)
+        raise AssertionError("forked child hung in usf_host_f32_to_bf16")
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
     assert L.usf_host_f32_to_bf16(C.c_void_p(x.data_ptr()), 10, C.c_void_p(out.data_ptr()), 40, 5, 40, 1) != 0
 
 
