@@ -6,6 +6,7 @@ scores.  Training is data parallel: one flat all-reduce (sum) of the gradients p
 optimizer step on every rank.
 """
 import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -50,6 +51,8 @@ class ShardedScorer:
         self.host_bf16 = score_fn is None and (want == "1" or (want is None and local_world == 1 and self.host_threads >= 16))
         self.last_h2d_bytes = 0
         self.raw_rows = int(os.environ.get("USF_HOST_RAW_ROWS", "16384"))    # leading rows sent as fp32 (pinned input)
+        self.autotune = "USF_HOST_RAW_ROWS" not in os.environ                # ... unless fixed: found per shape by trying
+        self._tune = {}
         self._ring = None
 
     def score_local(self, x_dev):
@@ -80,8 +83,24 @@ class ShardedScorer:
                   and x_host.dtype == torch.float32 and x_host.dim() == 2 and x_host.stride(1) == 1
                   and n >= self.chunk_rows)
         self.last_h2d_bytes = x_host.numel() * x_host.element_size()
+        tune = None
+        if narrow and self.autotune and x_host.is_pinned() and n >= 3 * self.chunk_rows:
+            # Host speed differs from box to box (measured 71-103 GB/s on the same pool), so the fp32 head that balances
+            # conversion against the link is found by trying: the first calls with a given shape cycle through the
+            # candidates twice -- every one is a full, valid scoring call -- then the fastest stays (None = plain copy).
+            tune = self._tune.setdefault((n, x_host.shape[1]), {"i": 0, "t": {}, "best": False})
+            if tune["best"] is False:
+                cands = [self.raw_rows] + [c for c in (self.raw_rows * 3 // 2, self.raw_rows // 2, 2 * self.raw_rows, None)
+                                           if c is None or 0 < c <= n - self.chunk_rows]
+                choice = cands[tune["i"] % len(cands)]
+                t_start = time.perf_counter()
+            else:
+                choice, tune = tune["best"], None
+            narrow = choice is not None
+        else:
+            choice = self.raw_rows
         if narrow:
-            scores = self._score_narrowed(x_host, dev)
+            scores = self._score_narrowed(x_host, dev, choice)
         elif dev.type != "cuda" or n < 2 * self.chunk_rows:
             x = x_host.to(dev, non_blocking=True)
             with torch.no_grad():
@@ -110,9 +129,16 @@ class ShardedScorer:
                     torch.neg(self.score_fn(xc), out=scores[lo:hi])
         if gather:
             scores = self.gather(scores)
-        return scores.cpu()
+        out = scores.cpu()
+        if tune is not None:
+            dt = time.perf_counter() - t_start
+            tune["t"][choice] = min(dt, tune["t"].get(choice, dt))
+            tune["i"] += 1
+            if tune["i"] >= 2 * len(cands):
+                tune["best"] = min(tune["t"], key=tune["t"].get)
+        return out
 
-    def _score_narrowed(self, x_host, dev):
+    def _score_narrowed(self, x_host, dev, raw_rows):
         """Three-stage pipeline over row chunks: host cores narrow chunk i+1 to bf16 into a pinned staging ring
         (usf_host_f32_to_bf16) while the copy stream moves chunk i over PCIe and the launch chain of chunk i-1 runs.
         From pinned memory the first half-chunk goes over as fp32 so that the link is busy from t = 0 (the conversion
@@ -127,7 +153,7 @@ class ShardedScorer:
             self._ring = [[torch.empty(self.chunk_rows, D, dtype=torch.bfloat16).pin_memory(), None] for _ in range(3)]
         half = max(1, self.chunk_rows // 2)
         plan, lo = [], 0
-        raw = min(self.raw_rows, n - self.chunk_rows) if x_host.is_pinned() else 0
+        raw = min(raw_rows, n - self.chunk_rows) if x_host.is_pinned() else 0
         while lo < raw:                                   # fp32 over the link while the first conversions run
             plan.append((lo, min(raw, lo + self.chunk_rows), False))
             lo = plan[-1][1]

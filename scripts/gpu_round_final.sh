@@ -14,6 +14,7 @@ if grep -q "bench exit 0" gpurun_out/summary.txt; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:usf_tc -s 51 -c 3 -o gpurun_out/prof_tc $PB > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?" >> gpurun_out/summary.txt
 fi
+timeout 300 python scripts/host_narrow.py > gpurun_out/host_narrow.txt 2>&1; echo "host_narrow exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 tail -n 2 gpurun_out/gpu_tests.log
 cat gpurun_out/smoke.log | grep smoke

@@ -508,6 +508,12 @@ def test_bf16_rows_and_host_narrowing_are_bit_identical(P):
     for xh in (x_host, x_host.pin_memory(), x_host[:16384], x_host[:33000].pin_memory()):
         got = sc.predict_score_host(xh)
         assert same(got, -ref[:xh.shape[0]].cpu())
+    # large pinned inputs: the first calls try the fp32-head candidates (each a valid call), then the fastest stays
+    big = torch.cat([x_host, x_host[:25536]]).pin_memory()
+    outs = [sc.predict_score_host(big) for _ in range(11)]
+    assert sc._tune[(65536, D)]["best"] is not False and len(sc._tune[(65536, D)]["t"]) == 5
+    want = torch.cat([-ref.cpu(), -ref[:25536].cpu()])
+    assert all(same(o, want) for o in outs)
     sc.host_bf16 = False
     assert same(sc.predict_score_host(x_host), -ref.cpu())
     # other tiers take bf16 rows as values (widened), never through the narrowed entry
