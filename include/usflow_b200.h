@@ -260,6 +260,10 @@ int usf_stack_run_bf16in(const usf_stack_desc* st, const uint16_t* x_bf16, int64
 int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
                          int threads);
 
+/* HOST function: the same threaded pass without narrowing -- stages pageable fp32 rows into a pinned buffer, so that the
+ * PCIe copy of a caller's numpy array is asynchronous and pipelined (fp32 / tf32x3 tiers). */
+int usf_host_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, int threads);
+
 /* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch

@@ -76,11 +76,13 @@ class ADBenchFlow:
         """Anomaly score = -log_prob, per sample (adbench_wrapper.py:406-433)."""
         X = torch.as_tensor(np.asarray(X_test), dtype=torch.float32)
         self.flow_model.eval()
-        scorer = ShardedScorer(self.flow_model)
+        scorer = self.__dict__.get("_scorer")
+        if scorer is None or scorer.flow is not self.flow_model:
+            scorer = self._scorer = ShardedScorer(self.flow_model)     # keeps its pinned staging ring between calls
         if scorer.world > 1:
             return scorer.predict_score(X).numpy()
-        if not X.is_pinned() and X.numel() > 0:
-            X = X.pin_memory()
+        # pageable rows go through the scorer's pinned staging ring (host thread pool), chunk by chunk, overlapped with
+        # the PCIe copy and the compute -- no whole-array pin_memory() copy
         return scorer.predict_score_host(X).numpy()
 
     def predict(self, X_test: np.ndarray, threshold: Optional[float] = None) -> np.ndarray:

@@ -72,8 +72,9 @@ narrow_fn pick_narrow() {
 struct Job {
   const float* src;
   int64_t lds;
-  uint16_t* dst;
+  void* dst;          // bf16 rows (narrow) or fp32 rows (plain staged copy)
   int64_t ldd, rows, cols;
+  int narrow;
 };
 
 // A small persistent pool: workers sleep on a condition variable between calls and pull row blocks from an atomic
@@ -143,10 +144,21 @@ class Pool {
       if (b >= blocks_) return;
       const int64_t r0 = b * block_rows_;
       const int64_t r1 = r0 + block_rows_ < job_.rows ? r0 + block_rows_ : job_.rows;
-      if (job_.lds == job_.cols && job_.ldd == job_.cols) {
-        fn_(job_.src + r0 * job_.lds, job_.dst + r0 * job_.ldd, (r1 - r0) * job_.cols);
+      const bool flat = job_.lds == job_.cols && job_.ldd == job_.cols;
+      if (job_.narrow) {
+        uint16_t* d = static_cast<uint16_t*>(job_.dst);
+        if (flat) {
+          fn_(job_.src + r0 * job_.lds, d + r0 * job_.ldd, (r1 - r0) * job_.cols);
+        } else {
+          for (int64_t r = r0; r < r1; ++r) fn_(job_.src + r * job_.lds, d + r * job_.ldd, job_.cols);
+        }
       } else {
-        for (int64_t r = r0; r < r1; ++r) fn_(job_.src + r * job_.lds, job_.dst + r * job_.ldd, job_.cols);
+        float* d = static_cast<float*>(job_.dst);
+        if (flat) {
+          memcpy(d + r0 * job_.ldd, job_.src + r0 * job_.lds, sizeof(float) * (size_t)((r1 - r0) * job_.cols));
+        } else {
+          for (int64_t r = r0; r < r1; ++r) memcpy(d + r * job_.ldd, job_.src + r * job_.lds, sizeof(float) * (size_t)job_.cols);
+        }
       }
     }
   }
@@ -181,8 +193,8 @@ class Pool {
 
 }  // namespace
 
-extern "C" int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
-                                    int threads) {
+static int host_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, int threads,
+                     int narrow) {
   if (rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (src == nullptr || dst == nullptr)) || lds < cols || ldd < cols)
     return USF_E_ARG;
   if (rows == 0 || cols == 0) return USF_OK;
@@ -191,6 +203,16 @@ extern "C" int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst
     if (threads <= 0) threads = 1;
   }
   if (threads > 64) threads = 64;
-  Pool::get().run(Job{src, lds, dst, ldd, rows, cols}, threads);
+  Pool::get().run(Job{src, lds, dst, ldd, rows, cols, narrow}, threads);
   return USF_OK;
+}
+
+extern "C" int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
+                                    int threads) {
+  return host_rows(src, lds, dst, ldd, rows, cols, threads, 1);
+}
+
+extern "C" int usf_host_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols,
+                                 int threads) {
+  return host_rows(src, lds, dst, ldd, rows, cols, threads, 0);
 }

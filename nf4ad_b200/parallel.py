@@ -49,6 +49,12 @@ class ShardedScorer:
         self.host_threads = int(os.environ.get("USF_HOST_THREADS", "0")) or max(1, avail // local_world)
         want = os.environ.get("USF_HOST_BF16")
         self.host_bf16 = score_fn is None and (want == "1" or (want is None and local_world == 1 and self.host_threads >= 16))
+        # Pageable rows (the numpy arrays the reference's callers pass): always staged through the pinned ring by the host
+        # thread pool -- narrowed in the bf16 tier, copied otherwise -- so that the PCIe copy is asynchronous and pipelined
+        # with the staging of the next chunk and the compute of the previous one (a pageable cudaMemcpy is neither):
+        # 65536 x 784 rows, bf16 tier: 20.2 -> 3.9 ms per call (scripts/pageable_e2e.py).
+        self.host_staging = os.environ.get("USF_HOST_STAGING", "1") != "0"
+        self.narrow_ok = score_fn is None       # a custom score function may not take bf16 rows
         self.last_h2d_bytes = 0
         self.raw_rows = int(os.environ.get("USF_HOST_RAW_ROWS", "16384"))    # leading rows sent as fp32 (pinned input)
         self.autotune = "USF_HOST_RAW_ROWS" not in os.environ                # ... unless fixed: found per shape by trying
@@ -79,12 +85,16 @@ class ShardedScorer:
         H2D and D2H happen inside the call (adbench_wrapper.py:419,433)."""
         dev = next(self.flow.parameters()).device if hasattr(self.flow, "parameters") else torch.device("cpu")
         n = x_host.shape[0]
-        narrow = (self.host_bf16 and dev.type == "cuda" and getattr(self.flow, "precision", None) == "bf16"
-                  and x_host.dtype == torch.float32 and x_host.dim() == 2 and x_host.stride(1) == 1
-                  and n >= self.chunk_rows)
+        stageable = (dev.type == "cuda" and x_host.dtype == torch.float32 and x_host.dim() == 2
+                     and x_host.stride(1) == 1 and n >= self.chunk_rows)
+        bf16_tier = self.narrow_ok and getattr(self.flow, "precision", None) == "bf16"
+        pinned = x_host.is_pinned() if stageable else False
+        # pinned rows: narrowing only where it was measured to pay (host_bf16); pageable rows: always through the ring
+        narrow = stageable and bf16_tier and (self.host_bf16 if pinned else (self.host_staging or self.host_bf16))
+        staged_copy = stageable and not narrow and not pinned and self.host_staging
         self.last_h2d_bytes = x_host.numel() * x_host.element_size()
         tune = None
-        if narrow and self.autotune and x_host.is_pinned() and n >= 3 * self.chunk_rows:
+        if narrow and self.autotune and pinned and n >= 3 * self.chunk_rows:
             # Host speed differs from box to box (measured 71-103 GB/s on the same pool), so the fp32 head that balances
             # conversion against the link is found by trying: the first calls with a given shape cycle through the
             # candidates twice -- every one is a full, valid scoring call -- then the fastest stays (None = plain copy).
@@ -99,8 +109,8 @@ class ShardedScorer:
             narrow = choice is not None
         else:
             choice = self.raw_rows
-        if narrow:
-            scores = self._score_narrowed(x_host, dev, choice)
+        if narrow or staged_copy:
+            scores = self._score_staged(x_host, dev, choice, narrow)
         elif dev.type != "cuda" or n < 2 * self.chunk_rows:
             x = x_host.to(dev, non_blocking=True)
             with torch.no_grad():
@@ -138,9 +148,10 @@ class ShardedScorer:
                 tune["best"] = min(tune["t"], key=tune["t"].get)
         return out
 
-    def _score_narrowed(self, x_host, dev, raw_rows):
-        """Three-stage pipeline over row chunks: host cores narrow chunk i+1 to bf16 into a pinned staging ring
-        (usf_host_f32_to_bf16) while the copy stream moves chunk i over PCIe and the launch chain of chunk i-1 runs.
+    def _score_staged(self, x_host, dev, raw_rows, narrow):
+        """Three-stage pipeline over row chunks: host cores stage chunk i+1 into a pinned ring -- narrowed to bf16
+        (usf_host_f32_to_bf16) or copied as fp32 (usf_host_copy_f32, pageable rows of the other tiers) -- while the copy
+        stream moves chunk i over PCIe and the launch chain of chunk i-1 runs.
         From pinned memory the first half-chunk goes over as fp32 so that the link is busy from t = 0 (the conversion
         of the following chunks runs under it), and the schedule ends on a short chunk (short compute tail)."""
         from . import _lib
@@ -149,8 +160,10 @@ class ShardedScorer:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        if self._ring is None or self._ring[0][0].shape != (self.chunk_rows, D):
-            self._ring = [[torch.empty(self.chunk_rows, D, dtype=torch.bfloat16).pin_memory(), None] for _ in range(3)]
+        rdt = torch.bfloat16 if narrow else torch.float32
+        if self._ring is None or self._ring[0][0].shape != (self.chunk_rows, D) or self._ring[0][0].dtype != rdt:
+            self._ring = [[torch.empty(self.chunk_rows, D, dtype=rdt).pin_memory(), None] for _ in range(3)]
+        stage = _lib.lib().usf_host_f32_to_bf16 if narrow else _lib.lib().usf_host_copy_f32
         half = max(1, self.chunk_rows // 2)
         plan, lo = [], 0
         raw = min(raw_rows, n - self.chunk_rows) if x_host.is_pinned() else 0
@@ -165,25 +178,23 @@ class ShardedScorer:
             lo = hi
         cs.wait_stream(cur)
         scores = torch.empty(n, device=dev, dtype=torch.float32)
-        lib = _lib.lib()
         k = 0
-        self.last_h2d_bytes = sum((hi - lo) * D * (2 if narrowed else 4) for lo, hi, narrowed in plan)
+        self.last_h2d_bytes = sum((hi - lo) * D * (2 if (staged and narrow) else 4) for lo, hi, staged in plan)
         with torch.no_grad():
-            for lo, hi, narrowed in plan:
-                if narrowed:
+            for lo, hi, staged in plan:
+                if staged:
                     slot = self._ring[k % len(self._ring)]
                     k += 1
                     if slot[1] is not None:
                         slot[1].synchronize()          # the copy that last read this staging buffer has finished
                     src = x_host[lo:hi]
-                    _lib.check(lib.usf_host_f32_to_bf16(_lib.ptr(src), src.stride(0) if hi - lo > 1 else D,
-                                                        _lib.ptr(slot[0]), D, hi - lo, D, self.host_threads),
-                               "usf_host_f32_to_bf16")
-                    staged = slot[0][:hi - lo]
+                    _lib.check(stage(_lib.ptr(src), src.stride(0) if hi - lo > 1 else D, _lib.ptr(slot[0]), D, hi - lo, D,
+                                     self.host_threads), "usf_host_f32_to_bf16 / usf_host_copy_f32")
+                    buf = slot[0][:hi - lo]
                 else:
-                    slot, staged = None, x_host[lo:hi]
+                    slot, buf = None, x_host[lo:hi]
                 with torch.cuda.stream(cs):
-                    xc = staged.to(dev, non_blocking=True)
+                    xc = buf.to(dev, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(cs)
                 if slot is not None:

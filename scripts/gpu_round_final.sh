@@ -15,6 +15,7 @@ if grep -q "bench exit 0" gpurun_out/summary.txt; then
   echo "ncu full exit $?" >> gpurun_out/summary.txt
 fi
 timeout 300 python scripts/host_narrow.py > gpurun_out/host_narrow.txt 2>&1; echo "host_narrow exit $?" >> gpurun_out/summary.txt
+timeout 300 python scripts/pageable_e2e.py > gpurun_out/pageable_e2e.txt 2>&1; echo "pageable_e2e exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 tail -n 2 gpurun_out/gpu_tests.log
 cat gpurun_out/smoke.log | grep smoke

@@ -100,6 +100,10 @@ def test_host_narrowing_is_round_to_nearest_even():
     nan = torch.isnan(ref[:, :40])
     assert torch.equal(out.view(torch.int16)[~nan], ref[:, :40].contiguous().view(torch.int16)[~nan])
     assert L.usf_host_f32_to_bf16(None, 83, None, 83, 0, 83, 1) == 0
+    # the plain staged copy of the same pool (pageable fp32 rows -> pinned ring)
+    cp = torch.full((1237, 48), 7.0)
+    assert L.usf_host_copy_f32(C.c_void_p(xs.data_ptr()), 83, C.c_void_p(cp.data_ptr()), 48, 1237, 40, 3) == 0
+    assert torch.equal(cp[:, :40].view(torch.int32), xs.contiguous().view(torch.int32)) and bool((cp[:, 40:] == 7.0).all())
     # a forked child (e.g. a data-loader worker) has none of the parent's pool threads: it must get its own pool.
     # No torch calls in the child (its OpenMP pool does not survive a fork either); the parent waits with a deadline.
     import os

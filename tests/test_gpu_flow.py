@@ -514,8 +514,16 @@ def test_bf16_rows_and_host_narrowing_are_bit_identical(P):
     assert sc._tune[(65536, D)]["best"] is not False and len(sc._tune[(65536, D)]["t"]) == 5
     want = torch.cat([-ref.cpu(), -ref[:25536].cpu()])
     assert all(same(o, want) for o in outs)
-    sc.host_bf16 = False
+    sc.host_bf16 = sc.host_staging = False          # the plain chunked copy
     assert same(sc.predict_score_host(x_host), -ref.cpu())
+    # pageable rows of the other tiers are staged through the pinned ring as fp32 (usf_host_copy_f32)
+    sc.host_staging = True
+    flow.precision = "fp32"
+    with torch.no_grad():
+        ref32 = flow.log_prob(x)
+    assert same(sc.predict_score_host(x_host), -ref32.cpu())
+    assert same(sc.predict_score_host(x_host[:33000]), -ref32[:33000].cpu())
+    flow.precision = "bf16"
     # other tiers take bf16 rows as values (widened), never through the narrowed entry
     flow.precision = "fp32"
     with torch.no_grad():
