@@ -33,7 +33,7 @@ flow.precision = "bf16"
 sc = ShardedScorer(flow)
 for narrow, chunk, raw, th in ((False, 16384, 0, 0), (True, 16384, 0, 0), (True, 16384, 8192, 0), (True, 16384, 16384, 0),
                                (True, 16384, 24576, 0), (True, 8192, 16384, 0), (True, 16384, 16384, 12), (True, 16384, 16384, 8)):
-    sc.host_bf16, sc.chunk_rows, sc.raw_rows, sc._ring = narrow, chunk, raw, None
+    sc.host_bf16, sc.chunk_rows, sc.raw_rows, sc._ring, sc.autotune = narrow, chunk, raw, None, False
     sc.host_threads = th or os.cpu_count()
     for _ in range(3):
         s = sc.predict_score_host(x)
