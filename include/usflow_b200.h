@@ -264,6 +264,21 @@ int usf_host_f32_to_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t l
  * PCIe copy of a caller's numpy array is asynchronous and pipelined (fp32 / tf32x3 tiers). */
 int usf_host_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, int threads);
 
+/* ---- VAE-flow latent tail (nf4ad/vaeflow.py) -- the steps either side of flow_prior.log_prob --------------------------
+ * usf_vae_reparam: z = mu + eps * exp(logvar / 2) (vaeflow.py:176-179) and, in the same pass, the posterior log-density
+ *   log_q[b] = sum_c log N(z | mu, std) = sum_c (-eps^2/2 - logvar/2) - L/2 log 2pi   (vaeflow.py:214-219); log_q may be NULL.
+ * usf_vae_reparam_bwd: dlogvar = dz * eps * std / 2 - dlog_q[b] / 2 (either upstream gradient may be NULL); dmu = dz.
+ * usf_recon_nll: out[b] = sum (x - x_recon)^2 / (2 sigma2) + D/2 log(2 pi sigma2) over contiguous rows (vaeflow.py:208-211,
+ *   255-259); usf_recon_nll_bwd: dx_recon = -dout[b] (x - x_recon) / sigma2, dx = -dx_recon (either may be NULL). */
+int usf_vae_reparam(const float* mu, int64_t ldm, const float* logvar, int64_t ldv, const float* eps, int64_t lde, float* z,
+                    int64_t ldz, float* log_q, int64_t B, int64_t L, usf_stream_t stream);
+int usf_vae_reparam_bwd(const float* dz, int64_t lddz, const float* dlog_q, const float* eps, int64_t lde,
+                        const float* logvar, int64_t ldv, float* dlogvar, int64_t lddv, int64_t B, int64_t L,
+                        usf_stream_t stream);
+int usf_recon_nll(const float* x, const float* x_recon, int64_t B, int64_t D, float sigma2, float* out, usf_stream_t stream);
+int usf_recon_nll_bwd(const float* x, const float* x_recon, const float* dout, int64_t B, int64_t D, float sigma2,
+                      float* dx_recon, float* dx, usf_stream_t stream);
+
 /* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch

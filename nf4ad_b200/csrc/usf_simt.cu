@@ -1456,3 +1456,120 @@ extern "C" int usf_pack_matrix(const float* src, int64_t lds, const int32_t* row
   USF_LAUNCH_CHECK("usf_pack_matrix_kernel");
   return USF_OK;
 }
+
+// ================================================================================================
+// VAE-flow latent tail (nf4ad/vaeflow.py:176-179 reparameterize, :214-224 log q(z|x), :208-211 / :255-262 recon NLL):
+// the element-wise steps either side of flow_prior.log_prob, one launch each, with the encoder-facing gradients.
+// ================================================================================================
+namespace usf {
+namespace {
+
+// one warp per row: z = mu + eps * exp(logvar / 2);  log_q[row] = sum_c (-eps^2 / 2 - logvar / 2) - L/2 log(2 pi)
+// (the Normal(mu, std) log-density at z, where (z - mu) / std is eps itself)
+__global__ void usf_vae_reparam_kernel(const float* __restrict__ mu, int64_t ldm, const float* __restrict__ lv, int64_t ldv,
+                                       const float* __restrict__ eps, int64_t lde, float* z, int64_t ldz, float* log_q,
+                                       int64_t B, int64_t L) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int64_t c = lane; c < L; c += 32) {
+    const float v = lv[row * ldv + c], e = eps[row * lde + c];
+    z[row * ldz + c] = fmaf(e, expf(0.5f * v), mu[row * ldm + c]);
+    acc += -0.5f * e * e - 0.5f * v;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && log_q != nullptr) log_q[row] = acc - 0.5f * (float)L * 1.8378770664093453f;
+}
+
+// dlogvar = dz * eps * exp(logvar / 2) / 2 - dlog_q[row] / 2   (dmu = dz: no kernel needed)
+__global__ void usf_vae_reparam_bwd_kernel(const float* __restrict__ dz, int64_t lddz, const float* __restrict__ dlogq,
+                                           const float* __restrict__ eps, int64_t lde, const float* __restrict__ lv,
+                                           int64_t ldv, float* dlv, int64_t lddv, int64_t B, int64_t L) {
+  const int64_t total = B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / L, c = i - r * L;
+    float g = 0.f;
+    if (dz != nullptr) g = 0.5f * dz[r * lddz + c] * eps[r * lde + c] * expf(0.5f * lv[r * ldv + c]);
+    if (dlogq != nullptr) g -= 0.5f * dlogq[r];
+    dlv[r * lddv + c] = g;
+  }
+}
+
+// one block per row: out[row] = sum (x - xr)^2 / (2 sigma2) + D/2 log(2 pi sigma2)
+__global__ void usf_recon_nll_kernel(const float* __restrict__ x, const float* __restrict__ xr, int64_t D, float inv_2s2,
+                                     float cst, float* out) {
+  const int64_t row = blockIdx.x;
+  const float* a = x + row * D;
+  const float* b = xr + row * D;
+  float acc = 0.f;
+  for (int64_t c = threadIdx.x; c < D; c += blockDim.x) {
+    const float d = a[c] - b[c];
+    acc = fmaf(d, d, acc);
+  }
+  __shared__ float part[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[row] = fmaf(t, inv_2s2, cst);
+  }
+}
+
+// dxr = -g[row] (x - xr) / sigma2 ; dx = -dxr (optional)
+__global__ void usf_recon_nll_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xr, const float* __restrict__ g,
+                                         int64_t D, int64_t B, float inv_s2, float* dxr, float* dx) {
+  const int64_t total = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = g[i / D] * (x[i] - xr[i]) * inv_s2;
+    if (dxr != nullptr) dxr[i] = -v;
+    if (dx != nullptr) dx[i] = v;
+  }
+}
+
+}  // namespace
+}  // namespace usf
+
+extern "C" int usf_vae_reparam(const float* mu, int64_t ldm, const float* logvar, int64_t ldv, const float* eps, int64_t lde,
+                               float* z, int64_t ldz, float* log_q, int64_t B, int64_t L, usf_stream_t stream) {
+  USF_CHECK_ARG(mu && logvar && eps && z && B >= 0 && L > 0 && ldm >= L && ldv >= L && lde >= L && ldz >= L,
+                "usf_vae_reparam: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_vae_reparam_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, as_stream(stream)>>>(mu, ldm, logvar, ldv, eps, lde, z, ldz, log_q,
+                                                                                B, L);
+  USF_LAUNCH_CHECK("usf_vae_reparam_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_vae_reparam_bwd(const float* dz, int64_t lddz, const float* dlog_q, const float* eps, int64_t lde,
+                                   const float* logvar, int64_t ldv, float* dlogvar, int64_t lddv, int64_t B, int64_t L,
+                                   usf_stream_t stream) {
+  USF_CHECK_ARG(eps && logvar && dlogvar && B >= 0 && L > 0 && lde >= L && ldv >= L && lddv >= L && (dz == nullptr || lddz >= L),
+                "usf_vae_reparam_bwd: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_vae_reparam_bwd_kernel<<<ew_grid(B * L), 256, 0, as_stream(stream)>>>(dz, lddz, dlog_q, eps, lde, logvar, ldv, dlogvar,
+                                                                           lddv, B, L);
+  USF_LAUNCH_CHECK("usf_vae_reparam_bwd_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_recon_nll(const float* x, const float* x_recon, int64_t B, int64_t D, float sigma2, float* out,
+                             usf_stream_t stream) {
+  USF_CHECK_ARG(x && x_recon && out && B >= 0 && D > 0 && sigma2 > 0.f, "usf_recon_nll: bad arguments");
+  if (B == 0) return USF_OK;
+  const float cst = 0.5f * (float)D * logf(6.283185307179586f * sigma2);
+  usf_recon_nll_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(x, x_recon, D, 0.5f / sigma2, cst, out);
+  USF_LAUNCH_CHECK("usf_recon_nll_kernel");
+  return USF_OK;
+}
+
+extern "C" int usf_recon_nll_bwd(const float* x, const float* x_recon, const float* dout, int64_t B, int64_t D, float sigma2,
+                                 float* dx_recon, float* dx, usf_stream_t stream) {
+  USF_CHECK_ARG(x && x_recon && dout && B >= 0 && D > 0 && sigma2 > 0.f, "usf_recon_nll_bwd: bad arguments");
+  if (B == 0) return USF_OK;
+  usf_recon_nll_bwd_kernel<<<ew_grid(B * D), 256, 0, as_stream(stream)>>>(x, x_recon, dout, D, B, 1.f / sigma2, dx_recon, dx);
+  USF_LAUNCH_CHECK("usf_recon_nll_bwd_kernel");
+  return USF_OK;
+}

@@ -6,6 +6,7 @@ on the bf16 tensor-core path; inverse(forward(x)) round-trip error is reported a
 These tests mirror the reference's own behavioural tests (`tests/test_flows.py`,
 `tests/test_adbench_flow_wrapper.py`) and add the numerical checks the reference lacks.
 """
+import math
 import numpy as np
 import pytest
 import torch
@@ -462,6 +463,46 @@ def test_mixed_precision_training_gradients_follow_fp32(P):
         opt.step()
         first = float(loss.detach()) if first is None else first
     assert float(loss.detach()) < first
+
+
+def test_vae_latent_tail_against_oracle_flow(P, O):
+    """`vae.loss_function` / `vae.anomaly_score` (nf4ad/vaeflow.py:198-269 with our flow as `flow_prior`) against the same
+    formulas evaluated with the fp64 oracle flow carrying the same weights; encoder-facing gradients included."""
+    from nf4ad_b200 import vae
+    B, L, D = 16, 32, 48
+    torch.manual_seed(0)
+    flow = build_flow(P, "NonUSFlow", L, 3, ("mlp", [64]), affine_conjugation=True, prior_scale=1.0)
+    tame(flow, 0.25)
+    ref_flow = build_flow(O, "NonUSFlow", L, 3, ("mlp", [64]), affine_conjugation=True, prior_scale=1.0).double()
+    ref_flow.load_state_dict({k: v.double() for k, v in flow.state_dict().items()})
+    flow = flow.to("cuda")
+    g = torch.Generator().manual_seed(8)
+    mu = (0.3 * torch.randn(B, L, generator=g)).cuda().requires_grad_()
+    lv = (0.3 * torch.randn(B, L, generator=g) - 1.0).cuda().requires_grad_()
+    eps = torch.randn(B, L, generator=g).cuda()
+    x = torch.randn(B, D, generator=g).cuda()
+    xr = torch.randn(B, D, generator=g).cuda().requires_grad_()
+    z, log_q = vae.reparameterize(mu, lv, eps)
+    loss = vae.loss_function(flow, x, xr, mu, lv, z, log_q, sigma_min=0.5, beta=0.7)
+    loss.backward()
+    score = vae.anomaly_score(flow, x, xr.detach(), z.detach(), 0.5)
+    # the reference's arithmetic, fp64, CPU
+    mud, lvd, xrd = (t.detach().cpu().double().requires_grad_() for t in (mu, lv, xr))
+    std = torch.exp(0.5 * lvd)
+    zd = mud + eps.cpu().double() * std
+    nll = 0.5 * ((x.cpu().double() - xrd) ** 2).sum(1) / 0.25 + 0.5 * D * math.log(2 * math.pi * 0.25)
+    lq = torch.distributions.Normal(mud, std).log_prob(zd).sum(1)
+    lp = ref_flow.log_prob(zd)
+    lossd = nll.sum() + 0.7 * (lq - lp).sum()
+    lossd.backward()
+    assert abs(float(loss.detach()) - float(lossd.detach())) <= 1e-4 * abs(float(lossd.detach()))
+    assert relerr_t(score.cpu().double(), (nll - lp).detach()) < 1e-4
+    for got, ref, name in ((mu.grad, mud.grad, "dmu"), (lv.grad, lvd.grad, "dlogvar"), (xr.grad, xrd.grad, "dx_recon")):
+        assert relerr_t(got.cpu().double(), ref) < 1e-3, (name, relerr_t(got.cpu().double(), ref))
+
+
+def relerr_t(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 def test_flow_fit_runs_on_the_graph_trainer(P):

@@ -1,6 +1,7 @@
 """GPU parity, kernel level: every C-ABI layer kernel against the fp64 CPU oracle on the same seeded
 inputs.  Tolerances: fp32 kernels max-norm relative error <= 2e-5 (well inside the 1e-4 log_prob
 tier); the tcgen05 bf16 GEMM is compared against an exact fp32 product of the bf16-rounded operands."""
+import math
 import ctypes as C
 
 import pytest
@@ -217,3 +218,37 @@ def test_tcgen05_linear_tf32x3(ops, B, N, K, relu):
         ref = ref.clamp_min(0)
     assert int(((y.view(torch.int32) & 8191) != 0).sum()) == 0          # hi part is tf32-exact
     assert relerr(y.double() + ylo.double(), ref) < 2e-5
+
+
+def test_vae_latent_tail_kernels():
+    """usf_vae_reparam / usf_recon_nll and their backward kernels against the reference's formulas
+    (nf4ad/vaeflow.py:176-179, 203-224) in float64 autograd."""
+    from nf4ad_b200 import vae
+    g = torch.Generator().manual_seed(21)
+    for (B, L, img) in ((16, 128, (1, 28, 28)), (3, 7, (5,)), (64, 256, (3, 32, 32))):
+        mu = torch.randn(B, L, generator=g).cuda().requires_grad_()
+        lv = (0.5 * torch.randn(B, L, generator=g)).cuda().requires_grad_()
+        eps = torch.randn(B, L, generator=g).cuda()
+        x = torch.randn(B, *img, generator=g).cuda()
+        xr = torch.randn(B, *img, generator=g).cuda().requires_grad_()
+        wz = torch.randn(B, L, generator=g).cuda()
+        wq, wn = torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()
+        z, log_q = vae.reparameterize(mu, lv, eps)
+        nll = vae.recon_nll(x, xr, 0.1)
+        ((z * wz).sum() + (log_q * wq).sum() + (nll * wn).sum()).backward()
+        mud, lvd, xrd = (t.detach().double().requires_grad_() for t in (mu, lv, xr))
+        std = torch.exp(0.5 * lvd)
+        zd = mud + eps.double() * std
+        lqd = torch.distributions.Normal(mud, std).log_prob(zd).view(B, -1).sum(1)
+        D = x[0].numel()
+        nlld = 0.5 * ((x.double() - xrd) ** 2).view(B, -1).sum(1) / 0.01 + 0.5 * D * math.log(2 * math.pi * 0.01)
+        ((zd * wz.double()).sum() + (lqd * wq.double()).sum() + (nlld * wn.double()).sum()).backward()
+        for got, ref, name in ((z, zd, "z"), (log_q, lqd, "log_q"), (nll, nlld, "nll"), (mu.grad, mud.grad, "dmu"),
+                               (lv.grad, lvd.grad, "dlogvar"), (xr.grad, xrd.grad, "dx_recon")):
+            assert relerr(got, ref) < 2e-5, (B, L, name, relerr(got, ref))
+    # log q evaluated through the reparameterised z has no gradient path to mu (z - mu = eps std): dmu == dz exactly
+    mu = torch.randn(4, 8).cuda().requires_grad_()
+    lv = torch.zeros(4, 8).cuda().requires_grad_()
+    z, log_q = vae.reparameterize(mu, lv, torch.randn(4, 8).cuda())
+    log_q.sum().backward()
+    assert float(mu.grad.abs().max()) == 0.0 and torch.allclose(lv.grad, torch.full_like(lv.grad, -0.5))
