@@ -3,6 +3,8 @@
 Every function here enqueues hand-written sm_100a kernels through libusflow_b200.so on torch's current
 stream; torch is used for device memory and autograd bookkeeping only.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -264,6 +266,32 @@ class LinearFn(torch.autograd.Function):
         return dx, dW, db, None
 
 
+_WGRAD_STREAMS = {}
+_WGRAD_OVERLAP = os.environ.get("USF_WGRAD_OVERLAP", "1") != "0"
+
+
+def _overlapped_wgrad(fn, operands):
+    """The weight-gradient GEMM of a linear layer reduces over the batch into a small (N, K) output -- 16-64 tiles, a
+    fraction of the GPU -- and nothing downstream in the backward chain needs it.  It is issued on a side stream while
+    the input-gradient GEMM runs on the current one (fork after the operands are ready, join before returning, so
+    autograd's stream bookkeeping is untouched); both GEMMs then share the SMs.  Survives CUDA-graph capture."""
+    if not _WGRAD_OVERLAP:
+        return fn()
+    dev = operands[0].device
+    cur = torch.cuda.current_stream(dev)
+    side = _WGRAD_STREAMS.get(dev.index)
+    if side is None:
+        side = _WGRAD_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    for t in operands:
+        if t is not None:
+            t.record_stream(side)
+    out.record_stream(cur)
+    return out, side
+
+
 class LinearTCFn(torch.autograd.Function):
     """y = relu?(x W^T + b) with bf16 tensor-core GEMMs (fp32 accumulate) forward and backward:
         y  = x  W^T        A = x   (B,K),  W-operand = W   (N,K)
@@ -291,8 +319,14 @@ class LinearTCFn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         dyb, dyT, db = to_bf16(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
                                want_colsum=need_b)
+        join = None
+        if need_w and need_x and _WGRAD_OVERLAP:
+            dW, join = _overlapped_wgrad(lambda: gemm_bf16(dyT, xT, N, K, B), (dyT, xT))
+        else:
+            dW = gemm_bf16(dyT, xT, N, K, B) if need_w else None
         dx = gemm_bf16(dyb, WT, B, K, N) if need_x else None
-        dW = gemm_bf16(dyT, xT, N, K, B) if need_w else None
+        if join is not None:
+            torch.cuda.current_stream(dy.device).wait_stream(join)
         return dx, dW, db, None
 
 
@@ -318,8 +352,14 @@ class LinearT3Fn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         dyr, dyT, db = to_t3(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
                              want_colsum=need_b)
+        join = None
+        if need_w and need_x and _WGRAD_OVERLAP:
+            dW, join = _overlapped_wgrad(lambda: gemm_t3(dyT, (xTh, xTl), N, K, B), (dyT[0], dyT[1], xTh, xTl))
+        else:
+            dW = gemm_t3(dyT, (xTh, xTl), N, K, B) if need_w else None
         dx = gemm_t3(dyr, (WTh, WTl), B, K, N) if need_x else None
-        dW = gemm_t3(dyT, (xTh, xTl), N, K, B) if need_w else None
+        if join is not None:
+            torch.cuda.current_stream(dy.device).wait_stream(join)
         return dx, dW, db, None
 
 
