@@ -401,6 +401,7 @@ def main():
     train32_ms = train3_ms = float("nan")
     if train_steps > 0:
         from nf4ad_b200.parallel import DataParallelTrainer
+        from nf4ad_b200.optim import FusedAdam
         xb = x[:train_B]
         for prec in ("bf16", "tf32x3", "fp32"):
             # "bf16" = mixed precision: bf16 tensor-core GEMMs with fp32 accumulation, fp32 parameters / gradients /
@@ -408,7 +409,7 @@ def main():
             # 3xTF32 tensor-core GEMMs (fp32-grade); "fp32" = the all-fp32 kernels
             tflow = build_flow(P, dev).train()
             tflow.precision = prec
-            opt = torch.optim.Adam(tflow.parameters(), lr=1e-4, capturable=True, fused=True)   # the step replays as one CUDA graph
+            opt = FusedAdam(tflow.parameters(), lr=1e-4)   # torch.optim.Adam's update via usf_adam_step; the step replays as one CUDA graph
             trainer = DataParallelTrainer(tflow, opt)
             trainer.broadcast_parameters()
             for _ in range(5):          # 3 eager steps + capture + first replay (single rank), all untimed

@@ -279,6 +279,21 @@ int usf_recon_nll(const float* x, const float* x_recon, int64_t B, int64_t D, fl
 int usf_recon_nll_bwd(const float* x, const float* x_recon, const float* dout, int64_t B, int64_t D, float sigma2,
                       float* dx_recon, float* dx, usf_stream_t stream);
 
+/* ---- optimizer step of the training loop (adbench_wrapper.py:369,391: the Adam optimizer) -------------------------------
+ * One launch per 32 parameter tensors: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t)
+ * + eps), the reference optimizer's arithmetic (weight_decay: L2 into g, or decoupled = 1 for AdamW's p *= 1 - lr wd).  `tensors` is
+ * a HOST array of DEVICE pointers (contiguous fp32); step_dev is a device float holding t (already incremented), so a
+ * captured step advances; grad_scale_dev (optional device float) multiplies every gradient (clipping coefficient). */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} usf_adam_tensor;
+int usf_adam_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, const float* grad_scale_dev, usf_stream_t stream);
+
 /* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch

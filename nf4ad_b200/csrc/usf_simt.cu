@@ -1573,3 +1573,93 @@ extern "C" int usf_recon_nll_bwd(const float* x, const float* x_recon, const flo
   USF_LAUNCH_CHECK("usf_recon_nll_bwd_kernel");
   return USF_OK;
 }
+
+// ================================================================================================
+// Adam step over many parameter tensors in one launch per 32 tensors (adbench_wrapper.py:369,391: torch.optim.Adam).
+// Pointers travel as kernel parameters (baked into a captured graph node like every other launch of the step); the step
+// count lives on the device so that the replayed graph advances it.
+// ================================================================================================
+namespace usf {
+namespace {
+
+constexpr int ADAM_MAX_TENSORS = 32;
+constexpr int ADAM_CHUNK = 8192;      // elements per block
+
+struct AdamBatch {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  int64_t n[ADAM_MAX_TENSORS];
+  int first_block[ADAM_MAX_TENSORS + 1];   // prefix sum of ceil(n / ADAM_CHUNK)
+  int count;
+};
+
+__global__ void __launch_bounds__(256) usf_adam_kernel(const __grid_constant__ AdamBatch b, const float* __restrict__ step,
+                                                       float lr, float beta1, float beta2, float eps, float wd, int decoupled,
+                                                       const float* __restrict__ grad_scale) {
+  int t = 0;
+  while (t + 1 < b.count && (int)blockIdx.x >= b.first_block[t + 1]) ++t;
+  const int64_t base = (int64_t)((int)blockIdx.x - b.first_block[t]) * ADAM_CHUNK;
+  const int64_t n = b.n[t];
+  const int64_t len = n - base < ADAM_CHUNK ? n - base : ADAM_CHUNK;
+  float* __restrict__ p = b.p[t] + base;
+  const float* __restrict__ g = b.g[t] + base;
+  float* __restrict__ m = b.m[t] + base;
+  float* __restrict__ v = b.v[t] + base;
+  const float steps = *step;
+  const float bc1 = 1.f - powf(beta1, steps), bc2 = 1.f - powf(beta2, steps);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const float gs = grad_scale != nullptr ? *grad_scale : 1.f;
+  auto upd = [&](float& pv, float gv, float& mv, float& vv) {
+    gv *= gs;
+    if (decoupled) pv *= 1.f - lr * wd; else gv = fmaf(wd, pv, gv);
+    mv = fmaf(beta1, mv, (1.f - beta1) * gv);
+    vv = fmaf(beta2, vv, (1.f - beta2) * gv * gv);
+    pv -= step_size * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec) {
+    const int64_t n4 = len >> 2;
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+      upd(pv.x, gv.x, mv.x, vv.x); upd(pv.y, gv.y, mv.y, vv.y); upd(pv.z, gv.z, mv.z, vv.z); upd(pv.w, gv.w, mv.w, vv.w);
+      reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < len; i += blockDim.x) upd(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+
+}  // namespace
+}  // namespace usf
+
+extern "C" int usf_adam_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int decoupled, const float* grad_scale_dev,
+                             usf_stream_t stream) {
+  USF_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || tensors != nullptr) && step_dev != nullptr, "usf_adam_step: bad arguments");
+  int i = 0;
+  while (i < n_tensors) {
+    AdamBatch b;
+    memset(&b, 0, sizeof(b));
+    int blocks = 0;
+    while (i < n_tensors && b.count < ADAM_MAX_TENSORS) {
+      const usf_adam_tensor& t = tensors[i++];
+      if (t.n <= 0) continue;
+      USF_CHECK_ARG(t.p && t.g && t.m && t.v, "usf_adam_step: null tensor pointer");
+      b.p[b.count] = t.p; b.g[b.count] = t.g; b.m[b.count] = t.m; b.v[b.count] = t.v; b.n[b.count] = t.n;
+      b.first_block[b.count] = blocks;
+      blocks += (int)ceil_div(t.n, ADAM_CHUNK);
+      ++b.count;
+    }
+    if (b.count == 0) continue;
+    b.first_block[b.count] = blocks;
+    usf_adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(b, step_dev, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                                                    grad_scale_dev);
+    USF_LAUNCH_CHECK("usf_adam_kernel");
+  }
+  return USF_OK;
+}

@@ -342,10 +342,17 @@ class Flow(torch.nn.Module):
         X = X.to(device=dev, dtype=torch.float32)
         n = X.shape[0]
         params = dict(optim_params or {})
-        if dev.type == "cuda" and optim in (torch.optim.Adam, torch.optim.AdamW):
-            params.setdefault("capturable", True)
-            params.setdefault("fused", True)
-        opt = optim(self.parameters(), **params)
+        if dev.type == "cuda" and optim in (torch.optim.Adam, torch.optim.AdamW) and \
+                set(params) <= {"lr", "betas", "eps", "weight_decay"}:
+            from .optim import FusedAdam        # the same update through usf_adam_step (AdamW: decoupled decay, default 1e-2)
+            if optim is torch.optim.AdamW:
+                params.setdefault("weight_decay", 1e-2)
+            opt = FusedAdam(self.parameters(), decoupled=optim is torch.optim.AdamW, **params)
+        else:
+            if dev.type == "cuda" and optim in (torch.optim.Adam, torch.optim.AdamW):
+                params.setdefault("capturable", True)
+                params.setdefault("fused", True)
+            opt = optim(self.parameters(), **params)
         with_prior = getattr(self, "prior_scale", None) is not None
 
         def loss_fn(batch):

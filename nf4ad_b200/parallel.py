@@ -271,13 +271,29 @@ class DataParallelTrainer:
         for g, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
             g.copy_(new)
 
+    def _clip(self):
+        """Global-norm clipping (`adbench_wrapper.py:388-389`).  With `FusedAdam` the coefficient goes into the update
+        kernel (a device scalar) instead of a scaling pass over the gradients."""
+        from .optim import FusedAdam
+        if not isinstance(self.opt, FusedAdam):
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads:
+            return
+        total = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+        coef = torch.clamp(float(self.clip) / (total + 1e-6), max=1.0)
+        if self.opt.clip_coef is None:
+            self.opt.clip_coef = torch.ones((), device=grads[0].device, dtype=torch.float32)
+        self.opt.clip_coef.copy_(coef)
+
     def _eager_step(self, batch):
         self.opt.zero_grad(set_to_none=True)
         loss = self.loss_fn(batch)
         loss.backward()
         self.allreduce_gradients()
         if self.clip is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+            self._clip()
         self.opt.step()
         return loss.detach()
 
@@ -291,7 +307,7 @@ class DataParallelTrainer:
             loss.backward()
             self.allreduce_gradients()
             if self.clip is not None:
-                torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+                self._clip()
             self.opt.step()
             static_loss = loss.detach()
         return graph, static_x, static_loss

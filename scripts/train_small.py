@@ -6,12 +6,14 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench, nf4ad_b200
 from _cases import build_flow
 from nf4ad_b200.parallel import DataParallelTrainer
+from nf4ad_b200.optim import FusedAdam
 P = nf4ad_b200.namespace()
 for name, D, K, hid in (("C2 D=784 K=8 [256,256]", 784, 8, [256, 256]), ("test D=32 K=3 [128]", 32, 3, [128]), ("C5 D=128 K=10 [512,256]", 128, 10, [512, 256])):
     torch.manual_seed(0)
     flow = build_flow(P, "NonUSFlow", D, K, ("mlp", hid), base="normal", affine_conjugation=True, prior_scale=1.0).to("cuda").train()
     flow.precision = os.environ.get("TRAIN_PREC", "fp32")
-    opt = torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True, fused=True)
+    opt = (torch.optim.Adam(flow.parameters(), lr=1e-4, capturable=True, fused=True) if os.environ.get("TRAIN_OPT") == "torch"
+           else FusedAdam(flow.parameters(), lr=1e-4))
     tr = DataParallelTrainer(flow, opt)
     for B in (32, 64, 4096):
         x = torch.randn(B, D, device="cuda")

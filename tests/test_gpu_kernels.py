@@ -252,3 +252,37 @@ def test_vae_latent_tail_kernels():
     z, log_q = vae.reparameterize(mu, lv, torch.randn(4, 8).cuda())
     log_q.sum().backward()
     assert float(mu.grad.abs().max()) == 0.0 and torch.allclose(lv.grad, torch.full_like(lv.grad, -0.5))
+
+
+def test_fused_adam_matches_torch_adam():
+    """usf_adam_step through `FusedAdam` against torch.optim.Adam / AdamW on the same parameters and gradients: ragged
+    sizes (more than one 32-tensor launch, unaligned views), weight decay in both forms, ten steps."""
+    from nf4ad_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    sizes = [1, 3, 17, 784 * 784, 8191, 8192, 8193, 256 * 784] + [7 * (i + 1) for i in range(40)]
+    for decoupled, wd in ((False, 0.0), (False, 0.01), (True, 0.05)):
+        ours = [torch.randn(n, generator=g).cuda().requires_grad_() for n in sizes]
+        base = torch.randn(101, generator=g).cuda()
+        ours.append(base[1:].detach().requires_grad_())           # 4-byte aligned only: scalar path
+        theirs = [p.detach().clone().requires_grad_() for p in ours]
+        a = FusedAdam(ours, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd, decoupled=decoupled)
+        cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+        b = cls(theirs, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+        for it in range(10):
+            for p, q in zip(ours, theirs):
+                gr = torch.randn(p.shape, generator=g).cuda() * (1.0 + it)
+                p.grad, q.grad = gr.clone(), gr.clone()
+            a.step()
+            b.step()
+        for p, q in zip(ours, theirs):
+            assert relerr(p, q) < 2e-6, (decoupled, wd, p.numel(), relerr(p, q))
+    # the clipping coefficient folded into the update == gradients scaled beforehand
+    p1 = torch.randn(1000, generator=g).cuda().requires_grad_()
+    p2 = p1.detach().clone().requires_grad_()
+    o1, o2 = FusedAdam([p1], lr=1e-2), FusedAdam([p2], lr=1e-2)
+    o1.clip_coef = torch.tensor(0.25, device="cuda")
+    gr = torch.randn(1000, generator=g).cuda()
+    p1.grad, p2.grad = gr.clone(), gr * 0.25
+    o1.step()
+    o2.step()
+    assert relerr(p1, p2) < 1e-6
