@@ -25,6 +25,26 @@ def _world(group=None):
     return 0, 1
 
 
+def stage_plan(n_rows, chunk_rows, raw_rows):
+    """Row chunks of one host -> device scoring call as (lo, hi, staged) triples, in order and covering [0, n_rows):
+    the leading `raw_rows` (at most n_rows - chunk_rows; 0 for pageable input) go over the link as they are (fp32), so
+    that it is busy from t = 0 while the host stages the next chunk; every later chunk is staged through the pinned ring
+    (narrowed or copied); the last full-size chunk is cut in two halves (short copy + compute tail)."""
+    half = max(1, chunk_rows // 2)
+    plan, lo = [], 0
+    raw = max(0, min(raw_rows, n_rows - chunk_rows))
+    while lo < raw:
+        plan.append((lo, min(raw, lo + chunk_rows), False))
+        lo = plan[-1][1]
+    while lo < n_rows:
+        hi = min(n_rows, lo + chunk_rows)
+        if n_rows - lo <= chunk_rows and n_rows - lo > half:
+            hi = lo + half
+        plan.append((lo, hi, True))
+        lo = hi
+    return plan
+
+
 class ShardedScorer:
     """Batch-sharded anomaly scoring: `predict_score` semantics of the reference wrapper
     (`/root/reference/src/nf4ad/adbench_wrapper.py:406-433`, score = -log_prob) over N GPUs."""
@@ -157,8 +177,7 @@ class ShardedScorer:
         """Three-stage pipeline over row chunks: host cores stage chunk i+1 into a pinned ring -- narrowed to bf16
         (usf_host_f32_to_bf16) or copied as fp32 (usf_host_copy_f32, pageable rows of the other tiers) -- while the copy
         stream moves chunk i over PCIe and the launch chain of chunk i-1 runs.
-        From pinned memory the first half-chunk goes over as fp32 so that the link is busy from t = 0 (the conversion
-        of the following chunks runs under it), and the schedule ends on a short chunk (short compute tail)."""
+        The chunk schedule is `stage_plan` (fp32 head from pinned memory, short last chunk)."""
         from . import _lib
         n, D = x_host.shape
         cur = torch.cuda.current_stream(dev)
@@ -169,18 +188,7 @@ class ShardedScorer:
         if self._ring is None or self._ring[0][0].shape != (self.chunk_rows, D) or self._ring[0][0].dtype != rdt:
             self._ring = [[torch.empty(self.chunk_rows, D, dtype=rdt).pin_memory(), None] for _ in range(3)]
         stage = _lib.lib().usf_host_f32_to_bf16 if narrow else _lib.lib().usf_host_copy_f32
-        half = max(1, self.chunk_rows // 2)
-        plan, lo = [], 0
-        raw = min(raw_rows, n - self.chunk_rows) if x_host.is_pinned() else 0
-        while lo < raw:                                   # fp32 over the link while the first conversions run
-            plan.append((lo, min(raw, lo + self.chunk_rows), False))
-            lo = plan[-1][1]
-        while lo < n:
-            hi = min(n, lo + self.chunk_rows)
-            if n - lo <= self.chunk_rows and n - lo > half:
-                hi = lo + half                            # the last chunk in two halves: short copy + compute tail
-            plan.append((lo, hi, True))
-            lo = hi
+        plan = stage_plan(n, self.chunk_rows, raw_rows if x_host.is_pinned() else 0)
         cs.wait_stream(cur)
         scores = torch.empty(n, device=dev, dtype=torch.float32)
         k = 0

@@ -70,3 +70,26 @@ def test_world2_scoring_and_dp_step(tmp_path):
     marker = str(tmp_path / "ok")
     mp.spawn(_worker, args=(2, port, marker), nprocs=2, join=True)
     assert open(marker).read() == "ok"
+
+
+def test_stage_plan_covers_rows_in_order():
+    """Host logic of the end-to-end scoring pipeline (`parallel.stage_plan`): chunks are contiguous, in order and cover
+    every row exactly once; only a leading block of at most `raw_rows` rows is sent unstaged and never so much that no
+    full chunk is left to stage under it; no chunk exceeds the ring's chunk size; the schedule ends on a short chunk."""
+    from nf4ad_b200.parallel import stage_plan
+    for chunk in (1, 7, 16384):
+        for raw in (0, chunk // 2, chunk, 3 * chunk):
+            for n in (1, chunk - 1, chunk, chunk + 1, 2 * chunk, 3 * chunk + 5, 4 * chunk, 10 * chunk + chunk // 2 + 1):
+                if n <= 0:
+                    continue
+                plan = stage_plan(n, chunk, raw)
+                assert plan[0][0] == 0 and plan[-1][1] == n
+                assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+                assert all(0 < hi - lo <= chunk for lo, hi, _ in plan)
+                flags = [st for _, _, st in plan]
+                assert flags == sorted(flags)                      # unstaged head first, then staged chunks only
+                head = sum(hi - lo for lo, hi, st in plan if not st)
+                assert head == max(0, min(raw, n - chunk))
+                assert plan[-1][2] and plan[-1][1] - plan[-1][0] <= chunk // 2 + 1       # short copy + compute tail
+    assert stage_plan(65536, 16384, 16384) == [(0, 16384, False), (16384, 32768, True), (32768, 49152, True),
+                                               (49152, 57344, True), (57344, 65536, True)]
