@@ -153,3 +153,20 @@ def test_lu_log_prior_matches_the_oracle_formula():
     a, b = ours.log_prior(), theirs.log_prior()
     assert abs(float(a) - float(b)) <= 1e-12 * abs(float(b))
     assert LUTransform(4, prior_scale=None).log_prior() == 0.0
+
+
+def test_fused_adam_has_no_cpu_path():
+    """`FusedAdam` validates its hyper-parameters like torch's Adam and refuses CPU parameters (no fallback)."""
+    import pytest
+    import torch
+    from nf4ad_b200 import _lib
+    from nf4ad_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    for bad in (dict(lr=-1.0), dict(betas=(1.0, 0.9)), dict(eps=-1e-8), dict(weight_decay=-0.1)):
+        with pytest.raises(ValueError):
+            FusedAdam([p], **bad)
+    opt = FusedAdam([p], lr=1e-3)
+    assert all(g["capturable"] for g in opt.param_groups)        # what DataParallelTrainer checks before capturing a step
+    p.grad = torch.ones(4)
+    with pytest.raises(_lib.USFError):
+        opt.step()
