@@ -97,10 +97,12 @@ int usf_sum_log_abs(const float* v, int64_t n, int64_t stride, float* out, usf_s
  *   inverse == 0: y = m*x + (1-m)*(x*exp(log_s) + t)      nf4ad/transforms.py:66-90
  *   inverse != 0: y = m*x + (1-m)*((x - t)*exp(-log_s))   nf4ad/transforms.py:92-113
  * ladj (optional, (B,)): ladj[b] += ladj_coef * sum_d (1-m_d) log_s[b,d]   (:115-140)
- * In place (y == x) allowed. */
+ * scale_activation 0 = "exp" (above); 1 = "softplus" (:83-85,107-108,131-132): scale = softplus(log_s) + 1e-6,
+ * the inverse divides by scale + 1e-12 and the log-det term is log(softplus(log_s) + 1e-12) (the reference's own
+ * 1e-6 / 1e-12 inconsistency is reproduced).  In place (y == x) allowed. */
 int usf_coupling(const float* x, int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
-                 const float* mask, float clamp, int inverse, float* y, int64_t ldy, float* ladj,
-                 float ladj_coef, int64_t B, int64_t D, usf_stream_t stream);
+                 const float* mask, float clamp, int inverse, int scale_activation, float* y, int64_t ldy,
+                 float* ladj, float ladj_coef, int64_t B, int64_t D, usf_stream_t stream);
 
 /* Base log-density summed over the event dim (Independent(base,1).log_prob):
  *   kind 0 Normal : -0.5*((z-loc)/scale)^2 - log scale - 0.5 log 2pi
@@ -163,8 +165,9 @@ int usf_gemm(const float* A, int64_t lda, int a_trans, const float* B, int64_t l
  * produces dx, ds (NULL if additive), dt from dy and dladj (scalar per row, may be NULL). */
 int usf_coupling_bwd(const float* dy, int64_t lddy, const float* dladj, float ladj_coef, const float* x,
                      int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
-                     const float* mask, float clamp, int inverse, float* dx, int64_t lddx, float* ds,
-                     int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D, usf_stream_t stream);
+                     const float* mask, float clamp, int inverse, int scale_activation, float* dx,
+                     int64_t lddx, float* ds, int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D,
+                     usf_stream_t stream);
 
 /* Backward of usf_householder: dx and dV (+=) from dy, given the layer input x. scratch: B*D floats * (nvs+1). */
 int usf_householder_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* V,
@@ -233,12 +236,15 @@ typedef struct {
   const float* loc;             /* (D) */
   const float* inv_scale;       /* (D) 1/scale */
   float const_term;             /* sum of all data-independent terms (affine log-dets, -sum log scale, -D/2 log 2pi ...) */
+  int32_t ctx_dim;              /* context columns appended to every input row (x:(B, D + ctx_dim)): a conditional flow's
+                                   per-sample context (USFlows soft training: the noise level) travels through the chain as
+                                   extra conditioning columns [a | ctx | pad | b]; 0 = unconditional */
 } usf_stack_desc;
 
 /* Workspace bytes needed to push up to B rows through the stack at the given precision. */
 size_t usf_stack_workspace_bytes(const usf_stack_desc* st, int64_t B, int precision);
 
-/* Runs the whole stack on x:(B,D) fp32.
+/* Runs the whole stack on x:(B, D + ctx_dim) fp32.
  *   out_logprob (B) : log p(x) (requires st->inverse==1 and base_kind >= 0); may be NULL
  *   out_y (B,D) ldy : transformed points (latent z if inverse, data x if generative); may be NULL
  *   out_ladj (B)    : accumulated log|det| of the applied direction (optional)
@@ -293,6 +299,13 @@ typedef struct {
 } usf_adam_tensor;
 int usf_adam_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int decoupled, const float* grad_scale_dev, usf_stream_t stream);
+
+/* SophiaG step (`src.usflows.sophia.SophiaG`, named by experiments/gmm/gaussian_mixture_standart_base.yaml:45), same tensor
+ * table (`v` = the diagonal Hessian estimate h):  every hess_every-th step h = b2 h + (1-b2) g^2;  p *= 1 - lr wd;
+ * m = b1 m + (1-b1) g;  p -= lr sign(m) min(|m| / (rho batch_size h + 1e-15), 1). */
+int usf_sophia_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1, float beta2,
+                    float rho, float batch_size, float weight_decay, int hess_every, const float* grad_scale_dev,
+                    usf_stream_t stream);
 
 /* Measurement only (thread-local): between usf_profile_begin and usf_profile_end every kernel that
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end

@@ -43,6 +43,6 @@ def namespace():
     import torch.distributions as tdist
     from . import distributions, flows, nn, transforms
     return types.SimpleNamespace(
-        dist=tdist, DenseNN=nn.DenseNN, Flow=flows.Flow, USFlow=flows.USFlow, NonUSFlow=flows.NonUSFlow,
+        dist=tdist, DenseNN=nn.DenseNN, ConditionalDenseNN=nn.ConditionalDenseNN, ConvNet=nn.ConvNet, Flow=flows.Flow, USFlow=flows.USFlow, NonUSFlow=flows.NonUSFlow,
         transforms=transforms, Normal=distributions.Normal,
         MaskedAffineCoupling=transforms.MaskedAffineCoupling, MaskedCoupling=transforms.MaskedCoupling)

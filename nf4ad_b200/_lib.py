@@ -31,7 +31,8 @@ class BlockDesc(C.Structure):
 
 class StackDesc(C.Structure):
     _fields_ = [("D", _i32), ("n_blocks", _i32), ("blocks", C.POINTER(BlockDesc)), ("G_final", LinearDesc),
-                ("inverse", _i32), ("base_kind", _i32), ("loc", _vp), ("inv_scale", _vp), ("const_term", _f32)]
+                ("inverse", _i32), ("base_kind", _i32), ("loc", _vp), ("inv_scale", _vp), ("const_term", _f32),
+                ("ctx_dim", _i32)]
 
 
 # name -> (restype, argtypes); mirrors include/usflow_b200.h one to one
@@ -46,7 +47,7 @@ _PROTOS = {
     "usf_householder": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
     "usf_scale": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
     "usf_sum_log_abs": (_int, [_vp, _i64, _i64, _vp, _vp]),
-    "usf_coupling": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _vp, _i64, _vp, _f32, _i64, _i64, _vp]),
+    "usf_coupling": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _int, _vp, _i64, _vp, _f32, _i64, _i64, _vp]),
     "usf_base_logprob": (_int, [_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _vp, _i64, _i64, _vp]),
     "usf_linear_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _int, _vp,
                               _i64, _i64, _i64, _vp]),
@@ -63,10 +64,11 @@ _PROTOS = {
     "usf_recon_nll": (_int, [_vp, _vp, _i64, _i64, _f32, _vp, _vp]),
     "usf_recon_nll_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp]),
     "usf_adam_step": (_int, [_vp, _int, _vp, _f32, _f32, _f32, _f32, _f32, _int, _vp, _vp]),
+    "usf_sophia_step": (_int, [_vp, _int, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _int, _vp, _vp]),
     "usf_to_tf32x3": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "usf_colsum": (_int, [_vp, _i64, _f32, _int, _vp, _i64, _i64, _vp]),
     "usf_gemm": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp]),
-    "usf_coupling_bwd": (_int, [_vp, _i64, _vp, _f32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _vp, _i64,
+    "usf_coupling_bwd": (_int, [_vp, _i64, _vp, _f32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _int, _vp, _i64,
                                 _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "usf_householder_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "usf_base_logprob_bwd": (_int, [_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
@@ -117,11 +119,26 @@ def check(rc, what=""):
 
 
 def require_cuda(*tensors):
+    """Every operand is a CUDA tensor of ONE device, and that device is the current one: the library launches on the
+    current device's current stream (`stream()`), so operands of another GPU would be touched through device 0's
+    stream -- an illegal access or silent peer traffic.  `Flow` / `ADBenchFlow` enter `torch.cuda.device(x.device)`
+    around their calls; direct callers of the layer kernels must do the same."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise USFError(
                 "nf4ad_b200 runs on CUDA (sm_100a) tensors only and has no CPU fallback; got a "
                 f"{t.device} tensor. Move the flow and its inputs to a B200 (`flow.to('cuda')`).")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise USFError(f"operands live on different GPUs ({dev} and {t.device})")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise USFError(
+            f"operands live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}: wrap the call "
+            f"in `with torch.cuda.device({dev.index}):` (Flow / ADBenchFlow do this themselves)")
 
 
 def ptr(t):
@@ -129,7 +146,22 @@ def ptr(t):
 
 
 def stream():
+    """torch's current stream of the current device (`require_cuda` has checked that the operands live there)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# Packed-weight caches (`Flow._compiled`) are keyed by the parameters' (id, _version) pairs.  Updates that bypass
+# torch's version counters -- `FusedAdam` writing through raw pointers, a CUDA-graph replay of a whole training step
+# -- bump this epoch instead; it is part of every flow's key.
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def weights_epoch():
+    return _WEIGHTS_EPOCH[0]
 
 
 def f32c(t):

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from .optim import FusedAdam
-from .parallel import DataParallelTrainer, ShardedScorer
+from .parallel import DataParallelTrainer, ShardedScorer, rank_batches, shared_permutation
 
 
 class ADBenchFlow:
@@ -43,6 +43,10 @@ class ADBenchFlow:
 
     def fit(self, X_train: np.ndarray, y_train: Optional[np.ndarray] = None):
         """Minimise -mean log_prob with Adam over shuffled mini-batches (adbench_wrapper.py:347-404)."""
+        with torch.cuda.device(self.device):
+            return self._fit(X_train)
+
+    def _fit(self, X_train):
         X = torch.as_tensor(np.asarray(X_train), dtype=torch.float32)
         if self.verbose:
             print(f"Training Flow model on {len(X)} samples...")
@@ -58,12 +62,12 @@ class ADBenchFlow:
         gen = torch.Generator(device=self.device)
         gen.manual_seed(int(torch.initial_seed()) & 0x7FFFFFFF)
         for epoch in range(self.epochs):
-            perm = torch.randperm(n, device=self.device, generator=gen)
+            # data parallel: every rank walks the same global batches and trains on its shard of each
+            perm = shared_permutation(n, self.device, gen, group=trainer.group)
             total = torch.zeros((), device=self.device)
             steps = 0
-            for i in range(0, n, self.batch_size):
-                batch = X.index_select(0, perm[i:i + self.batch_size])
-                total += trainer.step(batch)
+            for idx in rank_batches(perm, self.batch_size, trainer.rank, trainer.world):
+                total += trainer.step(X.index_select(0, idx))
                 steps += 1
             epoch_loss = float(total.cpu()) / max(steps, 1)      # one device->host sync per epoch
             self.training_losses.append(epoch_loss)
@@ -75,6 +79,10 @@ class ADBenchFlow:
 
     def predict_score(self, X_test: np.ndarray) -> np.ndarray:
         """Anomaly score = -log_prob, per sample (adbench_wrapper.py:406-433)."""
+        with torch.cuda.device(self.device):
+            return self._predict_score(X_test)
+
+    def _predict_score(self, X_test):
         X = torch.as_tensor(np.asarray(X_test), dtype=torch.float32)
         self.flow_model.eval()
         scorer = self.__dict__.get("_scorer")

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "usf_common.cuh"
 
 namespace usf {
@@ -76,11 +78,11 @@ constexpr int64_t kSmallRows = 2048;    // fp32 path: batches up to this size ma
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan* p) {
-  USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0, "stack: bad descriptor");
+  USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0 && st->ctx_dim >= 0, "stack: bad descriptor");
   USF_CHECK_ARG(st->n_blocks == 0 || st->blocks != nullptr, "stack: blocks pointer is null");
   USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16 || precision == USF_PREC_TF32X3,
                 "stack: unknown precision %d", precision);
-  int64_t wmax = st->D, hmax = 16, nmax = st->G_final.N;
+  int64_t wmax = st->D + st->ctx_dim, hmax = 16, nmax = st->G_final.N;
   for (int b = 0; b < st->n_blocks; ++b) {
     const usf_block_desc& blk = st->blocks[b];
     USF_CHECK_ARG(blk.n_mlp >= 1 && blk.n_mlp <= USF_MAX_MLP, "stack: block %d has %d conditioner layers", b, blk.n_mlp);
@@ -215,7 +217,8 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   USF_CHECK_ARG(!(out_logprob && (st->base_kind < 0 || !st->inverse)),
                 "usf_stack_run: log_prob needs the inverse direction and a base distribution");
   USF_CHECK_ARG(!(out_logprob && out_ladj), "usf_stack_run: request log_prob or ladj, not both");
-  USF_CHECK_ARG(ldx >= st->D && (out_y == nullptr || ldy >= st->D), "usf_stack_run: leading dimension < D");
+  const int64_t d_in = (int64_t)st->D + st->ctx_dim;   // input row = D coordinates + the context columns
+  USF_CHECK_ARG(ldx >= d_in && (out_y == nullptr || ldy >= st->D), "usf_stack_run: leading dimension < D");
   if (gpu_launches) *gpu_launches = 0;
   if (B == 0) return USF_OK;
   const int64_t rows_max = B < kChunkRows ? B : kChunkRows;
@@ -279,10 +282,10 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       ProfScope ps(s, 0);
       if (x_bf16)
         rc = launch_copy_rows_bf16(reinterpret_cast<const uint16_t*>(x) + r0 * ldx, ldx, reinterpret_cast<uint16_t*>(act[0]),
-                                   p.ld_act, rows, st->D, row_acc, acc_init, s);
+                                   p.ld_act, rows, d_in, row_acc, acc_init, s);
       else
         rc = launch_convert_rows(x + r0 * ldx, ldx, bf16 ? reinterpret_cast<uint16_t*>(act[0]) : nullptr,
-                                 bf16 ? nullptr : reinterpret_cast<float*>(act[0]), p.ld_act, rows, st->D, row_acc,
+                                 bf16 ? nullptr : reinterpret_cast<float*>(act[0]), p.ld_act, rows, d_in, row_acc,
                                  acc_init, s);
     }
     if (rc) return rc;
@@ -425,7 +428,8 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
 namespace {
 
 struct GraphEntry {
-  uint64_t key = 0;
+  uint64_t key = 0;                  // FNV hash of `bytes` (first-level filter only)
+  std::vector<unsigned char> bytes;  // the full key material: a hit needs these to compare equal, not just the hash
   cudaGraphExec_t exec = nullptr;
   int launches = 0;
   int seen = 0;
@@ -470,19 +474,25 @@ static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ld
       (st->n_blocks > 0 && st->blocks == nullptr))
     return stack_run_eager(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, workspace, workspace_bytes, precision,
                            gpu_launches, stream, x_bf16);
-  uint64_t key = 1469598103934665603ull;
-  key = fnv(key, st, sizeof(*st));
-  if (st->n_blocks > 0) key = fnv(key, st->blocks, sizeof(usf_block_desc) * (size_t)st->n_blocks);
+  // key material = every descriptor byte and every call argument; the 64-bit hash only pre-filters, a hit compares
+  // the bytes themselves (a hash collision must never replay another chain)
   const uint64_t extra[9] = {(uint64_t)(uintptr_t)x, (uint64_t)ldx, (uint64_t)B, (uint64_t)(uintptr_t)out_logprob,
                              (uint64_t)(uintptr_t)out_y, (uint64_t)ldy, (uint64_t)(uintptr_t)out_ladj,
                              (uint64_t)(uintptr_t)workspace,
                              (uint64_t)workspace_bytes * 8u + (uint64_t)precision + (x_bf16 ? 4u : 0u)};
-  key = fnv(key, extra, sizeof(extra));
+  const size_t nb_bytes = st->n_blocks > 0 ? sizeof(usf_block_desc) * (size_t)st->n_blocks : 0;
+  thread_local std::vector<unsigned char> kb;
+  kb.resize(sizeof(*st) + nb_bytes + sizeof(extra));
+  memcpy(kb.data(), st, sizeof(*st));
+  if (nb_bytes) memcpy(kb.data() + sizeof(*st), st->blocks, nb_bytes);
+  memcpy(kb.data() + sizeof(*st) + nb_bytes, extra, sizeof(extra));
+  uint64_t key = fnv(1469598103934665603ull, kb.data(), kb.size());
   if (key == 0) key = 1;
   GraphEntry* slot = nullptr;
   GraphEntry* victim = &g_graphs[0];
   for (int i = 0; i < kGraphSlots; ++i) {
-    if (g_graphs[i].key == key) { slot = &g_graphs[i]; break; }
+    if (g_graphs[i].key == key && g_graphs[i].bytes.size() == kb.size() &&
+        memcmp(g_graphs[i].bytes.data(), kb.data(), kb.size()) == 0) { slot = &g_graphs[i]; break; }
     if (g_graphs[i].stamp < victim->stamp) victim = &g_graphs[i];
   }
   cudaStream_t s = as_stream(stream);
@@ -497,6 +507,7 @@ static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ld
     if (victim->exec != nullptr) cudaGraphExecDestroy(victim->exec);
     *victim = GraphEntry();
     victim->key = key;
+    victim->bytes = kb;
     victim->seen = 1;
     victim->stamp = ++g_graph_clock;
     ++g_graph_stats[3];

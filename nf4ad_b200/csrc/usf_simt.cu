@@ -580,10 +580,16 @@ __global__ void usf_sum_log_abs_kernel(const float* __restrict__ v, int64_t n, i
   }
 }
 
-// y = m*x + (1-m)*(x*exp(ls)+t)  /  y = m*x + (1-m)*((x-t)*exp(-ls)), ls = clamp*tanh(s)
+// y = m*x + (1-m)*(x*scale+t)  /  y = m*x + (1-m)*((x-t)/scale), ls = clamp*tanh(s)
+//   act 0 ("exp", nf4ad/transforms.py:80-82,104-106,129-130):  scale = exp(ls), log-det term = ls
+//   act 1 ("softplus", :83-85,107-108,131-132): scale = softplus(ls) + 1e-6, inverse divides by scale + 1e-12, and the
+//          log-det term is log(softplus(ls) + 1e-12) -- WITHOUT the 1e-6 of the scale: the reference's own inconsistency,
+//          kept so that results match it
+__device__ __forceinline__ float softplus_f(float v) { return fmaxf(v, 0.f) + log1pf(expf(-fabsf(v))); }
+
 __global__ void usf_coupling_kernel(const float* x, int64_t ldx, const float* __restrict__ s, int64_t lds,
                                     const float* __restrict__ t, int64_t ldt, const float* __restrict__ mask,
-                                    float clamp, int inverse, float* y, int64_t ldy, float* ladj, float ladj_coef,
+                                    float clamp, int inverse, int act, float* y, int64_t ldy, float* ladj, float ladj_coef,
                                     int64_t B, int64_t D) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
@@ -593,9 +599,15 @@ __global__ void usf_coupling_kernel(const float* x, int64_t ldx, const float* __
     const float m = mask[d];
     const float xv = x[r * ldx + d];
     const float tv = t[r * ldt + d];
-    float ls = 0.f;
+    float ls = 0.f, inner;
     if (s != nullptr) ls = clamp * tanhf(s[r * lds + d]);
-    const float inner = inverse ? (xv - tv) * expf(-ls) : fmaf(xv, expf(ls), tv);
+    if (act == 0 || s == nullptr) {
+      inner = inverse ? (xv - tv) * expf(-ls) : fmaf(xv, expf(ls), tv);
+    } else {
+      const float sp = softplus_f(ls), sc = sp + 1e-6f;
+      inner = inverse ? (xv - tv) / (sc + 1e-12f) : fmaf(xv, sc, tv);
+      ls = logf(sp + 1e-12f);
+    }
     y[r * ldy + d] = xv * m + (1.f - m) * inner;
     lsum = fmaf(1.f - m, ls, lsum);
   }
@@ -608,7 +620,7 @@ __global__ void usf_coupling_kernel(const float* x, int64_t ldx, const float* __
 __global__ void usf_coupling_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ dladj,
                                         float ladj_coef, const float* __restrict__ x, int64_t ldx,
                                         const float* __restrict__ s, int64_t lds, const float* __restrict__ t,
-                                        int64_t ldt, const float* __restrict__ mask, float clamp, int inverse,
+                                        int64_t ldt, const float* __restrict__ mask, float clamp, int inverse, int act,
                                         float* dx, int64_t lddx, float* ds, int64_t ldds, float* dt, int64_t lddt,
                                         int64_t B, int64_t D) {
   const int64_t total = B * D;
@@ -622,16 +634,33 @@ __global__ void usf_coupling_bwd_kernel(const float* __restrict__ dy, int64_t ld
     if (s != nullptr) { th = tanhf(s[r * lds + d]); ls = clamp * th; }
     const float gl = dladj != nullptr ? dladj[r] * ladj_coef : 0.f;
     float gx, gt, gls;
-    if (!inverse) {
-      const float e = expf(ls);
-      gx = g * (m + om * e);
-      gt = g * om;
-      gls = g * om * xv * e + gl * om;
+    if (act == 0 || s == nullptr) {
+      if (!inverse) {
+        const float e = expf(ls);
+        gx = g * (m + om * e);
+        gt = g * om;
+        gls = g * om * xv * e + gl * om;
+      } else {
+        const float e = expf(-ls);
+        gx = g * (m + om * e);
+        gt = -g * om * e;
+        gls = -g * om * (xv - tv) * e + gl * om;
+      }
     } else {
-      const float e = expf(-ls);
-      gx = g * (m + om * e);
-      gt = -g * om * e;
-      gls = -g * om * (xv - tv) * e + gl * om;
+      // scale = softplus(ls) + 1e-6: d scale / d ls = sigmoid(ls); log-det term log(softplus(ls) + 1e-12)
+      const float sp = softplus_f(ls), sg = 1.f / (1.f + expf(-ls));
+      const float dl = sg / (sp + 1e-12f);
+      if (!inverse) {
+        const float sc = sp + 1e-6f;
+        gx = g * (m + om * sc);
+        gt = g * om;
+        gls = g * om * xv * sg + gl * om * dl;
+      } else {
+        const float inv = 1.f / (sp + 1e-6f + 1e-12f);
+        gx = g * (m + om * inv);
+        gt = -g * om * inv;
+        gls = -g * om * (xv - tv) * inv * inv * sg + gl * om * dl;
+      }
     }
     dx[r * lddx + d] = gx;
     dt[r * lddt + d] = gt;
@@ -1254,12 +1283,13 @@ extern "C" int usf_sum_log_abs(const float* v, int64_t n, int64_t stride, float*
 }
 
 extern "C" int usf_coupling(const float* x, int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
-                            const float* mask, float clamp, int inverse, float* y, int64_t ldy, float* ladj,
-                            float ladj_coef, int64_t B, int64_t D, usf_stream_t stream) {
+                            const float* mask, float clamp, int inverse, int scale_activation, float* y, int64_t ldy,
+                            float* ladj, float ladj_coef, int64_t B, int64_t D, usf_stream_t stream) {
   USF_CHECK_ARG(x && t && mask && y && D > 0 && B >= 0, "usf_coupling: bad arguments");
+  USF_CHECK_ARG(scale_activation == 0 || scale_activation == 1, "usf_coupling: scale_activation must be 0 (exp) or 1 (softplus)");
   if (B == 0) return USF_OK;
   usf_coupling_kernel<<<(unsigned)ceil_div(B, ROWS_PER_CTA), ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(
-      x, ldx, s, lds, t, ldt, mask, clamp, inverse, y, ldy, ladj, ladj_coef, B, D);
+      x, ldx, s, lds, t, ldt, mask, clamp, inverse, scale_activation, y, ldy, ladj, ladj_coef, B, D);
   USF_LAUNCH_CHECK("usf_coupling_kernel");
   return USF_OK;
 }
@@ -1345,13 +1375,16 @@ extern "C" int usf_lu_pack_bwd(const float* dW, const float* L_raw, const float*
 
 extern "C" int usf_coupling_bwd(const float* dy, int64_t lddy, const float* dladj, float ladj_coef, const float* x,
                                 int64_t ldx, const float* s, int64_t lds, const float* t, int64_t ldt,
-                                const float* mask, float clamp, int inverse, float* dx, int64_t lddx, float* ds,
-                                int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D, usf_stream_t stream) {
+                                const float* mask, float clamp, int inverse, int scale_activation, float* dx, int64_t lddx,
+                                float* ds, int64_t ldds, float* dt, int64_t lddt, int64_t B, int64_t D,
+                                usf_stream_t stream) {
   USF_CHECK_ARG(dy && x && t && mask && dx && dt && D > 0 && B >= 0, "usf_coupling_bwd: bad arguments");
+  USF_CHECK_ARG(scale_activation == 0 || scale_activation == 1, "usf_coupling_bwd: scale_activation must be 0 or 1");
   USF_CHECK_ARG((s == nullptr) == (ds == nullptr), "usf_coupling_bwd: s and ds must both be given or both NULL");
   if (B == 0) return USF_OK;
   usf_coupling_bwd_kernel<<<ew_grid(B * D), 256, 0, as_stream(stream)>>>(
-      dy, lddy, dladj, ladj_coef, x, ldx, s, lds, t, ldt, mask, clamp, inverse, dx, lddx, ds, ldds, dt, lddt, B, D);
+      dy, lddy, dladj, ladj_coef, x, ldx, s, lds, t, ldt, mask, clamp, inverse, scale_activation, dx, lddx, ds, ldds, dt, lddt,
+      B, D);
   USF_LAUNCH_CHECK("usf_coupling_bwd_kernel");
   return USF_OK;
 }
@@ -1634,8 +1667,66 @@ __global__ void __launch_bounds__(256) usf_adam_kernel(const __grid_constant__ A
   }
 }
 
+// SophiaG (Liu et al. 2023; `src.usflows.sophia.SophiaG`, experiments/gmm/gaussian_mixture_standart_base.yaml:45):
+//   every `hess_every`-th step  h = b2 h + (1-b2) g^2      (diagonal Gauss-Newton-Bartlett estimate from the mini-batch gradient)
+//   p *= 1 - lr wd;  m = b1 m + (1-b1) g;  p -= lr * sign(m) * min(|m| / (rho * bs * h + 1e-15), 1)
+// same batching as the Adam kernel; `v` carries h.
+__global__ void __launch_bounds__(256) usf_sophia_kernel(const __grid_constant__ AdamBatch b, const float* __restrict__ step,
+                                                         float lr, float beta1, float beta2, float rho, float bs, float wd,
+                                                         int hess_every, const float* __restrict__ grad_scale) {
+  int t = 0;
+  while (t + 1 < b.count && (int)blockIdx.x >= b.first_block[t + 1]) ++t;
+  const int64_t base = (int64_t)((int)blockIdx.x - b.first_block[t]) * ADAM_CHUNK;
+  const int64_t n = b.n[t];
+  const int64_t len = n - base < ADAM_CHUNK ? n - base : ADAM_CHUNK;
+  float* __restrict__ p = b.p[t] + base;
+  const float* __restrict__ g = b.g[t] + base;
+  float* __restrict__ m = b.m[t] + base;
+  float* __restrict__ h = b.v[t] + base;
+  const long long steps = (long long)(*step + 0.5f);                 // already incremented: 1, 2, ...
+  const bool upd_h = hess_every <= 1 || ((steps - 1) % hess_every) == 0;
+  const float gs = grad_scale != nullptr ? *grad_scale : 1.f;
+  const float rb = rho * bs;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+    const float gv = g[i] * gs;
+    float hv = h[i];
+    if (upd_h) { hv = fmaf(beta2, hv, (1.f - beta2) * gv * gv); h[i] = hv; }
+    const float mv = fmaf(beta1, m[i], (1.f - beta1) * gv);
+    m[i] = mv;
+    const float ratio = fminf(fabsf(mv) / (rb * hv + 1e-15f), 1.f);
+    p[i] = p[i] * (1.f - lr * wd) - lr * copysignf(ratio, mv) * (mv != 0.f ? 1.f : 0.f);
+  }
+}
+
 }  // namespace
 }  // namespace usf
+
+extern "C" int usf_sophia_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1,
+                               float beta2, float rho, float batch_size, float weight_decay, int hess_every,
+                               const float* grad_scale_dev, usf_stream_t stream) {
+  USF_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || tensors != nullptr) && step_dev != nullptr, "usf_sophia_step: bad arguments");
+  int i = 0;
+  while (i < n_tensors) {
+    AdamBatch b;
+    memset(&b, 0, sizeof(b));
+    int blocks = 0;
+    while (i < n_tensors && b.count < ADAM_MAX_TENSORS) {
+      const usf_adam_tensor& t = tensors[i++];
+      if (t.n <= 0) continue;
+      USF_CHECK_ARG(t.p && t.g && t.m && t.v, "usf_sophia_step: null tensor pointer");
+      b.p[b.count] = t.p; b.g[b.count] = t.g; b.m[b.count] = t.m; b.v[b.count] = t.v; b.n[b.count] = t.n;
+      b.first_block[b.count] = blocks;
+      blocks += (int)ceil_div(t.n, ADAM_CHUNK);
+      ++b.count;
+    }
+    if (b.count == 0) continue;
+    b.first_block[b.count] = blocks;
+    usf_sophia_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(b, step_dev, lr, beta1, beta2, rho, batch_size,
+                                                                      weight_decay, hess_every, grad_scale_dev);
+    USF_LAUNCH_CHECK("usf_sophia_kernel");
+  }
+  return USF_OK;
+}
 
 extern "C" int usf_adam_step(const usf_adam_tensor* tensors, int n_tensors, const float* step_dev, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int decoupled, const float* grad_scale_dev,

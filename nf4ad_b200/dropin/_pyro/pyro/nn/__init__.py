@@ -1,1 +1,1 @@
-from nf4ad_b200.nn import DenseNN  # noqa: F401
+from nf4ad_b200.nn import ConditionalDenseNN, DenseNN  # noqa: F401

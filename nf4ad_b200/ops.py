@@ -84,8 +84,20 @@ def scale(x, s, inverse=False):
     return y
 
 
-def coupling(x, s, t, mask, clamp, inverse):
-    """Returns (y, ladj) with ladj[b] = sum_d (1-m_d) clamp*tanh(s[b,d]) (zeros if s is None)."""
+SCALE_ACTIVATIONS = {"exp": 0, "softplus": 1}
+
+
+def scale_activation_id(name):
+    """`MaskedAffineCoupling.scale_activation` -> kernel flag; anything else is the reference's ValueError
+    (`nf4ad/transforms.py:86-87`)."""
+    try:
+        return SCALE_ACTIVATIONS[name]
+    except KeyError:
+        raise ValueError("Unsupported scale_activation") from None
+
+
+def coupling(x, s, t, mask, clamp, inverse, act=0):
+    """Returns (y, ladj) with ladj[b] = sum_d (1-m_d) log_scale[b,d] (zeros if s is None); act: 0 exp, 1 softplus."""
     require_cuda(x, t, mask)
     x, ldx = _rows(x)
     t, ldt = _rows(t)
@@ -97,7 +109,7 @@ def coupling(x, s, t, mask, clamp, inverse):
     B, D = x.shape
     y = torch.empty(B, D, device=x.device, dtype=torch.float32)
     ladj = torch.zeros(B, device=x.device, dtype=torch.float32)
-    check(lib().usf_coupling(ptr(x), ldx, ptr(s), lds, ptr(t), ldt, ptr(mask), float(clamp), int(inverse), ptr(y), D,
+    check(lib().usf_coupling(ptr(x), ldx, ptr(s), lds, ptr(t), ldt, ptr(mask), float(clamp), int(inverse), int(act), ptr(y), D,
                              ptr(ladj), 1.0, B, D, stream()), "usf_coupling")
     return y, ladj
 
@@ -541,9 +553,9 @@ class CouplingFn(torch.autograd.Function):
     """(y, ladj) = coupling(x, s, t); s may be None (additive)."""
 
     @staticmethod
-    def forward(ctx, x, s, t, mask, clamp, inverse):
-        y, ladj = coupling(x, s, t, mask, clamp, inverse)
-        ctx.clamp, ctx.inverse, ctx.has_s = float(clamp), bool(inverse), s is not None
+    def forward(ctx, x, s, t, mask, clamp, inverse, act=0):
+        y, ladj = coupling(x, s, t, mask, clamp, inverse, act)
+        ctx.clamp, ctx.inverse, ctx.has_s, ctx.act = float(clamp), bool(inverse), s is not None, int(act)
         ctx.save_for_backward(x, s, t, mask)
         return y, ladj
 
@@ -566,9 +578,9 @@ class CouplingFn(torch.autograd.Function):
         dt = torch.empty(B, D, device=dev, dtype=torch.float32)
         ds = torch.empty(B, D, device=dev, dtype=torch.float32) if ctx.has_s else None
         check(lib().usf_coupling_bwd(ptr(dy), lddy, ptr(dl), 1.0, ptr(x), ldx, ptr(s), lds, ptr(t), ldt, ptr(m),
-                                     ctx.clamp, int(ctx.inverse), ptr(dx), D, ptr(ds), D, ptr(dt), D, B, D, stream()),
+                                     ctx.clamp, int(ctx.inverse), ctx.act, ptr(dx), D, ptr(ds), D, ptr(dt), D, B, D, stream()),
               "usf_coupling_bwd")
-        return dx, ds, dt, None, None, None
+        return dx, ds, dt, None, None, None, None
 
 
 class BaseLogProbFn(torch.autograd.Function):

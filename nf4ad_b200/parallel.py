@@ -19,6 +19,31 @@ def shard_bounds(n_rows, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def rank_batches(perm, batch_size, rank, world):
+    """The reference's mini-batch schedule (`adbench_wrapper.py:364-377`: consecutive `batch_size` slices of one shuffled
+    index vector) under data parallelism: every rank walks the SAME global batches of the same `perm` and takes its
+    `shard_bounds` slice of each, so one optimizer step still sees exactly `batch_size` samples and an epoch sees every
+    sample once.  A trailing batch with fewer rows than ranks is dropped on every rank (it cannot be sharded)."""
+    n = perm.shape[0]
+    for i in range(0, n, batch_size):
+        idx = perm[i:i + batch_size]
+        if world > 1:
+            if idx.shape[0] < world:
+                return
+            lo, hi = shard_bounds(idx.shape[0], rank, world)
+            idx = idx[lo:hi]
+        yield idx
+
+
+def shared_permutation(n, device, generator, shuffle=True, group=None):
+    """One shuffled index vector, identical on every rank (rank 0's draw is broadcast)."""
+    perm = torch.randperm(n, device=device, generator=generator) if shuffle else torch.arange(n, device=device)
+    rank, world = _world(group)
+    if world > 1:
+        dist.broadcast(perm, 0, group=group)
+    return perm
+
+
 def _world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -115,6 +140,14 @@ class ShardedScorer:
         stageable = (dev.type == "cuda" and x_host.dtype == torch.float32 and x_host.dim() == 2
                      and x_host.stride(1) == 1 and n >= self.chunk_rows)
         bf16_tier = self.narrow_ok and getattr(self.flow, "precision", None) == "bf16"
+        if bf16_tier and stageable and hasattr(self.flow, "resolve_precision"):
+            # "bf16" is a verified tier (Flow._tier): rows may only be narrowed on the host when this stack really runs
+            # its bf16 kernels -- a stack routed to the 3xTF32 kernels wants the fp32 rows
+            tier = self.flow.cached_precision()
+            if tier is None:
+                with torch.no_grad():
+                    tier = self.flow.resolve_precision(x_host[:256].to(dev))
+            bf16_tier = tier == "bf16"
         pinned = x_host.is_pinned() if stageable else False
         # pinned rows: narrowing only where it was measured to pay (host_bf16); pageable rows: always through the ring
         narrow = stageable and bf16_tier and (self.host_bf16 if pinned else (self.host_staging or self.host_bf16))
@@ -259,8 +292,9 @@ class DataParallelTrainer:
             nccl = False
         self.use_graph = bool(use_graph) and nccl and capturable and on_cuda
         self.graph_warmup = int(graph_warmup)
-        self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss]
+        self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss, hyper-parameter signature]
         self.graph_replays = 0
+        self.graph_error = None     # the exception that switched graph replay off, if any
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -282,8 +316,8 @@ class DataParallelTrainer:
     def _clip(self):
         """Global-norm clipping (`adbench_wrapper.py:388-389`).  With `FusedAdam` the coefficient goes into the update
         kernel (a device scalar) instead of a scaling pass over the gradients."""
-        from .optim import FusedAdam
-        if not isinstance(self.opt, FusedAdam):
+        from .optim import FusedAdam, SophiaG
+        if not isinstance(self.opt, (FusedAdam, SophiaG)):
             torch.nn.utils.clip_grad_norm_(self.params, self.clip)
             return
         grads = [p.grad for p in self.params if p.grad is not None]
@@ -320,22 +354,56 @@ class DataParallelTrainer:
             static_loss = loss.detach()
         return graph, static_x, static_loss
 
+    def _hyper_sig(self):
+        """Scalars a captured optimizer launch bakes in (lr, betas, eps, weight decay): a scheduler that changes them
+        must trigger a re-capture, not be ignored by the replay."""
+        sig = []
+        for g in getattr(self.opt, "param_groups", []):
+            sig.append(tuple((k, float(v) if isinstance(v, (int, float)) else tuple(v) if isinstance(v, (tuple, list)) else None)
+                             for k, v in sorted(g.items()) if k in ("lr", "betas", "eps", "weight_decay")))
+        return tuple(sig)
+
     def step(self, batch):
+        from . import _lib
+        try:
+            return self._step(batch)
+        finally:
+            _lib.bump_weights_epoch()     # eager FusedAdam / graph replay: parameters changed behind torch's version counters
+
+    def _step(self, batch):
         if not self.use_graph or not batch.is_cuda:
             return self._eager_step(batch)
         key = (tuple(batch.shape), batch.dtype, batch.device.index)
-        slot = self._graphs.setdefault(key, [0, None, None, None])
+        slot = self._graphs.setdefault(key, [0, None, None, None, None])
+        if slot[1] is not None and slot[4] != self._hyper_sig():
+            slot[1] = None                                # lr / betas changed since the capture: record the step again
         if slot[1] is None:
             slot[0] += 1
             if slot[0] <= self.graph_warmup:          # real (eager) steps; they also initialise the optimizer state
                 return self._eager_step(batch)
             try:
                 slot[1], slot[2], slot[3] = self._capture(batch)     # records the step, does not run it
-            except Exception:
-                self.use_graph = False                 # e.g. a conditioner that is not capture-safe
-                torch.cuda.synchronize()
+                slot[4] = self._hyper_sig()
+            except Exception as e:                     # e.g. a conditioner that is not capture-safe
+                import warnings
+                self.use_graph = False
+                self.graph_error = e
+                warnings.warn(f"nf4ad_b200: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                              "continuing with eager steps", RuntimeWarning)
+                self._abandon_capture(batch.device)
                 return self._eager_step(batch)
         slot[2].copy_(batch)
         slot[1].replay()
         self.graph_replays += 1
         return slot[3].clone()
+
+    def _abandon_capture(self, device):
+        """After a failed capture: drop matrices a half-recorded pass left on the LU layers, let every side stream the
+        step forks (LU inversions, weight-gradient GEMMs) drain, and clear half-accumulated gradients."""
+        from . import ops
+        for m in self.flow.modules():
+            m.__dict__.pop("_A_pre", None)
+        torch.cuda.synchronize(device)
+        for st in list(getattr(self.flow, "_side_streams", None) or []) + list(ops._WGRAD_STREAMS.values()):
+            st.synchronize()
+        self.opt.zero_grad(set_to_none=True)

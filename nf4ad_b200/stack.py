@@ -20,7 +20,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import BlockDesc, LinearDesc, StackDesc, check, lib, ptr, stream
-from .transforms import mlp_layers
+from .transforms import context_dim, mlp_layers
 
 _LOG_2PI = math.log(2.0 * math.pi)
 
@@ -91,10 +91,23 @@ class CompiledStack:
         self._t3 = precision == _lib.USF_PREC_TF32X3      # fp32 weights travel as [W ; W - tf32(W)] (2N rows)
         runs, couplings = _classify(layers)
         n = len(couplings)
-        if n > 0:
-            for c in couplings:
-                if getattr(c, "scale_activation", "exp") != "exp":
-                    raise Unsupported("scale_activation != 'exp'")
+        # conditional flows (USFlows soft training): every conditioner takes `cd` context columns, which then travel
+        # through the chain as extra conditioning columns of the activation row
+        cds = {context_dim(c.conditioner) for c in couplings}
+        if len(cds) > 1:
+            raise Unsupported("couplings disagree on the context width")
+        cd = self.ctx_dim = cds.pop() if cds else 0
+        for c in couplings:                # before any packing work: is every coupling one the fused kernels run?
+            if getattr(c, "scale_activation", "exp") != "exp":
+                raise Unsupported("scale_activation != 'exp'")
+            lin = mlp_layers(c.conditioner)
+            if lin is None:
+                raise Unsupported("conditioner is not a Linear/ReLU chain")
+            if len(lin) > _lib.USF_MAX_MLP:
+                raise Unsupported("conditioner deeper than USF_MAX_MLP")
+            if lin[0].in_features != D + cd:
+                raise Unsupported("conditioner input width != D (+ context)")
+        Dx = D + cd                        # columns of an input row / of the natural layout: [x (D) | context (cd)]
 
         with torch.no_grad():
             # ---- per-coupling coordinate layout --------------------------------------------------
@@ -108,6 +121,9 @@ class CompiledStack:
                 Da, Db = idx_a.numel(), idx_b.numel()
                 if Db == 0:
                     raise Unsupported("coupling transforms no coordinate")
+                # conditioning part = [a coords | context columns]: contiguous, read by the first conditioner layer
+                idx_a = torch.cat([idx_a, torch.arange(D, Dx, dtype=torch.int32, device=device)])
+                Da = Da + cd
                 b_off = _round_up(Da, 16)      # 32-byte aligned b-part: the epilogues use 256-bit row accesses
                 width = _round_up(b_off + Db, 16)
                 cols = torch.full((width,), -1, dtype=torch.int32, device=device)
@@ -128,14 +144,20 @@ class CompiledStack:
             eye_aug[1:] = torch.eye(D, device=device, dtype=torch.float32)
 
             def run_matrix(run):
-                """rows: f(0) = c, f(e_i) = A[:, i] + c   for the run applied in this direction."""
+                """rows: f(0) = c, f(e_i) = A[:, i] + c   for the run applied in this direction; the context columns
+                pass through every affine run unchanged (identity block)."""
                 v = eye_aug
                 seq = reversed(run) if self.inverse else run
                 for layer in seq:
                     v = layer.backward(v) if self.inverse else layer.forward(v)
-                return v.contiguous()
+                if cd == 0:
+                    return v.contiguous()
+                M = torch.zeros(Dx + 1, Dx, device=device, dtype=torch.float32)
+                M[:D + 1, :D] = v
+                M[D + 1:, D:] = torch.eye(cd, device=device, dtype=torch.float32)
+                return M
 
-            natural = torch.arange(D, dtype=torch.int32, device=device)
+            natural = torch.arange(Dx, dtype=torch.int32, device=device)
             in_cols = natural                        # column layout of the current activation
             self.blocks = (BlockDesc * max(n, 1))()
             logdet = 0.0
@@ -150,7 +172,7 @@ class CompiledStack:
             Mt = run_matrix(last_run)
             out_w = _round_up(D, 16)
             out_cols = torch.full((out_w,), -1, dtype=torch.int32, device=device)
-            out_cols[:D] = natural
+            out_cols[:D] = natural[:D]
             self.G_final = LinearDesc()
             self._fill_affine(self.G_final, Mt, in_cols, out_cols, bf16)
 
@@ -162,7 +184,7 @@ class CompiledStack:
             self.logdet_const = logdet      # sum of log|det| of all affine layers (generative direction)
 
             st = StackDesc()
-            st.D, st.n_blocks = D, n
+            st.D, st.n_blocks, st.ctx_dim = D, n, cd
             st.blocks = C.cast(self.blocks, C.POINTER(BlockDesc))
             st.G_final = self.G_final
             st.inverse = 1 if self.inverse else 0
@@ -206,12 +228,7 @@ class CompiledStack:
 
     def _fill_conditioner(self, blk, cpl, L, D, bf16):
         linears = mlp_layers(cpl.conditioner)
-        if linears is None:
-            raise Unsupported("conditioner is not a Linear/ReLU chain")
-        if len(linears) > _lib.USF_MAX_MLP:
-            raise Unsupported("conditioner deeper than USF_MAX_MLP")
-        if linears[0].in_features != D:
-            raise Unsupported("conditioner input width != D")
+        cd = self.ctx_dim
         out_f = linears[-1].out_features
         additive = bool(getattr(cpl, "additive", False))
         if out_f == 2 * D and not additive:
@@ -220,8 +237,11 @@ class CompiledStack:
             affine = False
         else:
             raise Unsupported("conditioner output width is neither D nor 2D")
-        self._verify_mlp(cpl.conditioner, linears, D)
+        self._verify_mlp(cpl.conditioner, linears, D, cd)
         Da, Db, idx_a, idx_b = L["Da"], L["Db"], L["idx_a"], L["idx_b"]
+        # the module's own first layer reads cat([context, x]) (pyro ConditionalDenseNN): activation column j of the
+        # conditioning part [a | ctx] is weight column  cd + a_j  /  (j - |a|)
+        first_cols = torch.where(idx_a < D, idx_a + cd, idx_a - D).to(torch.int32).contiguous()
         dev = self.device
         # tile geometry of the last layer
         if bf16 or self._t3:
@@ -247,7 +267,7 @@ class CompiledStack:
             Wsrc = lin.weight.detach().to(device=dev, dtype=torch.float32)
             bsrc = lin.bias.detach().to(device=dev, dtype=torch.float32) if lin.bias is not None else \
                 torch.zeros(lin.out_features, device=dev)
-            col_idx = idx_a if first else None
+            col_idx = first_cols if first else None
             K = Da if first else lin.in_features
             if last:
                 row_idx, N = rows_last, rows_last.numel()
@@ -264,14 +284,18 @@ class CompiledStack:
             self._fill_linear(blk.mlp[li], W32, Wb, bias.reshape(-1), N, K, ldw)
 
     @staticmethod
-    def _verify_mlp(cond, linears, D):
+    def _verify_mlp(cond, linears, D, cd=0):
         """The Linear chain must reproduce the module (guards against a custom forward)."""
         p = linears[0].weight
         probe = torch.linspace(-1.0, 1.0, 2 * D, device=p.device, dtype=p.dtype).reshape(2, D)
-        ref = cond(probe)
+        if cd:
+            ctx = torch.linspace(0.1, 0.9, 2 * cd, device=p.device, dtype=p.dtype).reshape(2, cd)
+            ref = cond(probe, ctx)
+        else:
+            ref = cond(probe)
         if isinstance(ref, (tuple, list)):
             ref = torch.cat(list(ref), dim=-1)
-        h = probe
+        h = torch.cat([ctx, probe], dim=-1) if cd else probe
         for i, lin in enumerate(linears):
             h = torch.nn.functional.linear(h, lin.weight, lin.bias)
             if i + 1 < len(linears):
@@ -285,6 +309,8 @@ class CompiledStack:
         round to them).  Returns (logprob | None, y | None, ladj | None, n_launches)."""
         _lib.require_cuda(x)
         x_bf16 = x.dtype == torch.bfloat16 and self.precision == _lib.USF_PREC_BF16 and x.dim() == 2
+        if x.dim() != 2 or x.shape[1] != self.D + self.ctx_dim:
+            raise ValueError(f"expected rows of {self.D} coordinates (+ {self.ctx_dim} context columns), got shape {tuple(x.shape)}")
         if x_bf16:
             if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
                 x = x.contiguous()

@@ -32,11 +32,36 @@ class TransformModule(Transform, torch.nn.Module):
 
 
 def _as2d(x):
+    """(..., D) -> ((rows, D), restore): the 1-D layers act on the last dimension, whatever precedes it."""
+    if x.dim() == 2:
+        return x, False
     if x.dim() == 1:
         return x.unsqueeze(0), True
-    if x.dim() != 2:
-        raise ValueError(f"expected (B, D) or (D,) input, got shape {tuple(x.shape)}")
-    return x, False
+    if x.dim() == 0:
+        raise ValueError("expected at least a (D,) input")
+    return x.reshape(-1, x.shape[-1]), tuple(x.shape)
+
+
+def _as_event_rows(x, event_ndim):
+    """(*batch, *event) -> ((rows, prod(event)), restore) for the element-wise layers of an N-D event shape."""
+    if event_ndim == 1:
+        return _as2d(x)
+    if x.dim() < event_ndim:
+        raise ValueError(f"input of shape {tuple(x.shape)} has fewer dimensions than the event shape")
+    n = 1
+    for d in x.shape[x.dim() - event_ndim:]:
+        n *= int(d)
+    if x.dim() == event_ndim:
+        return x.reshape(1, n), tuple(x.shape)
+    return x.reshape(-1, n), (False if x.dim() == 2 and event_ndim == 1 else tuple(x.shape))
+
+
+def _restore(y, how):
+    if how is False:
+        return y
+    if how is True:
+        return y[0]
+    return y.reshape(how)
 
 
 class BaseTransform(TransformModule):
@@ -121,7 +146,7 @@ class LUTransform(BaseTransform):
     def forward(self, x, context=None):
         x2, squeeze = _as2d(x)
         y = ops.linear_fn(x2, self.weight, self.bias, False)
-        return y[0] if squeeze else y
+        return _restore(y, squeeze)
 
     def backward(self, y, context=None):
         y2, squeeze = _as2d(y)
@@ -137,7 +162,7 @@ class LUTransform(BaseTransform):
             x = ops.linear_fn(y2, A, -(A @ self.bias), False)
         else:
             x = ops.LUSolveFn.apply(y2, self.L_raw, self.U_raw, self.bias)
-        return x[0] if squeeze else x
+        return _restore(x, squeeze)
 
     def log_abs_det_jacobian(self, x, y, context=None):
         # O(D) parameter-only constant: plain tensor ops (not on the data path)
@@ -178,12 +203,12 @@ class HouseholderTransform(BaseTransform):
     def forward(self, x, context=None):
         x2, squeeze = _as2d(x)
         y = ops.HouseholderFn.apply(x2, self.vk_householder, False)
-        return y[0] if squeeze else y
+        return _restore(y, squeeze)
 
     def backward(self, y, context=None):
         y2, squeeze = _as2d(y)
         x = ops.HouseholderFn.apply(y2, self.vk_householder, True)
-        return x[0] if squeeze else x
+        return _restore(x, squeeze)
 
     def log_abs_det_jacobian(self, x, y, context=None):
         return torch.zeros((), dtype=x.dtype, device=x.device)
@@ -199,20 +224,19 @@ class ScaleTransform(BaseTransform):
 
     def __init__(self, dim: Iterable[int], *args, **kwargs):
         super().__init__()
-        self.dim = tuple(int(d) for d in dim)
-        if len(self.dim) != 1:
-            raise NotImplementedError("only 1-D event shapes in_dims=[D] are supported")
+        self.dim = tuple(int(d) for d in dim)            # the event shape: [D] or image-shaped [C, H, W]
         self.scale = torch.nn.Parameter(torch.ones(self.dim))
 
+    def _run(self, v, inverse):
+        v2, how = _as_event_rows(v, len(self.dim))
+        out = ops.ScaleFn.apply(v2, self.scale.reshape(-1), inverse)
+        return _restore(out, how)
+
     def forward(self, x, context=None):
-        x2, squeeze = _as2d(x)
-        y = ops.ScaleFn.apply(x2, self.scale, False)
-        return y[0] if squeeze else y
+        return self._run(x, False)
 
     def backward(self, y, context=None):
-        y2, squeeze = _as2d(y)
-        x = ops.ScaleFn.apply(y2, self.scale, True)
-        return x[0] if squeeze else x
+        return self._run(y, True)
 
     def log_abs_det_jacobian(self, x, y, context=None):
         return self.scale.abs().log().sum()
@@ -266,26 +290,39 @@ class SequentialAffineTransform(BaseTransform):
 
 
 class BlockAffineTransform(BaseTransform):
-    """`BlockAffineTransform(in_dims, block_transform)` (`nf4ad/flows.py:95,111`); for the 1-D event
-    shapes nf4ad uses it is the wrapped transform itself (image-shaped in_dims: not supported)."""
+    """`BlockAffineTransform(in_dims, block_transform)` (`nf4ad/flows.py:95,111`): applies a `dim = in_dims[0]` affine
+    layer along the LEADING event dimension.  For `in_dims=[D]` that is the wrapped transform itself; for an image-shaped
+    event `[C, H, W]` it is the same C x C map at every pixel (a 1x1 convolution): the input is viewed as
+    `(B*H*W, C)` rows -- one GEMM / triangular solve over all pixels -- and the log-det counts once per pixel."""
 
     is_affine = True
 
     def __init__(self, in_dims, block_transform: BaseTransform, *args, **kwargs):
         super().__init__()
         self.in_dims = tuple(int(d) for d in in_dims)
-        if len(self.in_dims) != 1:
-            raise NotImplementedError("only 1-D event shapes in_dims=[D] are supported")
         self.block_transform = block_transform
+        self.n_positions = 1
+        for d in self.in_dims[1:]:
+            self.n_positions *= d
+
+    def _run(self, v, fn):
+        n = len(self.in_dims)
+        if n == 1:
+            return fn(v)
+        if v.dim() < n:
+            raise ValueError(f"input of shape {tuple(v.shape)} does not end in the event shape {self.in_dims}")
+        vm = v.movedim(v.dim() - n, -1)                   # (*batch, *spatial, C)
+        out = fn(vm.reshape(-1, self.in_dims[0]))
+        return out.reshape(vm.shape).movedim(-1, v.dim() - n)
 
     def forward(self, x, context=None):
-        return self.block_transform.forward(x)
+        return self._run(x, self.block_transform.forward)
 
     def backward(self, y, context=None):
-        return self.block_transform.backward(y)
+        return self._run(y, self.block_transform.backward)
 
     def log_abs_det_jacobian(self, x, y, context=None):
-        return self.block_transform.log_abs_det_jacobian(x, y)
+        return self.block_transform.log_abs_det_jacobian(x, y) * self.n_positions
 
     def is_feasible(self) -> bool:
         return self.block_transform.is_feasible()
@@ -328,10 +365,16 @@ class InverseTransform(BaseTransform):
 # ------------------------------------------------------------------------------------------------
 # couplings
 # ------------------------------------------------------------------------------------------------
+def context_dim(module):
+    """Width of the context a conditional conditioner takes (`pyro.nn.ConditionalDenseNN`: `forward(x, context)` =
+    DenseNN on `cat([context, x])`); 0 for an unconditional one."""
+    return int(getattr(module, "context_dim", 0) or 0)
+
+
 def mlp_layers(module):
     """If `module` is a plain Linear/ReLU chain (the conditioners nf4ad configures: `nn.Sequential`
-    MLPs wrapped in `.net` -- `tests/conftest.py:111-121` -- or `pyro.nn.DenseNN`), return its Linear
-    layers in call order, else None (opaque conditioner)."""
+    MLPs wrapped in `.net` -- `tests/conftest.py:111-121` -- or `pyro.nn.DenseNN` / `ConditionalDenseNN`), return its
+    Linear layers in call order, else None (opaque conditioner)."""
     if isinstance(module, torch.nn.Linear):
         return [module]
     layers = getattr(module, "layers", None)
@@ -339,6 +382,8 @@ def mlp_layers(module):
             and len(layers) > 0 and all(isinstance(l, torch.nn.Linear) for l in layers):
         linears = list(layers)                                   # DenseNN duck type
     else:
+        if context_dim(module):
+            return None
         leaves = [m for m in module.modules()
                   if len(list(m.children())) == 0 and not isinstance(m, torch.nn.Identity)]
         if len(leaves) % 2 == 0:
@@ -354,14 +399,18 @@ def mlp_layers(module):
 
 
 def run_conditioner(cond, xm, context=None):
-    """Evaluates the conditioner.  Recognised Linear/ReLU chains run on usf_linear (our GEMM +
-    bias/ReLU epilogue); anything else is an opaque user module evaluated as given."""
-    if context is not None:
-        return cond(xm, context)
-    linears = mlp_layers(cond)
-    if linears is None or not xm.is_cuda:
-        return cond(xm)
+    """Evaluates the conditioner on flat rows `xm` (B, D).  Recognised Linear/ReLU chains run on usf_linear (our GEMM +
+    bias/ReLU epilogue) -- a conditional one on `cat([context, xm])`; anything else is an opaque user module evaluated
+    as given (`conditioner(x_masked)` / `conditioner(x_masked, context)`, `nf4ad/transforms.py:71-74`)."""
+    linears = mlp_layers(cond) if xm.is_cuda and xm.dim() == 2 else None
+    cd = context_dim(cond)
+    if linears is None or (context is not None) != (cd > 0) or linears[0].in_features != xm.shape[1] + cd:
+        return cond(xm) if context is None else cond(xm, context)
     h = xm
+    if cd:
+        ctx = context.to(xm.dtype)
+        ctx = ctx.reshape(-1, cd) if ctx.dim() != 2 else ctx
+        h = torch.cat([ctx.expand(xm.shape[0], cd), xm], dim=-1)
     for i, lin in enumerate(linears):
         h = ops.linear_fn(h, lin.weight, lin.bias, i + 1 < len(linears))
     pd = getattr(cond, "param_dims", None)
@@ -375,14 +424,16 @@ def run_conditioner(cond, xm, context=None):
 
 
 def split_params(params, x):
-    """`MaskedAffineCoupling._parse_params` contract (`nf4ad/transforms.py:40-64`)."""
+    """`MaskedAffineCoupling._parse_params` contract (`nf4ad/transforms.py:40-64`): an `(s, t)` pair; ONE tensor of x's
+    shape = additive shift (s = 0, returned as None: the kernels skip the scale arithmetic); ONE tensor with twice x's
+    size along dim 1 = `[s | t]` split there (channels for an image-shaped event); anything else is a ValueError."""
     if isinstance(params, (list, tuple)) and len(params) == 2:
         s, t = params
     elif params.shape == x.shape:
         s, t = None, params
     elif params.dim() >= 2 and x.dim() >= 2 and params.shape[1] == 2 * x.shape[1]:
         c = x.shape[1]
-        s, t = params[:, :c], params[:, c:]
+        s, t = params[:, :c, ...], params[:, c:, ...]
     else:
         raise ValueError(
             "Conditioner output shape not compatible. "
@@ -390,11 +441,52 @@ def split_params(params, x):
     return (None if s is None else s.to(x.dtype)), t.to(x.dtype)
 
 
+def coupling_apply(layer, v, inverse, context=None, additive=False):
+    """One masked coupling in either direction -> (output, per-row log-det of the FORWARD map), for this package's
+    classes and for any layer with the same attributes (`mask`, `conditioner`, `clamp`, `scale_activation`: the
+    reference's own `MaskedAffineCoupling` running unmodified on the drop-in).  The event shape is the mask's
+    (`(1, D)`, or image-shaped `(1, C, H, W)`): the conditioner sees the masked input in that shape
+    (`nf4ad/transforms.py:70-74`), its output is split per `_parse_params` (`:40-64`), and the element-wise part
+    -- mask select, scale activation, scale-shift or its inverse, per-row log-det -- is ONE kernel over the flattened
+    rows (usf_coupling)."""
+    act = ops.scale_activation_id(getattr(layer, "scale_activation", "exp"))
+    mask = layer.mask
+    ev = tuple(mask.shape[1:]) if mask.dim() > 1 else tuple(mask.shape)
+    n = len(ev)
+    if v.dim() == n:
+        vb, how = v.unsqueeze(0), True
+    elif v.dim() == n + 1:
+        vb, how = v, False
+    elif v.dim() > n + 1:
+        vb, how = v.reshape(-1, *v.shape[v.dim() - n:]), tuple(v.shape)
+    else:
+        raise ValueError(f"input of shape {tuple(v.shape)} does not end in the event shape {ev}")
+    B = vb.shape[0]
+    v2 = vb.reshape(B, -1)
+    m = mask.reshape(-1)
+    vm = ops.ScaleFn.apply(v2, m, False)
+    if vb.dim() == 2:
+        params = run_conditioner(layer.conditioner, vm, context)
+    else:                                   # image-shaped event: the conditioner sees (B, C, H, W)
+        vmb = vm.reshape(vb.shape)
+        params = layer.conditioner(vmb) if context is None else layer.conditioner(vmb, context)
+    if additive:
+        t = params[-1] if isinstance(params, (tuple, list)) else params
+        s, t = None, t.to(vb.dtype)
+    else:
+        s, t = split_params(params, vb)
+    s = None if s is None else s.reshape(B, -1)
+    out, ladj = ops.CouplingFn.apply(v2, s, t.reshape(B, -1), m, float(getattr(layer, "clamp", 5.0)), inverse, act)
+    return _restore(out.reshape(vb.shape), how), ladj
+
+
 class MaskedAffineCoupling(BaseTransform):
     """Affine masked coupling (`nf4ad/transforms.py:8-149`):
-    `y = m x + (1-m)(x exp(clamp tanh s(m x)) + t(m x))`, inverse, per-row log-det.
-    The elementwise part is one fused kernel (usf_coupling); the conditioner is evaluated ONCE per call
-    pair (the reference evaluates it again inside log_abs_det_jacobian, `:121-125`)."""
+    `y = m x + (1-m)(x scale(s(m x)) + t(m x))`, `scale = exp(clamp tanh s)` (or the `softplus` variant), inverse,
+    per-row log-det.  Event shape = the mask's (`(1, D)` or image-shaped `(1, C, H, W)`): the input keeps its shape for
+    the conditioner, the element-wise part runs on the flattened rows as one fused kernel (usf_coupling); the
+    conditioner is evaluated ONCE per call pair (the reference evaluates it again inside log_abs_det_jacobian,
+    `:121-125`)."""
 
     bijective = True
 
@@ -411,26 +503,28 @@ class MaskedAffineCoupling(BaseTransform):
     additive = False
 
     def _apply_dir(self, v, inverse, context=None):
-        if self.scale_activation != "exp":
-            raise NotImplementedError("only scale_activation='exp' is implemented on the B200 path")
-        v2, squeeze = _as2d(v)
-        mask = self.mask.reshape(-1)
-        vm = ops.ScaleFn.apply(v2, mask, False)
-        s, t = split_params(run_conditioner(self.conditioner, vm, context), v2)
-        if self.additive:
-            s = None
-        out, ladj = ops.CouplingFn.apply(v2, s, t, mask, self.clamp, inverse)
-        return (out[0] if squeeze else out), ladj
+        return coupling_apply(self, v, inverse, context, additive=self.additive)
 
+    # `TransformedDistribution.log_prob` asks for `x = T.inv(y)` and then `T.log_abs_det_jacobian(x, y)`; the reference
+    # evaluates the conditioner again for the second call (`nf4ad/transforms.py:121-125`).  Here the pair of calls shares
+    # ONE evaluation through a single-use memo: it is replaced by every forward / backward, dropped by train() / eval(),
+    # consumed by the first log_abs_det_jacobian and only honoured for the very (x, y, context) objects it was made from
+    # -- so at most one batch is ever referenced, and never a log-det computed under another context.
     def forward(self, x, context=None):
+        self._memo = None
         y, ladj = self._apply_dir(x, False, context)
-        self._memo = (x, y, ladj)
+        self._memo = (x, y, context, ladj)
         return y
 
     def backward(self, y, context=None):
+        self._memo = None
         x, ladj = self._apply_dir(y, True, context)
-        self._memo = (x, y, ladj)
+        self._memo = (x, y, context, ladj)
         return x
+
+    def train(self, mode: bool = True):
+        self._memo = None
+        return super().train(mode)
 
     def inverse_and_ladj(self, y, context=None):
         x, ladj = self._apply_dir(y, True, context)
@@ -441,8 +535,8 @@ class MaskedAffineCoupling(BaseTransform):
 
     def log_abs_det_jacobian(self, x, y, context=None):
         memo, self._memo = self._memo, None
-        if memo is not None and (memo[0] is x or memo[1] is y):
-            return memo[2]
+        if memo is not None and memo[0] is x and memo[1] is y and memo[2] is context:
+            return memo[3]
         _, ladj = self._apply_dir(x, False, context)
         return ladj
 
@@ -462,13 +556,3 @@ class MaskedCoupling(MaskedAffineCoupling):
 
     def __init__(self, mask, conditioner, *args, **kwargs):
         super().__init__(mask, conditioner)
-
-    def _apply_dir(self, v, inverse, context=None):
-        v2, squeeze = _as2d(v)
-        mask = self.mask.reshape(-1)
-        vm = ops.ScaleFn.apply(v2, mask, False)
-        t = run_conditioner(self.conditioner, vm, context)
-        if isinstance(t, (tuple, list)):
-            t = t[-1]
-        out, ladj = ops.CouplingFn.apply(v2, None, t.to(v2.dtype), mask, self.clamp, inverse)
-        return (out[0] if squeeze else out), ladj

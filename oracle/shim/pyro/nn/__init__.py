@@ -36,3 +36,18 @@ class DenseNN(torch.nn.Module):
         if self.count_params == 1:
             return h
         return tuple(h[..., s] for s in self.param_slices)
+
+
+class ConditionalDenseNN(DenseNN):
+    """Published pyro semantics: `ConditionalDenseNN(input_dim, context_dim, hidden_dims, param_dims)` is a DenseNN over
+    `torch.cat([context, x], dim=-1)` with the context broadcast over x's batch dims.  The conditioner form of USFlows'
+    soft training [RECALL]; reached through `conditioner(x_masked, context)` (`nf4ad/transforms.py:71-74`)."""
+
+    def __init__(self, input_dim, context_dim, hidden_dims, param_dims=(1, 1), nonlinearity=None):
+        super().__init__(int(input_dim) + int(context_dim), hidden_dims, param_dims, nonlinearity)
+        self.input_dim = int(input_dim)
+        self.context_dim = int(context_dim)
+
+    def forward(self, x, context):
+        context = context.expand(x.shape[:-1] + (context.shape[-1],))
+        return super().forward(torch.cat([context, x], dim=-1))

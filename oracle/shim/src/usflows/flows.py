@@ -50,12 +50,40 @@ class Flow(torch.nn.Module):
         self.__dict__["transform"] = dist.TransformedDistribution(self._event_base, self.layers)
 
     # ---- density path (transformed_distribution.py:143-190) ----
+    @property
+    def event_ndim(self):
+        return max(1, len(self._event_base.event_shape))
+
+    def _soft_context(self, x, context):
+        """[RECALL] soft training: the conditioners take the per-sample noise level as context; scoring without
+        one means noise level 0."""
+        if context is None and self.soft_training:
+            lead = x.shape[:x.dim() - self.event_ndim]
+            context = torch.zeros(*lead, 1, dtype=x.dtype, device=x.device)
+        return context
+
     def log_prob(self, x, context=None):
-        return self.transform.log_prob(x)
+        context = self._soft_context(x, context)
+        if context is None and self.event_ndim == 1:
+            return self.transform.log_prob(x)
+        # the same recursion (transformed_distribution.py:168-190) written out, so that a context reaches every layer
+        # and a per-sample (B,) log-det is subtracted as such for an N-D event shape
+        lp = 0.0
+        y = x
+        for layer in reversed(self.layers):
+            xin = layer.backward(y) if context is None else layer.backward(y, context)
+            ladj = layer.log_abs_det_jacobian(xin, y) if context is None else layer.log_abs_det_jacobian(xin, y, context)
+            lp = lp - ladj
+            y = xin
+        return lp + self._event_base.log_prob(y)
 
     def sample(self, sample_shape=None, context=None):
         shape = torch.Size() if sample_shape is None else torch.Size(sample_shape)
-        return self.transform.sample(shape)
+        if context is None and not self.soft_training:
+            return self.transform.sample(shape)
+        with torch.no_grad():
+            z = self._event_base.sample(shape)
+            return self.latent_to_data(z, self._soft_context(z, context))
 
     def rsample(self, sample_shape=None):
         shape = torch.Size() if sample_shape is None else torch.Size(sample_shape)
@@ -63,8 +91,9 @@ class Flow(torch.nn.Module):
 
     def backward(self, x, context=None):
         """data -> latent: every layer's inverse, last layer first."""
+        context = self._soft_context(x, context)
         for layer in reversed(self.layers):
-            x = layer.backward(x)
+            x = layer.backward(x) if context is None else layer.backward(x, context)
         return x
 
     def forward(self, x=None, context=None):
@@ -79,9 +108,10 @@ class Flow(torch.nn.Module):
             x = layer.forward(x)
         return x
 
-    def latent_to_data(self, z):
+    def latent_to_data(self, z, context=None):
+        context = self._soft_context(z, context)
         for layer in self.layers:
-            z = layer.forward(z)
+            z = layer.forward(z) if context is None else layer.forward(z, context)
         return z
 
     # ---- housekeeping ----
@@ -118,6 +148,15 @@ class Flow(torch.nn.Module):
             self.device = kwargs["device"]
         return out
 
+    def soft_noise(self, batch, generator=None):
+        """[RECALL] soft training (SoftFlow-style): one noise level per sample from `training_noise_prior`, the sample is
+        perturbed by N(0, level^2) noise and the level is handed to the conditioners as context.
+        -> (noisy batch, context of shape (B, 1))."""
+        B = batch.shape[0]
+        level = self.training_noise_prior.sample([B]).reshape(B).to(batch)
+        eps = torch.randn(batch.shape, dtype=batch.dtype, device=batch.device, generator=generator)
+        return batch + level.reshape(B, *([1] * (batch.dim() - 1))) * eps, level.reshape(B, 1).detach()
+
     def fit(self, data_train, optim=torch.optim.Adam, optim_params=None, batch_size=32,
             shuffle=True, gradient_clip=None, device=None, jitter=1e-6, epochs=1):
         """[RECALL] feasibility check + jitter, then minimise -mean log_prob (- log_prior)."""
@@ -136,7 +175,10 @@ class Flow(torch.nn.Module):
                 while not self.is_feasible():
                     self.add_jitter(jitter)
                 opt.zero_grad()
-                loss = -self.log_prob(batch).mean()
+                ctx = None
+                if self.soft_training:
+                    batch, ctx = self.soft_noise(batch)
+                loss = -self.log_prob(batch, ctx).mean()
                 if getattr(self, "prior_scale", None) is not None:
                     loss = loss - self.log_prior() / n
                 loss.backward()

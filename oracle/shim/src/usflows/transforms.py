@@ -245,26 +245,35 @@ class SequentialAffineTransform(BaseTransform):
 class BlockAffineTransform(BaseTransform):
     """[INFER flows.py:95,111] `BlockAffineTransform(in_dims, block_transform)`.
 
-    [RECALL] applies `block_transform` along the leading event dim.  Only the
-    1-D event shape `in_dims=[D]` occurs in nf4ad, where it is the
-    wrapped transform itself; image-shaped inputs are out of scope.
+    [RECALL] applies the `dim = in_dims[0]` affine layer along the LEADING event
+    dimension: for `in_dims=[D]` (every nf4ad config) it is the wrapped
+    transform itself; for an image-shaped event `[C, H, W]` it is the same C x C
+    map at every pixel (a 1x1 convolution), so the log-det counts H*W times.
     """
 
     def __init__(self, in_dims, block_transform: BaseTransform, *args, **kwargs):
         super().__init__()
         self.in_dims = tuple(int(d) for d in in_dims)
-        if len(self.in_dims) != 1:
-            raise NotImplementedError("only 1-D event shapes in_dims=[D] are supported")
         self.block_transform = block_transform
 
+    def _per_position(self, v, fn):
+        n = len(self.in_dims)
+        if n == 1:
+            return fn(v)
+        vm = v.movedim(v.dim() - n, -1)                  # (*batch, *spatial, C)
+        return fn(vm.reshape(-1, self.in_dims[0])).reshape(vm.shape).movedim(-1, v.dim() - n)
+
     def forward(self, x, context=None):
-        return self.block_transform.forward(x)
+        return self._per_position(x, self.block_transform.forward)
 
     def backward(self, y, context=None):
-        return self.block_transform.backward(y)
+        return self._per_position(y, self.block_transform.backward)
 
     def log_abs_det_jacobian(self, x, y, context=None):
-        return self.block_transform.log_abs_det_jacobian(x, y)
+        positions = 1
+        for d in self.in_dims[1:]:
+            positions *= d
+        return self.block_transform.log_abs_det_jacobian(x, y) * positions
 
     def is_feasible(self) -> bool:
         return self.block_transform.is_feasible()
@@ -309,20 +318,21 @@ class MaskedCoupling(BaseTransform):
         self.register_buffer("mask", mask.float())
         self.conditioner = conditioner
 
-    def _shift(self, xm):
-        t = self.conditioner(xm)
+    def _shift(self, xm, context=None):
+        t = self.conditioner(xm) if context is None else self.conditioner(xm, context)
         if isinstance(t, (tuple, list)):
             t = t[-1]
         return t.to(xm.dtype)
 
     def forward(self, x, context=None):
-        return x + (1.0 - self.mask) * self._shift(x * self.mask)
+        return x + (1.0 - self.mask) * self._shift(x * self.mask, context)
 
     def backward(self, y, context=None):
-        return y - (1.0 - self.mask) * self._shift(y * self.mask)
+        return y - (1.0 - self.mask) * self._shift(y * self.mask, context)
 
     def log_abs_det_jacobian(self, x, y, context=None):
-        return torch.zeros(x.shape[0] if x.dim() > 1 else (), dtype=x.dtype, device=x.device)
+        batched = x.dim() > self.mask.dim() - 1
+        return torch.zeros(x.shape[0] if batched else (), dtype=x.dtype, device=x.device)
 
     def is_feasible(self) -> bool:
         m = self.mask
