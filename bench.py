@@ -30,20 +30,42 @@ ROWS_PER_GPU = 65536
 ALG_FLOP_PER_SAMPLE = 26.84e6      # mask-pruned, conditioner counted once (SURVEY 8d / BASELINE.md section 4)
 ALG_BYTES_PER_SAMPLE = 4 * D + 4
 LAST_LAYER_GAIN = 0.25             # trained-flow-like activations (see DESIGN.md "Synthetic weights")
-CPU_SAMPLE_ROWS = 4096
-EXEC_FLOP_PER_SAMPLE = 17.7e6      # what the launch chain executes: 9 merged dense maps + 8 pruned MLPs
-# DRAM bytes per tensor-core launch at 65536 rows from the committed ncu capture: 9 GEMM launches at 174.4 MB
-# (106.2 read + 68.2 written) and 8 fused conditioner launches at 120.3 MB (106.0 + 14.3), profiles/r1b_final
-NCU_DRAM_BYTES_PER_LAUNCH = (9 * 174.4e6 + 8 * 120.3e6) / 17
+CPU_ROWS = 65536                   # the CPU arm scores B = 65536 (and B = 32) like the GPU arm
+CPU_SMALL_ROWS = 32
+# DRAM bytes per launch at 65536 rows from the committed ncu capture (profiles/): {kind: bytes}; filled from
+# profiles/r2/ncu_dram_bytes.json when present (written by scripts/ncu_summary.py), else the round-1 capture
+NCU_DRAM_BYTES = {"affine_gemm": 174.4e6, "conditioner+coupling": 120.3e6, "final_gemm+base": 174.4e6}
+
+# Every BASELINE.json config shape (SURVEY.md 8d "Config -> concrete stack"): name -> (flow kind, D, K, conditioner,
+# base, last-layer gain, constructor kwargs, algorithmic MFLOP/sample (pruned, SURVEY 8d / BASELINE.md section 4),
+# roofline that bounds it).  `--config NAME` benches one of them; the default run adds a short resident-input line for
+# each under "configs" (at whatever GPU count it was launched with -> 1 / 2 / 4 / 8 through the driver's scaling run).
+CONFIGS = {
+    "C1-gmm-D2": ("USFlow", 2, 10, ("densenn1", [128, 128]), "usnormal", 0.5, dict(affine_conjugation=True, householder=0, prior_scale=1.0), 0.333, "hbm"),
+    "C1-gmm-D128": ("USFlow", 128, 10, ("densenn1", [128, 128]), "usnormal", 0.5, dict(affine_conjugation=True, householder=0, prior_scale=1.0), 1.35, "tensor"),
+    "C2-mnist-D784": ("NonUSFlow", 784, 8, ("mlp", [256, 256]), "normal", 0.25, dict(affine_conjugation=True, prior_scale=1.0), 26.84, "tensor"),
+    "C3-fashion-D784": ("NonUSFlow", 784, 11, ("mlp", [200, 200, 200]), "laplace", 0.25, dict(affine_conjugation=True, householder=0), 35.24, "tensor"),
+    "C4-adbench-D6": ("NonUSFlow", 6, 3, ("mlp", [6]), "normal", 0.25, dict(affine_conjugation=True, prior_scale=1.0), 0.001, "hbm"),
+    "C4-adbench-D64": ("NonUSFlow", 64, 3, ("mlp", [64]), "normal", 0.25, dict(affine_conjugation=True, prior_scale=1.0), 0.10, "hbm"),
+    "C4-adbench-D500-K3": ("NonUSFlow", 500, 3, ("mlp", [128]), "normal", 0.25, dict(affine_conjugation=True, prior_scale=1.0), 4.10, "tensor"),
+    "C4-adbench-D500-K8": ("NonUSFlow", 500, 8, ("mlp", [256, 256]), "normal", 0.25, dict(affine_conjugation=True), 12.67, "tensor"),
+    "C5-mvtec-D128": ("USFlow", 128, 10, ("densenn1", [512, 256]), "normal", 0.5, dict(affine_conjugation=True, householder=0), 4.30, "tensor"),
+    "C5-mvtec-D256": ("NonUSFlow", 256, 10, ("mlp", [512, 256]), "normal", 0.25, dict(affine_conjugation=True), 8.00, "tensor"),
+}
+DEFAULT_CONFIG = "C2-mnist-D784"
+
+
+def build_config_flow(ns, name, device):
+    from _cases import build_flow as _bf, tame
+    kind, d, k, cond, base, gain, kw, _, _ = CONFIGS[name]
+    torch.manual_seed(0)
+    flow = _bf(ns, kind, d, k, cond, base=base, **kw)
+    tame(flow, gain)
+    return flow.to(device).eval()
 
 
 def build_flow(ns, device, dtype=torch.float32):
-    from _cases import build_flow as _bf, tame
-    torch.manual_seed(0)
-    flow = _bf(ns, "NonUSFlow", D, K_BLOCKS, ("mlp", HIDDEN), base="normal",
-               affine_conjugation=True, prior_scale=1.0)
-    tame(flow, LAST_LAYER_GAIN)
-    return flow.to(device).eval()
+    return build_config_flow(ns, DEFAULT_CONFIG, device)
 
 
 class ClockSampler:
@@ -207,17 +229,62 @@ def measured_peak_tflops():
     return 1400.0, "fallback (B200_PROFILING.md sustained)"
 
 
-def cpu_reference_run(steps, warmup, rows):
-    """The reference's CPU PyTorch path for the same workload: the oracle's restatement of
-    `nf4ad.flows.NonUSFlow` + `MaskedAffineCoupling` on the `src.usflows` shim (the genuine USFlows /
-    pyro packages are not installable), fp32, eval() + no_grad() as `adbench_wrapper.py:422-424`,
-    all host threads."""
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_dram_bytes():
+    p = os.path.join(ROOT, "profiles", "r2", "ncu_dram_bytes.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return {k: float(v) for k, v in j["bytes_per_launch"].items()}, j.get("source", "profiles/r2/ncu_dram_bytes.json")
+        except Exception:
+            pass
+    return dict(NCU_DRAM_BYTES), "ncu --set full dram__bytes_read+write per launch, profiles/r1b_final/tc_kernels_full_raw.csv (round 1 capture)"
+
+
+_FLUSH = {}
+
+
+def timed_steps_with_flush(step, steps, dev):
+    """K steps timed one by one with CUDA events, a 256 MB write (> the 126 MB L2) between them outside the timed
+    intervals: for workloads whose inputs would otherwise sit in L2 from one step to the next.  -> (total ms, last result)"""
+    buf = _FLUSH.get(dev)
+    if buf is None:
+        buf = _FLUSH[dev] = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    out = None
+    for a, b in evs:
+        buf.fill_(1)
+        a.record()
+        out = step()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return sum(a.elapsed_time(b) for a, b in evs), out
+
+
+def cpu_reference_run(steps, warmup, rows, config=DEFAULT_CONFIG):
+    """The reference's CPU PyTorch path for the same workload, fp32, eval() + no_grad() exactly as
+    `adbench_wrapper.py:422-424`, all host threads: the reference's OWN unmodified `nf4ad.flows.NonUSFlow` +
+    `nf4ad.transforms.MaskedAffineCoupling` (snapshot `oracle/_ref`, kind "reference") -- or, if the snapshot is missing,
+    the oracle's restatement of them (kind "port") -- on the oracle's `src.usflows` / `pyro` shim (the genuine USFlows /
+    pyro packages are not installable: no network, un-vendored, un-pinned).  3 warm-ups, median of >= 10 repeats with
+    perf_counter.  -> (samples/s from the median, cores, median ms, kind)"""
     import oracle
-    O = oracle.load()
+    kind = "reference" if oracle.ref_available() else "port"
+    ns = oracle.load_ref() if kind == "reference" else oracle.load()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    flow = build_flow(O, "cpu")
-    x = torch.randn(rows, D, generator=torch.Generator().manual_seed(42))
+    flow = build_config_flow(ns, config, "cpu")
+    d = CONFIGS[config][1]
+    x = torch.randn(rows, d, generator=torch.Generator().manual_seed(42))
     with torch.no_grad():
         for _ in range(warmup):
             flow.log_prob(x)
@@ -226,8 +293,9 @@ def cpu_reference_run(steps, warmup, rows):
             t0 = time.perf_counter()
             flow.log_prob(x)
             ts.append(time.perf_counter() - t0)
-    total = sum(ts)
-    return rows * steps / total, cores, total / steps * 1e3
+    ts.sort()
+    med = ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2])
+    return rows / med, cores, med * 1e3, kind
 
 
 def main():
@@ -236,37 +304,53 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32x3", "fp32"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-s", type=float, default=1.0, help="untimed clock pre-warm (0 for profiler runs)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps (0 disables the leg)")
     ap.add_argument("--train-rows", type=int, default=4096, help="per-GPU training batch")
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS), help="BASELINE.json config shape to bench")
+    ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the short per-config lines")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the batch-size sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "C2 MNIST-shape NonUSFlow log_prob scoring: D=784, K=8, MLP 784-256-256-1568, "
-                          "LU+Householder conjugation, Normal base",
+    ckind, cD, cK, ccond, cbase, cgain, ckw, calg, cbound = CONFIGS[args.config]
+    config = {"workload": f"{args.config}: {ckind} log_prob scoring, D={cD}, K={cK}, conditioner {ccond[0]} {ccond[1]}, "
+                          f"{'LU+Householder' if ckw.get('householder', 1) else 'LU'} conjugation, {cbase} base"
+                          + (" (BASELINE.json configs[1], MNIST shape: MLP 784-256-256-1568)" if args.config == DEFAULT_CONFIG else ""),
               "rows_per_gpu": args.rows, "global_rows": args.rows * max(world, 1), "parallelism": f"batch-shard x{world}",
-              "l2_policy": "inputs larger than L2 (205 MB fp32 per GPU), no flush needed",
-              "weights": "seeded init (seed 0), last conditioner layer x0.25"}
+              "l2_policy": f"inputs larger than L2 ({args.rows * cD * 4 / 1e6:.0f} MB fp32 per GPU), no flush needed"
+                           if args.rows * cD * 4 > 126e6 else "L2 flushed between timed steps (256 MB write)",
+              "weights": f"seeded init (seed 0), last conditioner layer x{cgain}"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        rows = CPU_SAMPLE_ROWS
-        v, cores, ms = cpu_reference_run(args.steps, args.warmup, rows)
+        # the same workload (B = rows per GPU of our arm) on the host cores.  A step is one
+        # log_prob call over the whole batch; if K + W steps of it would not end within a few minutes the step becomes a
+        # bounded row sample of it (said in cpu_baseline.sample)
+        rows = args.rows
+        t_probe = cpu_reference_run(1, 1, min(rows, 4096), args.config)[2] * 1e-3 * rows / min(rows, 4096)
+        budget_s = 240.0
+        if (args.steps + args.warmup) * t_probe > budget_s:
+            rows = max(1024, int(rows * budget_s / ((args.steps + args.warmup) * t_probe)) // 1024 * 1024)
+        v, cores, ms, kind = cpu_reference_run(args.steps, args.warmup, rows, args.config)
+        v32, _, ms32, _ = cpu_reference_run(max(args.steps, 10), 3, CPU_SMALL_ROWS, args.config)
         line = {"impl": "reference", "metric": "log_prob samples/sec", "value": v, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": dict(config, rows_per_step=rows),
-                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"{rows} rows x {args.steps} steps of the same stack (oracle port of the "
-                                           "reference's PyTorch path; real USFlows/pyro not installable)"},
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+                                 "sample": f"{rows} rows per step ({'the full batch' if rows == args.rows else 'bounded sample of the ' + str(args.rows) + '-row batch'}), "
+                                           f"median of {args.steps} steps after {args.warmup} warm-ups; the reference's own NonUSFlow + "
+                                           "MaskedAffineCoupling (oracle/_ref snapshot) on the oracle's src.usflows/pyro shim "
+                                           "(real USFlows/pyro not installable), fp32, eval()+no_grad()",
+                                 "small_batch": {"rows": CPU_SMALL_ROWS, "value": v32, "ms_per_step": ms32}},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -281,9 +365,10 @@ def main():
     from nf4ad_b200 import _lib
     from nf4ad_b200.parallel import ShardedScorer
     P = nf4ad_b200.namespace()
-    flow = build_flow(P, dev)
+    flow = build_config_flow(P, args.config, dev)
     flow.precision = args.precision
     B = args.rows
+    D = cD
     gen = torch.Generator().manual_seed(42 + rank)
     x_host = torch.randn(B, D, generator=gen).pin_memory()
     x = x_host.to(dev)
@@ -324,17 +409,25 @@ def main():
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        small_input = B * D * 4 <= 126e6          # fits the 126 MB L2: flush it between timed steps (untimed)
         barrier()
-        e0.record()
         t_host = time.perf_counter()
-        for i in range(args.steps):
-            lp = scorer.score_local(x)
-            if rank == 0 and i == args.steps // 2 and not sampler.sm:
-                sampler.sample_once()          # kernels are in flight: launches are asynchronous
-        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to enqueue one step
-        e1.record()
-        barrier()
-        ms_total = e0.elapsed_time(e1)
+        if not small_input:
+            e0.record()
+            for i in range(args.steps):
+                lp = scorer.score_local(x)
+                if rank == 0 and i == args.steps // 2 and not sampler.sm:
+                    sampler.sample_once()          # kernels are in flight: launches are asynchronous
+            host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to enqueue one step
+            e1.record()
+            barrier()
+            ms_total = e0.elapsed_time(e1)
+        else:
+            ms_total, lp = timed_steps_with_flush(lambda: scorer.score_local(x), args.steps, dev)
+            host_enqueue_ms = float("nan")
+            if rank == 0 and not sampler.sm:
+                sampler.sample_once()
+            barrier()
         gstats = (ctypes.c_longlong * 4)()
         gfail = ctypes.create_string_buffer(160)
         _lib.lib().usf_debug_graph_stats(gstats, gfail, 160)
@@ -342,6 +435,8 @@ def main():
                       "eager_runs": int(gstats[3]), "last_failure": gfail.value.decode()}
         clocks = sampler.stop() if rank == 0 else None
         launches_per_step = flow.last_launches
+        eff_main, cal_err = flow.effective_precision, flow.bf16_calibration_err      # the tier the timed steps ran at
+        fpr_main = flow._stack(True, dev, eff_main).flops_per_row()
         assert launches_per_step > 0, "fused CUDA path did not run"
         assert bool(torch.isfinite(lp).all())
 
@@ -358,6 +453,27 @@ def main():
         f1.record()
         barrier()
         e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0)
+
+        # ---- the same call as the reference's callers make it: a PAGEABLE numpy array through
+        # ADBenchFlow.predict_score (adbench_wrapper.py:406-433: torch.FloatTensor(X).to(device) ... .cpu().numpy());
+        # host wall clock around the blocking calls (the result is a host array)
+        import numpy as np
+        from nf4ad_b200.adbench import ADBenchFlow
+        X_np = np.array(x_host.numpy(), copy=True)              # a plain (pageable) copy, as a caller's array is
+        wrapper = ADBenchFlow(flow_model=flow, device=str(dev), verbose=False)
+        score_np = (lambda: wrapper.predict_score(X_np)) if world == 1 else \
+            (lambda: scorer.predict_score_host(torch.from_numpy(X_np)).numpy())
+        for _ in range(3):
+            score_np()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_np = score_np()
+        torch.cuda.synchronize()
+        pageable_ms = (time.perf_counter() - t0) * 1e3
+        pageable_h2d = int(getattr(wrapper, "_scorer", scorer).last_h2d_bytes) if world == 1 else int(scorer.last_h2d_bytes)
+        assert s_np.shape == (B,) and bool(np.isfinite(s_np).all())
+        barrier()
 
         # ---- per-launch device time of every kernel of one step (CUDA events on the launching stream)
         n_prof = launches_per_step * 3
@@ -382,6 +498,8 @@ def main():
                         continue
                     flow.precision = prec
                     xs = torch.randn(rows_s, D, device=dev)
+                    if prec == "bf16":
+                        flow.bf16_trust = True      # sweep entries are labelled by the kernels that ran
                     for _ in range(5):
                         flow.log_prob(xs)
                     torch.cuda.synchronize()
@@ -395,6 +513,54 @@ def main():
                     ms_s = h0.elapsed_time(h1) / reps
                     sweep[f"{prec}_rows{rows_s}"] = {"ms_per_call": ms_s, "samples_per_s": rows_s / (ms_s * 1e-3)}
             flow.precision = args.precision
+            flow.bf16_trust = False
+            flow.invalidate_cache()
+
+    # ---- every other BASELINE.json config shape (north star: "throughput on synthetic data of EACH config's shape at 1, 2,
+    # 4 and 8 GPUs ... as a fraction of the roofline"): short resident-input runs, every rank scores its own 65536 rows
+    # (weak scaling like the headline), device-timed, max over ranks; reported under "configs"
+    per_config = {}
+    if args.configs:
+        names = [n for n in CONFIGS if n != args.config]
+        times = torch.zeros(len(names), device=dev, dtype=torch.float64)
+        meta = []
+        with torch.no_grad():
+            for i, name in enumerate(names):
+                kind_, d_, k_, cond_, base_, gain_, kw_, alg_, bound_ = CONFIGS[name]
+                f_ = build_config_flow(P, name, dev)
+                f_.precision = args.precision
+                xs = torch.randn(ROWS_PER_GPU, d_, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+                for _ in range(5):
+                    f_.log_prob(xs)
+                torch.cuda.synchronize()
+                ms_c, _ = timed_steps_with_flush(lambda: f_.log_prob(xs), 20, dev)
+                times[i] = ms_c / 20
+                cs_ = f_._stack(True, dev, f_.effective_precision)
+                fl_ = cs_.flops_per_row() if cs_ is not None else {}
+                meta.append((f_.last_launches, f_.effective_precision, sum(v[1] for v in fl_.values()),
+                             sum(v[0] for v in fl_.values())))
+                del f_, xs, cs_
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        peak_t, _ = measured_peak_tflops()
+        peak_h, _ = measured_peak_hbm()
+        for i, name in enumerate(names):
+            kind_, d_, k_, cond_, base_, gain_, kw_, alg_, bound_ = CONFIGS[name]
+            ms_c = float(times[i])
+            launches_, eff_, useful_, executed_ = meta[i]
+            entry = {"value": ROWS_PER_GPU * world / (ms_c * 1e-3), "unit": "samples/s", "ms_per_step": ms_c,
+                     "rows_per_gpu": ROWS_PER_GPU, "launches_per_step": launches_, "effective_precision": eff_,
+                     "alg_mflop_per_sample": alg_, "bound": bound_}
+            if bound_ == "tensor":
+                ach = useful_ * ROWS_PER_GPU / (ms_c * 1e-3) / 1e12
+                entry["roofline"] = {"achieved": ach, "peak": peak_t, "unit": "TFLOP/s", "frac": ach / peak_t,
+                                     "frac_executed_padded": executed_ * ROWS_PER_GPU / (ms_c * 1e-3) / 1e12 / peak_t,
+                                     "frac_algorithmic": alg_ * 1e6 * ROWS_PER_GPU / (ms_c * 1e-3) / 1e12 / peak_t,
+                                     "note": "bf16 peak; a stack routed to 3xTF32 (effective_precision) is bound at 1/6 of it"}
+            else:
+                ach = (4 * d_ + 4) * ROWS_PER_GPU / (ms_c * 1e-3) / 1e9
+                entry["roofline"] = {"achieved": ach, "peak": peak_h, "unit": "GB/s", "frac": ach / peak_h}
+            per_config[name] = entry
 
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
     train_ms, train_B, train_steps, train_graph = float("nan"), args.train_rows, args.train_steps, False
@@ -407,7 +573,7 @@ def main():
             # "bf16" = mixed precision: bf16 tensor-core GEMMs with fp32 accumulation, fp32 parameters / gradients /
             # Adam state, LU layers applied through their per-step dense inverse; "tf32x3" = the same step with
             # 3xTF32 tensor-core GEMMs (fp32-grade); "fp32" = the all-fp32 kernels
-            tflow = build_flow(P, dev).train()
+            tflow = build_config_flow(P, args.config, dev).train()
             tflow.precision = prec
             opt = FusedAdam(tflow.parameters(), lr=1e-4)   # torch.optim.Adam's update via usf_adam_step; the step replays as one CUDA graph
             trainer = DataParallelTrainer(tflow, opt)
@@ -430,50 +596,103 @@ def main():
                 train32_ms = g0.elapsed_time(g1)
             assert bool(torch.isfinite(loss))
             del tflow, opt, trainer
-    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms, train32_ms, train3_ms = (float(v) for v in t)
+    ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms = (float(v) for v in t)
 
     if rank == 0:
-        n_gemm = sum(len(v) for k, v in per_tag.items() if k != 0)
-        gemm_ms = sum(sum(v) for k, v in per_tag.items() if k != 0)
         steps_prof = 3
-        gemm_ms_per_step = gemm_ms / steps_prof
-        avg_launch_ms = gemm_ms / max(n_gemm, 1)
-        flop_per_launch = ALG_FLOP_PER_SAMPLE * B / (n_gemm / steps_prof)
-        achieved = flop_per_launch / (avg_launch_ms * 1e-3) / 1e12
         peak, peak_src = measured_peak_tflops()
+        peak_hbm, peak_hbm_src = measured_peak_hbm()
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
-        names = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base",
-                 5: "fused_conditioner+coupling"}
+        step_ms = ms_total / args.steps
+        # ---- roofline on what the kernels execute: FLOPs per launch from the packed descriptors (CompiledStack.
+        # flops_per_row: `useful` = the GEMM shapes without tile padding, `executed` = with it), time per launch from the
+        # CUDA events usf_stack_run recorded around every launch of three profiled steps
+        tag_kind = {0: "pack_input", 1: "affine_gemm", 2: "conditioner+coupling", 3: "conditioner+coupling",
+                    4: "final_gemm+base", 5: "conditioner+coupling"}
+        tag_name = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base",
+                    5: "fused_conditioner+coupling"}
+        eff, fpr = eff_main, fpr_main
+        dram, dram_src = ncu_dram_bytes()
+        kernel_of = {"affine_gemm": "usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"),
+                     "final_gemm+base": "usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"),
+                     "conditioner+coupling": "usf_tc_mlp_coupling_kernel" if 5 in per_tag else
+                                             ("usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"))}
+        by_kind, kind_ms = {}, {}
+        for tg, v in per_tag.items():
+            kind_ms.setdefault(tag_kind[tg], []).extend(v)
+        tc_peak = peak if eff == "bf16" else (peak / 6.0 if eff == "tf32x3" else None)
+        for kind, v in kind_ms.items():
+            n_launch = len(v) / steps_prof
+            avg_ms = sum(v) / len(v)
+            e = {"launches_per_step": n_launch, "avg_launch_ms": avg_ms, "share_of_step": sum(v) / steps_prof / step_ms}
+            if kind in fpr:
+                ex, us = fpr[kind]
+                e.update({"kernel": kernel_of[kind], "gflop_useful_per_launch": us * B / n_launch / 1e9,
+                          "gflop_executed_per_launch": ex * B / n_launch / 1e9,
+                          "achieved_tflops": us * B / n_launch / (avg_ms * 1e-3) / 1e12,
+                          "frac": us * B / n_launch / (avg_ms * 1e-3) / 1e12 / peak,
+                          "frac_executed_padded": ex * B / n_launch / (avg_ms * 1e-3) / 1e12 / peak,
+                          "dram_bytes_per_launch_ncu": dram.get(kind)})
+            else:   # pack_input: HBM-bound, reads 4*D and writes 2*ld (bf16) / 4*ld bytes per row
+                ld = (D + 15) // 16 * 16
+                bytes_ = B * (4 * D + (2 if eff == "bf16" else 4) * ld + 4)
+                e.update({"kernel": "usf_convert_rows_kernel", "achieved_gbs": bytes_ / (avg_ms * 1e-3) / 1e9,
+                          "frac": bytes_ / (avg_ms * 1e-3) / 1e9 / peak_hbm, "bound": "hbm"})
+            by_kind[kind] = e
+        dominant = max((k for k in by_kind if k in fpr), key=lambda k: by_kind[k]["share_of_step"])
+        exec_per_row = sum(v[0] for v in fpr.values())
+        useful_per_row = sum(v[1] for v in fpr.values())
+        gemm_ms_per_step = sum(sum(v) for k, v in kind_ms.items() if k in fpr) / steps_prof
+        n_gemm_per_step = sum(len(v) for k, v in kind_ms.items() if k in fpr) / steps_prof
+        dk = by_kind[dominant]
         line = {
             "metric": "log_prob samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3 (fp32 operands as hi+lo on tcgen05)", "fp32": "f32"}[eff],
+            "requested_precision": args.precision, "effective_precision": eff,
+            "bf16_calibration_err": cal_err, "data": "synthetic", "config": config,
             "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms, "graph": graph_info,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scorer.last_h2d_bytes),
                     "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "ShardedScorer.predict_score_host(pinned fp32 rows): the ADBenchFlow.predict_score call sequence",
                     "host_input_bytes_per_step": B * D * 4,
-                    "host_narrowing": bool(scorer.host_bf16 and args.precision == "bf16"),
+                    "host_narrowing": bool(scorer.host_bf16 and eff == "bf16"),
                     "host_threads": int(scorer.host_threads),
                     "fp32_head_rows": (scorer._tune.get((B, D), {}).get("best", None) if scorer.host_bf16 else None)},
+            "e2e_pageable": {"value": B * world * args.steps / (pageable_ms * 1e-3), "unit": "samples/s",
+                             "ms_per_step": pageable_ms / args.steps, "h2d_bytes_per_step": pageable_h2d,
+                             "d2h_bytes_per_step": B * 4,
+                             "api": "nf4ad_b200.adbench.ADBenchFlow.predict_score(pageable numpy array) "
+                                    "(adbench_wrapper.py:406-433), host wall clock" if world == 1 else
+                                    "ShardedScorer.predict_score_host(pageable rows) per rank, host wall clock"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": _lib.lib().usf_gemm_kernel_name(
-                             _lib.USF_PREC_BF16 if args.precision == "bf16" else _lib.USF_PREC_FP32).decode(),
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "ncu --set full dram__bytes_read+write per launch, mean over the 9 GEMM + 8 fused "
-                                           "conditioner launches of a step, profiles/r1b_final/tc_kernels_full_raw.csv",
-                         "executed_flop_per_sample": EXEC_FLOP_PER_SAMPLE,
-                         "frac_executed": achieved / peak * EXEC_FLOP_PER_SAMPLE / ALG_FLOP_PER_SAMPLE,
-                         "alg_flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_ms,
-                         "gemm_share_of_step": gemm_ms_per_step / (ms_total / args.steps),
-                         "launch_ms_by_kind": {names[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},
-                         "launches_by_kind": {names[k]: len(v) // steps_prof for k, v in sorted(per_tag.items())}},
+            "roofline": {"bound": "tensor", "kernel": dk["kernel"], "kind": dominant,
+                         "why_this_kernel": "largest share of the step's device time (launch_ms_by_kind)",
+                         "achieved": dk["achieved_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dk["frac"],
+                         "flop_basis": "executed useful FLOPs of this kernel per launch (GEMM shapes of the packed descriptors "
+                                       "without tile padding) / its mean CUDA-event time",
+                         "peak_source": peak_src + (" -- bf16 figure; this run executed 3xTF32 MMAs (1/6 of it)" if eff == "tf32x3" else ""),
+                         "traffic": dram.get(dominant), "traffic_source": dram_src,
+                         "by_kind": by_kind,
+                         "step": {"flop_useful_per_sample": useful_per_row, "flop_executed_padded_per_sample": exec_per_row,
+                                  "achieved": useful_per_row * B / (step_ms * 1e-3) / 1e12,
+                                  "frac": useful_per_row * B / (step_ms * 1e-3) / 1e12 / peak,
+                                  "gemm_share_of_step": gemm_ms_per_step / step_ms,
+                                  "gemm_launches_per_step": n_gemm_per_step},
+                         "frac_algorithmic": calg * 1e6 * B / (step_ms * 1e-3) / 1e12 / peak,
+                         "alg_flop_per_sample": calg * 1e6,
+                         "alg_note": "SURVEY 8d count (2 dense maps per block, conditioner once); the chain executes fewer FLOPs "
+                                     "because adjacent affine maps are merged at weight-prep time",
+                         "launch_ms_by_kind": {tag_name[k]: sum(v) / len(v) for k, v in sorted(per_tag.items())},
+                         "launches_by_kind": {tag_name[k]: len(v) // steps_prof for k, v in sorted(per_tag.items())}},
         }
+        if per_config:
+            line["configs"] = per_config
         if sweep:
             line["sweep"] = sweep
         if train_steps > 0:
@@ -486,13 +705,17 @@ def main():
                              "fp32_path": {"value": train_B * world * train_steps / (train32_ms * 1e-3),
                                            "ms_per_step": train32_ms / train_steps}}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, cms = cpu_reference_run(3, 1, CPU_SAMPLE_ROWS)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_ROWS} rows x 3 steps of the same stack, fp32, "
-                                              f"{cores} threads ({cms:.0f} ms/step)"}
+            # B = 65536 (and 32), 3 warm-ups, median of 10 -- about 30 s of host work
+            v, cores, cms, kind = cpu_reference_run(10, 3, CPU_ROWS, args.config)
+            v32, _, cms32, _ = cpu_reference_run(10, 3, CPU_SMALL_ROWS, args.config)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{CPU_ROWS} rows per step, 3 warm-ups, median of 10 steps ({cms:.0f} ms), fp32, "
+                                              f"{cores} threads; the reference's own NonUSFlow + MaskedAffineCoupling "
+                                              "(oracle/_ref) on the oracle's src.usflows/pyro shim",
+                                    "small_batch": {"rows": CPU_SMALL_ROWS, "value": v32, "ms_per_step": cms32}}
             # the same leg also checks the timed GPU path against the fp64 oracle on the first 256 rows
             import oracle
-            fo = build_flow(oracle.load(), "cpu").double()
+            fo = build_config_flow(oracle.load(), args.config, "cpu").double()
             with torch.no_grad():
                 ref = fo.log_prob(x_host[:256].double())
                 got = flow.log_prob(x[:256]).double().cpu()

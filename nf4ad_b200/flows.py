@@ -150,6 +150,7 @@ class Flow(torch.nn.Module):
         self._compiled = {}
         self._key_slots = None
         self.__dict__.pop("_ctx_dim", None)
+        self.__dict__.pop("_tier_cache", None)
 
     def _weights_key(self):
         slots = self.__dict__.get("_key_slots") or self._scan_key_slots()

@@ -87,6 +87,7 @@ class CompiledStack:
         self.D, self.inverse, self.precision = D, bool(inverse), precision
         self.device = device
         self._keep = []          # every tensor the descriptors point to
+        self._mlp_widths = {}    # block -> unpadded widths of its conditioner layers
         bf16 = precision == _lib.USF_PREC_BF16
         self._t3 = precision == _lib.USF_PREC_TF32X3      # fp32 weights travel as [W ; W - tf32(W)] (2N rows)
         runs, couplings = _classify(layers)
@@ -154,6 +155,7 @@ class CompiledStack:
                     return v.contiguous()
                 M = torch.zeros(Dx + 1, Dx, device=device, dtype=torch.float32)
                 M[:D + 1, :D] = v
+                M[D + 1:, :D] = v[0]          # row i is f(e_i) = A e_i + c: a context unit vector maps x-coordinates to c
                 M[D + 1:, D:] = torch.eye(cd, device=device, dtype=torch.float32)
                 return M
 
@@ -252,6 +254,7 @@ class CompiledStack:
             Cc = 64 if affine else 128
             nt = -(-Db // Cc)
         blk.C, blk.affine, blk.n_mlp = Cc, 1 if affine else 0, len(linears)
+        self._mlp_widths[len(self._mlp_widths)] = [l.out_features for l in linears]    # block order (flops_per_row)
         t_off = D if (out_f == 2 * D) else 0        # row offset of the shift parameters in the last Linear
         coord = torch.arange(nt * Cc, dtype=torch.int32, device=dev).reshape(nt, Cc)
         valid = coord < Db
@@ -304,6 +307,27 @@ class CompiledStack:
             raise Unsupported("conditioner is not equivalent to its Linear/ReLU chain")
 
     # -------------------------------------------------------------------------------------------
+    def flops_per_row(self):
+        """FLOPs one row costs in this launch chain, per kernel kind, as {kind: (executed, useful)}: `executed` counts the
+        padded GEMM shapes the kernels really multiply (N, K rounded up to the tile granularity, the half-empty last
+        [s|t] tile), `useful` the same GEMMs without padding.  (bench.py: roofline per kernel kind.)"""
+        out = {"affine_gemm": [0, 0], "conditioner+coupling": [0, 0], "final_gemm+base": [0, 0]}
+        D = self.D
+        for j in range(self.desc.n_blocks):
+            blk = self.blocks[j]
+            out["affine_gemm"][0] += 2 * blk.G.N * blk.G.K
+            out["affine_gemm"][1] += 2 * (D + self.ctx_dim) * (D + self.ctx_dim)
+            o = 2 if blk.affine else 1
+            for l in range(blk.n_mlp):
+                lin = blk.mlp[l]
+                out["conditioner+coupling"][0] += 2 * lin.N * lin.K
+                n_useful = o * blk.Db if l == blk.n_mlp - 1 else self._mlp_widths[j][l]
+                k_useful = blk.Da if l == 0 else self._mlp_widths[j][l - 1]
+                out["conditioner+coupling"][1] += 2 * n_useful * k_useful
+        out["final_gemm+base"][0] += 2 * self.G_final.N * self.G_final.K
+        out["final_gemm+base"][1] += 2 * D * D
+        return {k: tuple(v) for k, v in out.items()}
+
     def run(self, x, want_logprob=False, want_y=False, want_ladj=False):
         """x: (B, D) fp32 CUDA -- or bf16 rows for the bf16 tier (usf_stack_run_bf16in: bit-identical to fp32 rows that
         round to them).  Returns (logprob | None, y | None, ladj | None, n_launches)."""

@@ -73,7 +73,7 @@ def build_flow(ns, kind, D, K, cond, base="normal", device="cpu", dtype=torch.fl
                                                                         torch.ones(shape, dtype=dtype))
         cls = ns.NonUSFlow if kind == "NonUSFlow" else ns.USFlow
         return cls(base_distribution=bd, in_dims=in_dims, coupling_blocks=K, conditioner_cls=ccls,
-                   conditioner_args=cargs, **kw)
+                   conditioner_args=cargs, device=device, **kw)
     if ckind == "cond2":             # conditional conditioner (context), affine (s, t) tuple
         ccls, cargs = ns.ConditionalDenseNN, dict(input_dim=D, context_dim=1, hidden_dims=hidden, param_dims=[D, D])
     elif ckind == "cond1":
@@ -100,7 +100,7 @@ def build_flow(ns, kind, D, K, cond, base="normal", device="cpu", dtype=torch.fl
         raise ValueError(base)
     cls = ns.NonUSFlow if kind == "NonUSFlow" else ns.USFlow
     flow = cls(base_distribution=bd, in_dims=[D], coupling_blocks=K,
-               conditioner_cls=ccls, conditioner_args=cargs, **kw)
+               conditioner_cls=ccls, conditioner_args=cargs, device=device, **kw)
     return flow
 
 
