@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32x3", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32x3", "fp32", "auto"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-s", type=float, default=1.0, help="untimed clock pre-warm (0 for profiler runs)")
@@ -612,9 +612,9 @@ def main():
         # flops_per_row: `useful` = the GEMM shapes without tile padding, `executed` = with it), time per launch from the
         # CUDA events usf_stack_run recorded around every launch of three profiled steps
         tag_kind = {0: "pack_input", 1: "affine_gemm", 2: "conditioner+coupling", 3: "conditioner+coupling",
-                    4: "final_gemm+base", 5: "conditioner+coupling"}
+                    4: "final_gemm+base", 5: "conditioner+coupling", 6: "whole_stack"}
         tag_name = {0: "pack_input", 1: "affine_gemm", 2: "mlp_hidden_gemm", 3: "mlp_last_gemm+coupling", 4: "final_gemm+base",
-                    5: "fused_conditioner+coupling"}
+                    5: "fused_conditioner+coupling", 6: "whole_stack_kernel"}
         eff, fpr = eff_main, fpr_main
         dram, dram_src = ncu_dram_bytes()
         kernel_of = {"affine_gemm": "usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"),
@@ -637,13 +637,27 @@ def main():
                           "frac": us * B / n_launch / (avg_ms * 1e-3) / 1e12 / peak,
                           "frac_executed_padded": ex * B / n_launch / (avg_ms * 1e-3) / 1e12 / peak,
                           "dram_bytes_per_launch_ncu": dram.get(kind)})
+            elif kind == "whole_stack":   # small event shapes: ONE kernel, rows in shared memory across all layers
+                bytes_ = B * (4 * D + 4)
+                us = sum(v[1] for v in fpr.values())
+                e.update({"kernel": "usf_small_stack_kernel", "achieved_gbs": bytes_ / (avg_ms * 1e-3) / 1e9,
+                          "frac": bytes_ / (avg_ms * 1e-3) / 1e9 / peak_hbm, "bound": "hbm",
+                          "achieved_tflops": us * B / (avg_ms * 1e-3) / 1e12, "note": "fp32 FFMA kernel"})
             else:   # pack_input: HBM-bound, reads 4*D and writes 2*ld (bf16) / 4*ld bytes per row
                 ld = (D + 15) // 16 * 16
                 bytes_ = B * (4 * D + (2 if eff == "bf16" else 4) * ld + 4)
                 e.update({"kernel": "usf_convert_rows_kernel", "achieved_gbs": bytes_ / (avg_ms * 1e-3) / 1e9,
                           "frac": bytes_ / (avg_ms * 1e-3) / 1e9 / peak_hbm, "bound": "hbm"})
             by_kind[kind] = e
-        dominant = max((k for k in by_kind if k in fpr), key=lambda k: by_kind[k]["share_of_step"])
+        tensor_kinds = [k for k in by_kind if k in fpr]
+        if not tensor_kinds:           # whole-stack kernel: report it against the HBM roofline
+            ws = by_kind["whole_stack"]
+            by_kind["whole_stack"].update({"achieved_tflops": ws.get("achieved_tflops", 0.0)})
+            fpr = dict(fpr, whole_stack=(sum(v[0] for v in fpr_main.values()), sum(v[1] for v in fpr_main.values())))
+            for k in ("affine_gemm", "conditioner+coupling", "final_gemm+base"):
+                fpr.pop(k, None)
+            tensor_kinds = ["whole_stack"]
+        dominant = max(tensor_kinds, key=lambda k: by_kind[k]["share_of_step"])
         exec_per_row = sum(v[0] for v in fpr.values())
         useful_per_row = sum(v[1] for v in fpr.values())
         gemm_ms_per_step = sum(sum(v) for k, v in kind_ms.items() if k in fpr) / steps_prof
@@ -671,9 +685,11 @@ def main():
                                     "(adbench_wrapper.py:406-433), host wall clock" if world == 1 else
                                     "ShardedScorer.predict_score_host(pageable rows) per rank, host wall clock"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": dk["kernel"], "kind": dominant,
+            "roofline": {"bound": dk.get("bound", "tensor"), "kernel": dk["kernel"], "kind": dominant,
                          "why_this_kernel": "largest share of the step's device time (launch_ms_by_kind)",
-                         "achieved": dk["achieved_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dk["frac"],
+                         "achieved": dk["achieved_gbs"] if dk.get("bound") == "hbm" else dk["achieved_tflops"],
+                         "peak": peak_hbm if dk.get("bound") == "hbm" else peak,
+                         "unit": "GB/s" if dk.get("bound") == "hbm" else "TFLOP/s", "frac": dk["frac"],
                          "flop_basis": "executed useful FLOPs of this kernel per launch (GEMM shapes of the packed descriptors "
                                        "without tile padding) / its mean CUDA-event time",
                          "peak_source": peak_src + (" -- bf16 figure; this run executed 3xTF32 MMAs (1/6 of it)" if eff == "tf32x3" else ""),

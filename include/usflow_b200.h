@@ -253,6 +253,11 @@ int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t
                   float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
                   int precision, int* gpu_launches, usf_stream_t stream);
 
+/* 1 if usf_stack_run serves this stack at this precision with ONE whole-stack kernel (small event shapes: D + ctx_dim
+ * <= 64, every layer width <= 128, fp32 weights; rows stay in shared memory across all layers, deterministic row sums),
+ * 0 if it runs the launch chain. */
+int usf_stack_is_single_kernel(const usf_stack_desc* st, int precision);
+
 /* usf_stack_run (precision USF_PREC_BF16) on rows that are bf16 already: x_bf16:(B,D) with ldx in bf16 elements.  The bf16
  * tier rounds its fp32 input to bf16 (round-to-nearest-even) as its first device step, so rows narrowed the same way
  * beforehand -- usf_host_f32_to_bf16 on the host, halving the PCIe copy of a scoring call -- give bit-identical results. */
@@ -311,7 +316,8 @@ int usf_sophia_step(const usf_adam_tensor* tensors, int n_tensors, const float* 
  * usf_stack_run enqueues is bracketed by CUDA events on the launching stream.  usf_profile_end
  * synchronises and returns per-launch device milliseconds and a tag per launch
  * (0 input pack, 1 affine GEMM, 2 conditioner hidden GEMM, 3 last conditioner GEMM + coupling
- * epilogue, 4 final GEMM + base density, 5 fused conditioner chain + coupling).  ms/tags must hold
+ * epilogue, 4 final GEMM + base density, 5 fused conditioner chain + coupling, 6 the whole stack in one
+ * kernel (small event shapes)).  ms/tags must hold
  * max_launches entries. */
 int usf_profile_begin(int max_launches);
 int usf_profile_end(float* ms, int* tags, int* n_out);

@@ -221,6 +221,18 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   USF_CHECK_ARG(ldx >= d_in && (out_y == nullptr || ldy >= st->D), "usf_stack_run: leading dimension < D");
   if (gpu_launches) *gpu_launches = 0;
   if (B == 0) return USF_OK;
+  // small event shapes (D + context <= 64, widths <= 128; fp32 weights): the whole stack in ONE kernel, rows resident
+  // in shared memory across all layers (usf_small.cu) -- the chain below would be 8-40 launches of a few microseconds
+  if (!x_bf16 && small_stack_supported(st, precision)) {
+    USF_CHECK_ARG(out_logprob != nullptr || out_y != nullptr || out_ladj != nullptr, "usf_stack_run: nothing to compute (no output requested)");
+    int rc1;
+    {
+      ProfScope ps(as_stream(stream), 6);
+      rc1 = small_stack_run(st, x, ldx, B, out_logprob, out_y, ldy, out_ladj, as_stream(stream));
+    }
+    if (rc1 == USF_OK && gpu_launches) *gpu_launches = 1;
+    return rc1;
+  }
   const int64_t rows_max = B < kChunkRows ? B : kChunkRows;
   StackPlan p;
   int rc = plan_stack(st, rows_max, precision, &p);
@@ -249,11 +261,19 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   (void)act_lo; (void)hid_lo;
 
   int launches = 0;
+  // Serpentine tile order (bf16 tier): every tensor-core kernel of the chain walks the row tiles in the opposite
+  // direction of its predecessor, so that it starts on the rows that kernel wrote last and that are still in L2
+  // (usf_tc.cu: tc_set_tile_order).  The input pack walks first -> last, so the first GEMM starts reversed.
+  static const bool serpentine = []() { const char* e = getenv("USF_TC_SERPENTINE"); return !(e != nullptr && e[0] == '0'); }();
+  int flip = 1;
+  auto next_order = [&]() { tc_set_tile_order(serpentine ? flip : 0); flip ^= 1; };
+  struct OrderReset { ~OrderReset() { tc_set_tile_order(0); } } order_reset;   // stand-alone GEMM calls stay first -> last
 
   // One GEMM of the chain at the chosen precision.
   auto gemm = [&](const void* A, int64_t lda, const usf_linear_desc& L, int bn, EpiParams& ep, int64_t rows) -> int {
     if (bf16) {
       USF_CHECK_ARG(L.Wb != nullptr, "usf_stack_run: bf16 weights missing in descriptor");
+      next_order();
       return tc_gemm(reinterpret_cast<const uint16_t*>(A), lda, L.Wb, L.ldw, rows, L.N, L.K, bn, ep, s);
     }
     USF_CHECK_ARG(L.W != nullptr, "usf_stack_run: fp32 weights missing in descriptor");
@@ -278,6 +298,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
 
     // stage 0: bring x into the activation layout (bf16, or padded fp32) and seed the per-row accumulator
     int cur = 0;
+    flip = 1;
     {
       ProfScope ps(s, 0);
       if (x_bf16)
@@ -339,6 +360,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.C = blk.C;
           ep.clamp = blk.clamp;
           ep.row_acc = row_acc;
+          next_order();
           {
             ProfScope ps(s, 5);
             rc = tc_mlp_coupling(reinterpret_cast<const uint16_t*>(act[cur]), p.ld_act, rows, blk.n_mlp, Wbs, ldws, biases,
@@ -552,6 +574,10 @@ static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ld
   USF_CUDA(cudaGraphLaunch(exec, s));
   if (gpu_launches) *gpu_launches = launches;
   return USF_OK;
+}
+
+extern "C" int usf_stack_is_single_kernel(const usf_stack_desc* st, int precision) {
+  return small_stack_supported(st, precision) ? 1 : 0;
 }
 
 extern "C" int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob,

@@ -90,6 +90,7 @@ int simt_gemm_plain(const float* A, int64_t lda, int a_trans, const float* W, in
 int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int64_t M, int64_t N,
             int64_t K, int bn, const EpiParams& ep, cudaStream_t stream);
 int tc_pick_bn(int64_t N);
+void tc_set_tile_order(int reverse);   // tile walk of the next tcgen05 launches of this thread: 0 first -> last, 1 last -> first
 // 3xTF32 GEMM (fp32 operands as hi + lo parts, fp32-grade accuracy on the tensor cores), see usf_tc3_gemm_kernel
 int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, const float* Wlo, int64_t ldw, int64_t M,
              int64_t N, int64_t K, int bn, const EpiParams& ep, float* out_lo, float* ub_lo, cudaStream_t stream);
@@ -109,6 +110,11 @@ int tc_timeout_flag(int* out, int reset);
 int tc_trace_ctl(int on, unsigned long long* out, int max_records);
 int trsm_rows(const float* T, int64_t D, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr,
               const float* bias, float* X, int64_t ldx, int64_t B, cudaStream_t stream);
+
+// ---- whole-stack kernel for small event shapes (usf_small.cu): one launch instead of the chain ------------------
+bool small_stack_supported(const usf_stack_desc* st, int precision);
+int small_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob, float* out_y,
+                    int64_t ldy, float* out_ladj, cudaStream_t stream);
 
 // ---- small helpers launched by the stack runner ---------------------------------------------
 int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_f32, int64_t ldy,

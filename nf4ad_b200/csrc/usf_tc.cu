@@ -371,6 +371,7 @@ struct TcArgs {
   int n_tiles;   // ceil(N / bn)
   int m_tiles;   // ceil(M / (128 * CG))
   int n_valid;   // valid output columns for fp32 stores / base density (<= N)
+  int reverse;                // walk the tiles from the last row tile to the first (see tc_set_tile_order)
   int stages;                 // smem ring depth (<= TC_MAX_STAGES)
   uint32_t stage_bytes;       // bytes per stage (A tile + this CTA's W rows), multiple of 1024
   uint32_t backoff_ns;        // sleep between polls of the epilogue / producer waits (0 = spin)
@@ -474,7 +475,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t ph = 0;
       bool ok = true;
       for (int t = unit; t < total_tiles && ok; t += num_units) {
-        const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+        const int tt = args.reverse ? total_tiles - 1 - t : t;
+        const int mt = tt / args.n_tiles, nt = tt - mt * args.n_tiles;
         int width = (int)(args.N - (int64_t)nt * args.bn);
         if (width > args.bn) width = args.bn;
         // a pair splits the tile's N columns evenly: CTA r stages W rows [n0 + r*width/2, +width/2)
@@ -518,7 +520,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint64_t desc_hi = make_smem_desc(0);
       const uint32_t desc_lo0 = (smem_base & 0x3FFFFu) >> 4, desc_stage = TC_STAGE_BYTES >> 4;
       for (int t = unit; t < total_tiles && ok; t += num_units) {
-        const int nt = t % args.n_tiles;
+        const int nt = (args.reverse ? total_tiles - 1 - t : t) % args.n_tiles;
         int width = (int)(args.N - (int64_t)nt * args.bn);
         if (width > args.bn) width = args.bn;
         const uint32_t idesc = make_idesc((uint32_t)width, TC_BM * CG);
@@ -602,7 +604,8 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int a = 0;
     uint32_t aph = 0;
     for (int t = unit; t < total_tiles; t += num_units) {
-      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      const int tt = args.reverse ? total_tiles - 1 - t : t;
+      const int mt = tt / args.n_tiles, nt = tt - mt * args.n_tiles;
       const int64_t row = (int64_t)(mt * CG + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
       const bool rvalid = row < args.M;
       const int64_t n0 = (int64_t)nt * args.bn;
@@ -805,6 +808,7 @@ struct MlpArgs {
   int boff[MLP_MAX_LAYERS];      // offset of layer l's bias vector in the resident smem copy (prefix sums of N)
   const float* bias[MLP_MAX_LAYERS];
   EpiParams ep;                  // coupling epilogue of the last layer
+  int reverse;                   // walk the row tiles from the last to the first (see tc_set_tile_order)
   uint32_t backoff_ns;           // sleep between polls of the epilogue / producer waits (0 = spin)
   unsigned long long* trace;     // debug timeline (see usf_debug_tc_trace); events use tile = (m_tile << 4) | gemm index
 };
@@ -886,12 +890,15 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       };
       const int nkb0 = (args.K[0] + TC_BK - 1) / TC_BK;
       for (int t = unit; t < args.m_tiles && ok; t += num_units) {
-        const int a_row = (t * 2 + (int)cta_rank) * TC_BM;
+        const int rt = args.reverse ? args.m_tiles - 1 - t : t;       // row tile
+        const int a_row = (rt * 2 + (int)cta_rank) * TC_BM;
         // All CTAs run their first layer at about the same time, and its activation rows come from HBM: that phase
         // was HBM-bound (~5.4 TB/s) while HBM idled through the rest of the row tile.  The NEXT row tile's rows are
         // therefore requested into L2 while this tile's last layer streams its (L2-resident) weights.
         int pf_kb = 0;
-        const int pf_row = t + num_units < args.m_tiles ? ((t + num_units) * 2 + (int)cta_rank) * TC_BM : -1;
+        const int pf_row = t + num_units < args.m_tiles
+                               ? ((args.reverse ? args.m_tiles - 1 - (t + num_units) : t + num_units) * 2 + (int)cta_rank) * TC_BM
+                               : -1;
         for (int l = 0; l < L && ok; ++l) {
           const int nkb = (args.K[l] + TC_BK - 1) / TC_BK;
           const uint32_t w_bytes = (uint32_t)(args.bn[l] >> 1) * TC_BK * 2;
@@ -1001,7 +1008,7 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint32_t aph = 0;
     const int ntl = args.ntile[L - 1];
     for (int t = unit; t < args.m_tiles; t += num_units) {
-      const int64_t row = (int64_t)(t * 2 + (int)cta_rank) * TC_BM + rloc;
+      const int64_t row = (int64_t)((args.reverse ? args.m_tiles - 1 - t : t) * 2 + (int)cta_rank) * TC_BM + rloc;
       const bool rvalid = row < args.M;
       // accumulator hand-over: wait until the MMAs of the next GEMM of the chain are complete / give the buffer back
       auto acquire = [&](int gi) -> bool {
@@ -1597,6 +1604,17 @@ static bool tc_pdl() {
   return v == 1;
 }
 
+// Tile order of the next tensor-core launches on this thread.  A launch chain alternates it kernel by kernel
+// ("serpentine"): a kernel walks its row tiles first -> last and leaves the rows it wrote LAST in L2 (126 MB; the two
+// ping-pong activation buffers of a 65536-row chunk are 2 x 105 MB), so the next kernel walks last -> first and reads
+// what is still resident instead of streaming the whole buffer through an LRU cache in exactly the order that evicts
+// every line just before it is needed (ncu, round 1: the GEMM read its whole 106 MB operand from DRAM).
+// Measured on one box, alternating (profiles/r2/ab_matrix.txt): affine GEMM 69.6 -> 67.8 us, fused conditioner kernel
+// 85.5 -> 82.9 us per launch.  (Tried with it and dropped: L2 eviction-priority hints on the TMA loads -- evict_first
+// for the dead activation operand, evict_last for the weights -- cost 1 us per launch.)
+static thread_local int g_tile_reverse = 0;
+void tc_set_tile_order(int reverse) { g_tile_reverse = reverse ? 1 : 0; }
+
 int tc_pick_bn(int64_t N) {
   // balanced N tiles: as few tiles as possible, equal width, multiple of 16, <= 256
   const int64_t nt = ceil_div(N, TC_MAX_BN);
@@ -1647,6 +1665,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   args.m_tiles = (int)ceil_div(M, TC_BM * cg);
   args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
   args.ep = ep;
+  args.reverse = g_tile_reverse;
   args.stage_bytes = TC_A_BYTES + (uint32_t)round_up((int64_t)(bn / cg) * TC_BK * 2, 1024);
   args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES) / args.stage_bytes);
   if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
@@ -1827,6 +1846,7 @@ int tc_mlp_coupling(const uint16_t* A, int64_t lda, int64_t M, int n_layers, con
                       (N[n_layers - 1] % bn_last) == 0 && (reinterpret_cast<uintptr_t>(ep.ub) & 31) == 0 && (ep.ldub % 16) == 0,
                   "tc_mlp_coupling: bad additive tile");
   args.ep = ep;
+  args.reverse = g_tile_reverse;
   args.backoff_ns = tc_backoff_ns();
   args.trace = nullptr;
   if (g_trace_on == 2) {

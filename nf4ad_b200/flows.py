@@ -39,12 +39,19 @@ def _on_device(method):
 
 
 _PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16, "tf32x3": _lib.USF_PREC_TF32X3}
+# `flow.precision`:
+#   "auto"   (default) the <= 1e-4 tier on the fastest kernels that hold it: 3xTF32 tensor-core kernels for D >= 128, fp32
+#            FFMA kernels below (the one-kernel path for small event shapes)
+#   "fp32"   fp32 FFMA kernels (the tightest: ~1e-6)
+#   "tf32x3" 3xTF32 tcgen05 kernels (fp32 operands as hi + lo: <= 1e-4)
+#   "bf16"   bf16 tcgen05 kernels, <= 1e-2 -- verified per weight version (Flow._tier)
+_REQUESTS = ("auto",) + tuple(_PRECISIONS)
 
 
 def _default_precision():
-    p = os.environ.get("USF_PRECISION", "fp32").lower()
-    if p not in _PRECISIONS:
-        raise ValueError(f"USF_PRECISION must be one of {sorted(_PRECISIONS)}, got {p!r}")
+    p = os.environ.get("USF_PRECISION", "auto").lower()
+    if p not in _REQUESTS:
+        raise ValueError(f"USF_PRECISION must be one of {sorted(_REQUESTS)}, got {p!r}")
     return p
 
 
@@ -169,34 +176,51 @@ class Flow(torch.nn.Module):
     # `precision = "bf16"` promises log_prob within 1e-2 of the fp64 result (BASELINE.json north star).  bf16 operands
     # hold that on the large trained-flow-like stacks (D >= 128: 1e-3 .. 6e-3) but not on every stack: the small ADBench /
     # GMM shapes (D < 128) and ill-conditioned untrained stacks amplify the 2^-9 operand rounding past it (4e-2 at D = 6).
-    # So the tier is not taken on trust: stacks with D < 128 always run the 3xTF32 kernels (fp32-grade; those shapes are
-    # launch-latency bound, the tensor-core rate does not matter), and for the others the first scoring call after every
-    # weight change scores its first rows (<= 256) at both tiers and keeps bf16 only if the two agree within
-    # `BF16_CALIBRATION_TOL` on every row.  `effective_precision` reports the outcome; USF_BF16_CALIBRATE=0 trusts bf16.
+    # So the tier is not taken on trust:
+    #   * small event shapes (D + context <= 64, widths <= 128) run the ONE-kernel fp32 path (csrc/usf_small.cu) whatever
+    #     tier was asked for -- those shapes are launch-latency bound, it is both the fastest and the most accurate form;
+    #   * other stacks with D < 128 run the 3xTF32 kernels (fp32-grade; the tensor-core rate does not matter there);
+    #   * for the rest the first scoring call after every weight change scores its first rows (<= 256) at both tiers and
+    #     keeps bf16 only if the two agree within `BF16_CALIBRATION_TOL` on every row.
+    # `effective_precision` reports the outcome; USF_BF16_CALIBRATE=0 / `bf16_trust` run the bf16 kernels regardless.
     BF16_CALIBRATION_TOL = 5e-3
     BF16_MIN_DIM = 128
+    SMALL_MAX_DIM = 64
+
+    def _small_ok(self, device):
+        """Does the one-kernel path take this stack (both directions share the shapes)?"""
+        if self.event_dim + self.context_dim() > self.SMALL_MAX_DIM or len(self.event_shape) != 1:
+            return False
+        cs = self._stack(True, device, "fp32")
+        return cs is not None and cs.single_kernel
 
     def _tier(self, x2=None, context_rows=None):
-        if self.precision != "bf16":
-            self.effective_precision = self.precision
-            return self.precision
+        want = self.precision
+        if want == "auto":
+            want = "tf32x3" if self.event_dim >= self.BF16_MIN_DIM else "fp32"
+        if want == "fp32" or (want == "bf16" and self.__dict__.get("bf16_trust", False)) or \
+                (want == "bf16" and os.environ.get("USF_BF16_CALIBRATE", "1") == "0"):
+            self.effective_precision = want
+            return want
         key = self._weights_key()
         hit = self.__dict__.get("_tier_cache")
-        if hit is not None and hit[0] == key and (hit[2] or x2 is None):
+        if hit is not None and hit[0] == (key, want) and (hit[2] or x2 is None):
+            self.effective_precision = hit[1]
             return hit[1]
-        tier, calibrated, err = "bf16", False, None
-        if os.environ.get("USF_BF16_CALIBRATE", "1") == "0" or self.__dict__.get("bf16_trust", False):
-            calibrated = True                          # run the bf16 kernels whatever the stack (kernel tests, experiments)
+        device = x2.device if x2 is not None else next(self.parameters()).device
+        tier, calibrated, err = want, False, None
+        if self._small_ok(device):
+            tier, calibrated = "fp32", True
+        elif want == "tf32x3":
+            calibrated = True
         elif self.event_dim < self.BF16_MIN_DIM:
             tier, calibrated = "tf32x3", True
         elif x2 is not None and x2.shape[0] > 0 and not self._needs_grad(x2):
             rows = (x2 if context_rows is None else context_rows)[:256]
-            lo = self._stack(True, x2.device, "bf16")
-            hi = self._stack(True, x2.device, "tf32x3") or self._stack(True, x2.device, "fp32")
-            if lo is None or lo.desc.base_kind < 0:
-                calibrated = True                      # no fused bf16 path at all: nothing to calibrate
-            elif hi is None:
-                calibrated = True
+            lo = self._stack(True, device, "bf16")
+            hi = self._stack(True, device, "tf32x3") or self._stack(True, device, "fp32")
+            if lo is None or lo.desc.base_kind < 0 or hi is None:
+                calibrated = True                      # no fused bf16 path at all / nothing to compare with
             else:
                 a = lo.run(rows, want_logprob=True)[0].double()
                 b = hi.run(rows.float(), want_logprob=True)[0].double()
@@ -206,20 +230,19 @@ class Flow(torch.nn.Module):
                 calibrated = True
                 # the packed weights of the tier that lost are not needed until the weights change again
                 self._compiled.pop((True, lo.precision if tier != "bf16" else hi.precision), None)
-        if tier == "tf32x3" and x2 is not None and self._stack(True, x2.device, "tf32x3") is None \
-                and self._stack(True, x2.device, "fp32") is not None:
+        if tier == "tf32x3" and self._stack(True, device, "tf32x3") is None and self._stack(True, device, "fp32") is not None:
             tier = "fp32"                              # shapes the 3xTF32 kernels do not take (N > 1024)
-        self.__dict__["_tier_cache"] = (key, tier, calibrated, err)
+        self.__dict__["_tier_cache"] = ((key, want), tier, calibrated, err)
         self.effective_precision = tier
         self.bf16_calibration_err = err
         return tier
 
     def cached_precision(self):
         """The resolved tier of the current weights, or None when it has not been calibrated since they changed."""
-        if self.precision != "bf16":
-            return self.precision
+        if self.precision == "fp32":
+            return "fp32"
         hit = self.__dict__.get("_tier_cache")
-        return hit[1] if hit is not None and hit[2] and hit[0] == self._weights_key() else None
+        return hit[1] if hit is not None and hit[2] and hit[0][0] == self._weights_key() else None
 
     def resolve_precision(self, x):
         """The tier grad-free calls on these weights run at ("bf16" may resolve to "tf32x3" / "fp32", see above);
@@ -234,7 +257,10 @@ class Flow(torch.nn.Module):
 
     def _stack(self, inverse, device, precision=None):
         """Compiled (packed) stack for this direction / precision / weight version, or None."""
-        prec = _PRECISIONS[precision or self.precision]
+        precision = precision or self.precision
+        if precision == "auto":
+            precision = "tf32x3" if self.event_dim >= self.BF16_MIN_DIM else "fp32"
+        prec = _PRECISIONS[precision]
         slot = (bool(inverse), prec)
         key = (self._weights_key(), str(device))
         hit = self._compiled.get(slot)
@@ -304,7 +330,8 @@ class Flow(torch.nn.Module):
             lp, _, _, n = cs.run(xin, want_logprob=True)
             self.last_launches = n
             return lp.reshape(lead)
-        # autograd (training) pass; "bf16" / "tf32x3" select the tensor-core forms of its GEMMs (ops.tc_training)
+        # autograd (training) pass; "bf16" / "tf32x3" select the tensor-core forms of its GEMMs (ops.tc_training);
+        # "auto" trains on the fp32 kernels (the reference's arithmetic)
         mode = {"bf16": 1, "tf32x3": 2}.get(self.precision, 0) if torch.is_grad_enabled() else 0
         with ops.tc_training(mode):
             z, neg_ladj = self._inverse_layers(self._unflat(x2), context)

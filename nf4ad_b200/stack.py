@@ -15,6 +15,7 @@ last GEMM whose epilogue performs the coupling update + log-det reduction (or th
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -245,8 +246,16 @@ class CompiledStack:
         # conditioning part [a | ctx] is weight column  cd + a_j  /  (j - |a|)
         first_cols = torch.where(idx_a < D, idx_a + cd, idx_a - D).to(torch.int32).contiguous()
         dev = self.device
-        # tile geometry of the last layer
-        if bf16 or self._t3:
+        # tile geometry of the last layer: tiles of Cc coordinates, packed per tile as [s(Cc) | t(Cc)] (additive: [t(Cc)])
+        # (Tried: tiles of 128 coordinates plus one ragged last tile -- Db = 392: 3 x 128 + 16 = 800 [s|t] columns instead of
+        # 4 x 112 = 896.  The last layer of the fused kernel is bound by its coupling epilogue, not by its MMAs, and the
+        # longer 128-coordinate tiles plus the hand-over of a fourth, tiny tile cost 1.3 us per launch: dropped.)
+        ragged = False
+        if bf16:
+            cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
+            nt = -(-Db // cap)
+            Cc = _round_up(-(-Db // nt), 16)
+        elif self._t3:
             cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
             nt = -(-Db // cap)
             Cc = _round_up(-(-Db // nt), 16)
@@ -254,15 +263,17 @@ class CompiledStack:
             Cc = 64 if affine else 128
             nt = -(-Db // Cc)
         blk.C, blk.affine, blk.n_mlp = Cc, 1 if affine else 0, len(linears)
-        self._mlp_widths[len(self._mlp_widths)] = [l.out_features for l in linears]    # block order (flops_per_row)
         t_off = D if (out_f == 2 * D) else 0        # row offset of the shift parameters in the last Linear
-        coord = torch.arange(nt * Cc, dtype=torch.int32, device=dev).reshape(nt, Cc)
-        valid = coord < Db
-        src_b = torch.where(valid, idx_b[torch.clamp(coord, max=Db - 1).long()], torch.full_like(coord, -1))
-        if affine:
-            rows_last = torch.cat([src_b, torch.where(valid, src_b + t_off, src_b)], dim=1).reshape(-1)
-        else:
-            rows_last = torch.where(valid, src_b + t_off, src_b).reshape(-1)
+        self._mlp_widths[len(self._mlp_widths)] = [l.out_features for l in linears]    # block order (flops_per_row)
+        tiles = []
+        for ti in range(nt):
+            Ct = Cc if not (ragged and ti == nt - 1) else _round_up(Db - (nt - 1) * Cc, 16)
+            coord = ti * Cc + torch.arange(Ct, dtype=torch.int32, device=dev)
+            valid = coord < Db
+            src_b = torch.where(valid, idx_b[torch.clamp(coord, max=Db - 1).long()], torch.full_like(coord, -1))
+            shifted = torch.where(valid, src_b + t_off, src_b)
+            tiles.append(torch.cat([src_b, shifted]) if affine else shifted)
+        rows_last = torch.cat(tiles)
         rows_last = rows_last.contiguous()
 
         for li, lin in enumerate(linears):
@@ -327,6 +338,11 @@ class CompiledStack:
         out["final_gemm+base"][0] += 2 * self.G_final.N * self.G_final.K
         out["final_gemm+base"][1] += 2 * D * D
         return {k: tuple(v) for k, v in out.items()}
+
+    @property
+    def single_kernel(self):
+        """True when usf_stack_run serves this stack with the one whole-stack kernel (small event shapes)."""
+        return bool(lib().usf_stack_is_single_kernel(C.byref(self.desc), self.precision))
 
     def run(self, x, want_logprob=False, want_y=False, want_ladj=False):
         """x: (B, D) fp32 CUDA -- or bf16 rows for the bf16 tier (usf_stack_run_bf16in: bit-identical to fp32 rows that

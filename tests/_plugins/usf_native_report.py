@@ -14,7 +14,7 @@ def pytest_sessionfinish(session, exitstatus):
         st = (ctypes.c_longlong * 4)()
         buf = ctypes.create_string_buffer(160)
         _lib.lib().usf_debug_graph_stats(st, buf, 160)
-        stats = f"replays={st[0]} captures={st[1]} failed={st[2]} eager={st[3]}"
+        stats = f"graph_replays={st[0]} graph_captures={st[1]} capture_failures={st[2]} eager_runs={st[3]}"
     except Exception as e:          # report, never fail the inner session for this
         stats = f"unavailable ({type(e).__name__})"
     print(f"\nUSF_NATIVE_REPORT loaded={int(loaded)} {stats}")

@@ -339,3 +339,47 @@ def test_image_shaped_flow_trains_and_samples(P):
     twin.load_state_dict(sd)
     with torch.no_grad():
         assert torch.allclose(twin.eval().log_prob(x), flow.eval().log_prob(x), rtol=1e-5, atol=1e-4)
+
+
+SMALL = [
+    # kind, D, K, conditioner, base, kwargs -- shapes the one-kernel path takes (D + context <= 64, widths <= 128)
+    ("NonUSFlow", 2, 4, ("mlp", [16]), "normal", dict(affine_conjugation=True)),
+    ("USFlow", 2, 10, ("densenn1", [128, 128]), "usnormal", dict(affine_conjugation=True, householder=0, prior_scale=1.0)),
+    ("NonUSFlow", 6, 3, ("mlp", [6]), "laplace", dict(affine_conjugation=True, prior_scale=1.0)),
+    ("NonUSFlow", 20, 3, ("mlp", [20]), "normal", dict(affine_conjugation=True, prior_scale=1.0)),
+    ("NonUSFlow", 32, 3, ("mlp", [128]), "normal", dict(affine_conjugation=True, prior_scale=1.0)),
+    ("NonUSFlow", 33, 2, ("densenn2", [40]), "normal", dict(affine_conjugation=False, lu_transform=2, householder=2)),
+    ("USFlow", 50, 5, ("mlp_add", [64, 64, 64]), "normal", dict(affine_conjugation=True)),
+    ("NonUSFlow", 64, 3, ("mlp", [64]), "normal", dict(affine_conjugation=True, prior_scale=1.0)),
+    ("NonUSFlow", 16, 3, ("cond2", [32]), "normal", dict(affine_conjugation=True, soft_training=True)),
+]
+
+
+@pytest.mark.parametrize("cfg", SMALL, ids=lambda c: f"{c[0]}-D{c[1]}-K{c[2]}-{c[3][0]}")
+def test_small_stack_single_kernel(O, P, cfg):
+    """Small event shapes run the WHOLE stack as one kernel (csrc/usf_small.cu), whatever tier is requested: fp32-grade
+    against the fp64 oracle in both directions, ragged batches, deterministic (bit-identical repeats: no atomics)."""
+    kind, D, K, cond, base, kw = cfg
+    fo, fp = _pair(O, P, kind, D, K, cond, base, 0.5, seed=D * 3 + K, **kw)
+    g = torch.Generator().manual_seed(11)
+    for B in (1, 63, 64, 65, 1000):
+        x = torch.randn(B, D, generator=g)
+        zs = torch.randn(B, D, generator=g)
+        with torch.no_grad():
+            ref, z_ref, xs_ref = fo.log_prob(x.double()), fo.backward(x.double()), fo.latent_to_data(zs.double())
+            for precision in ("auto", "fp32", "tf32x3", "bf16"):
+                fp.precision = precision
+                lp = fp.log_prob(x.cuda())
+                assert fp.last_launches == 1 and fp.effective_precision == "fp32", (precision, fp.last_launches, fp.effective_precision)
+                assert float(lp_err(lp, ref).max()) < FP32_TOL
+            z = fp.backward(x.cuda())
+            assert fp.last_launches == 1 and float(row_err(z, z_ref).max()) < FP32_TOL
+            xs = fp.latent_to_data(zs.cuda())
+            assert fp.last_launches == 1 and float(row_err(xs, xs_ref).max()) < FP32_TOL
+            assert torch.equal(fp.log_prob(x.cuda()), lp) and torch.equal(fp.log_prob(x.cuda()), lp)      # deterministic
+    # a row's score does not depend on the batch it travels in
+    with torch.no_grad():
+        big = torch.randn(70000, D, generator=g).cuda()
+        lp = fp.log_prob(big)
+        assert torch.equal(lp[12345:12400], fp.log_prob(big[12345:12400].contiguous()))
+        assert bool(torch.isfinite(lp).all())
