@@ -12,8 +12,12 @@
 //   * deterministic: a row's log-det / log-density terms are summed by one half-warp in a fixed order -- no atomics;
 //   * 256 threads = 16 row groups x 16 column lanes; a thread owns a 4 x 8 register tile (rows 4 ty..+3, columns
 //     tx + 16 j), operands are read as float4 along K from padded rows (conflict-free quarter-warp accesses);
-//   * shared memory is sized from the widest layer of the stack (22 KB for D = 6 -> several CTAs per SM hide the
-//     barrier latency of the tiny layers; 200 KB for 128-wide hidden layers).
+//   * latency: the next layer's packed weights (and the next tile's input rows) travel into the second half of a
+//     double-buffered staging area with cp.async while the current layer computes -- one __syncthreads per layer, no
+//     global-memory latency on the layer-to-layer critical path; only the output columns a coupling really uses
+//     (round_up(Db, 16) of s and of t out of the packed 64 + 64) are staged and multiplied;
+//   * shared memory is sized from the widest layer of the stack (a few KB for D = 6 -> two CTAs per SM; ~200 KB for
+//     128-wide hidden layers).
 //
 // Layout conventions are those of the packed descriptors (include/usflow_b200.h): activation row
 // [a-part | pad | b-part at b_off], last conditioner layer packed as ONE tile [s(64) | t(64)] (affine) or [t(128)]
@@ -31,12 +35,14 @@ constexpr int SS_MAXW = 128;
 enum SsKind : int { SS_AFFINE = 0, SS_HIDDEN = 1, SS_COUPLING = 2, SS_FINAL = 3 };
 
 struct SsOp {
-  const float* W;      // (N, ldw) fp32, K-major rows
+  const float* W;      // (N, ldw) fp32, K-major rows (ldw a multiple of 8, pad columns zero: usf_pack_matrix)
   const float* bias;   // (N)
-  int N, K, ldw;
+  int N, K, ldw;       // N: columns this kernel computes (a coupling: 2 x Db16 (affine) / Db16 (additive))
   int kind;
   int first;           // conditioner layer whose input is the activation row (columns [0, K)) instead of the hidden buffer
   int b_off, Db, affine;
+  int t_row;           // affine coupling: first packed row of the shift parameters (64)
+  int woff;            // resident mode: offset (floats) of this layer's staged weights, the bias follows them
   float clamp;
 };
 
@@ -44,10 +50,14 @@ struct SsArgs {
   int n_ops;
   int d_in;            // input columns (D + context)
   int D;
-  int lda;             // shared-memory row stride of the activation / hidden buffers (floats)
-  int wbuf_floats;     // capacity of the weight staging buffer
+  int lda;             // shared-memory row stride of the activation buffers (floats)
+  int ldh;             // ... of the hidden buffers
+  int ldxs;            // ... of the input staging buffers
+  int wbuf_floats;     // capacity of ONE weight staging buffer (resident mode: of the whole weight area)
+  int resident;        // every layer's weights fit in shared memory together: staged once per CTA, not once per row tile
   int inverse;
   int base_kind;       // -1: none
+  int x_vec;           // input rows can be fetched in 16-byte pieces
   int64_t B;
   const float* x;
   int64_t ldx;
@@ -69,71 +79,144 @@ __device__ __forceinline__ float half_warp_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   return v;
 }
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(SS_THREADS) usf_small_stack_kernel(const __grid_constant__ SsArgs args) {
+// Requests one layer's weights + bias into a staging buffer (asynchronously; rows beyond N are zeroed with plain stores).
+// A coupling layer only brings the rows it uses: [0, Db16) of s and [t_row, t_row + Db16) of t, packed back to back.
+__device__ __forceinline__ void stage_op(const SsOp& op, float* wbuf, float* bbuf, int tid) {
+  const int K4 = (op.K + 3) & ~3, ldw = K4 + 4, N = op.N, N16 = (N + 15) & ~15, kq = K4 >> 2;
+  const int half = op.kind == SS_COUPLING && op.affine ? (N >> 1) : N;   // rows of the first (or only) source range
+  for (int i = tid; i < N16 * kq; i += SS_THREADS) {
+    const int n = i / kq, k = (i - n * kq) << 2;
+    float* dst = wbuf + n * ldw + k;
+    if (n < N) {
+      const int src_row = n < half ? n : op.t_row + (n - half);
+      cp_async16(dst, op.W + (size_t)src_row * op.ldw + k);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int i = tid; i < N16; i += SS_THREADS) {
+    if (i < N && op.bias != nullptr) cp_async4(bbuf + i, op.bias + (i < half ? i : op.t_row + (i - half)));
+    else bbuf[i] = 0.f;
+  }
+}
+
+// Requests the input rows of one tile into a staging buffer (columns [d_in, d4) and rows beyond the batch are zeroed).
+__device__ __forceinline__ void stage_x(const SsArgs& args, int64_t tile, float* xbuf, int tid) {
+  const int64_t row0 = tile * SS_ROWS;
+  const int nrows = (int)((args.B - row0) < SS_ROWS ? (args.B - row0) : SS_ROWS);
+  const int d4 = (args.d_in + 3) & ~3;
+  if (args.x_vec) {
+    const int q = d4 >> 2;
+    for (int i = tid; i < SS_ROWS * q; i += SS_THREADS) {
+      const int r = i / q, c = (i - r * q) << 2;
+      float* dst = xbuf + r * args.ldxs + c;
+      if (r < nrows) cp_async16(dst, args.x + (row0 + r) * args.ldx + c);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    for (int i = tid; i < SS_ROWS * d4; i += SS_THREADS) {
+      const int r = i / d4, c = i - r * d4;
+      float* dst = xbuf + r * args.ldxs + c;
+      if (r < nrows && c < args.d_in) cp_async4(dst, args.x + (row0 + r) * args.ldx + c);
+      else *dst = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SS_THREADS, 2) usf_small_stack_kernel(const __grid_constant__ SsArgs args) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const int lda = args.lda;
-  float* act[2] = {smem, smem + SS_ROWS * lda};
-  float* hid[2] = {smem + 2 * SS_ROWS * lda, smem + 3 * SS_ROWS * lda};
-  float* wbuf = smem + 4 * SS_ROWS * lda;
-  float* bbuf = wbuf + args.wbuf_floats;
-  float* racc = bbuf + SS_MAXW;
+  const int lda = args.lda, ldh = args.ldh;
+  float* const act0 = smem;
+  float* const act1 = act0 + SS_ROWS * lda;
+  float* const hid0 = act1 + SS_ROWS * lda;
+  float* const hid1 = hid0 + SS_ROWS * ldh;
+  float* const xb0 = hid1 + SS_ROWS * ldh;
+  float* const xb1 = xb0 + SS_ROWS * args.ldxs;
+  float* const wb0 = xb1 + SS_ROWS * args.ldxs;
+  float* const wb1 = wb0 + (args.resident ? 0 : args.wbuf_floats);
+  float* const bb0 = wb0 + (args.resident ? 1 : 2) * args.wbuf_floats;
+  float* const bb1 = bb0 + SS_MAXW;
+  float* const racc = bb1 + SS_MAXW;
+  float* const locs = racc + SS_ROWS;
+  float* const iscs = locs + 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t n_tiles = (args.B + SS_ROWS - 1) / SS_ROWS;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
 
+  if (tid < 64) {
+    locs[tid] = (args.base_kind >= 0 && tid < args.D) ? args.loc[tid] : 0.f;
+    iscs[tid] = (args.base_kind >= 0 && tid < args.D) ? args.inv_scale[tid] : 0.f;
+  }
+  // in flight before the first layer: this CTA's first input tile and the first layer's weights -- or, when they all
+  // fit, EVERY layer's weights, which then stay for all the row tiles of this CTA
+  stage_x(args, blockIdx.x, xb0, tid);
+  if (args.resident) {
+    for (int oi = 0; oi < args.n_ops; ++oi) {
+      const SsOp& op = args.ops[oi];
+      const int n16 = (op.N + 15) & ~15, ldw = ((op.K + 3) & ~3) + 4;
+      stage_op(op, wb0 + op.woff, wb0 + op.woff + n16 * ldw, tid);
+    }
+  } else {
+    stage_op(args.ops[0], wb0, bb0, tid);
+  }
+  cp_async_commit();
+
+  int sbuf = 0;   // staging buffer holding the CURRENT layer's weights
+  int xsel = 0;   // staging buffer holding the CURRENT tile's input rows
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * SS_ROWS;
     const int nrows = (int)((args.B - row0) < SS_ROWS ? (args.B - row0) : SS_ROWS);
-    __syncthreads();   // the previous tile's last reads of the buffers are done
-    {
-      // x rows -> act[0] (columns beyond d_in up to the next multiple of 4 are zero: the first map reads K rounded up)
-      const int d4 = (args.d_in + 3) & ~3;
-      for (int i = tid; i < SS_ROWS * d4; i += SS_THREADS) {
-        const int r = i / d4, c = i - r * d4;
-        act[0][r * lda + c] = (r < nrows && c < args.d_in) ? args.x[(row0 + r) * args.ldx + c] : 0.f;
-      }
-      if (tid < SS_ROWS) racc[tid] = args.acc_init;
-    }
+    if (tid < SS_ROWS) racc[tid] = args.acc_init;   // (its previous values were stored by these same threads)
     int cur = 0, hp = 0;
     for (int oi = 0; oi < args.n_ops; ++oi) {
       const SsOp& op = args.ops[oi];
-      const int N = op.N, K = op.K;
-      const int K4 = (K + 3) & ~3, ldw = K4 + 4, N16 = (N + 15) & ~15;
-      __syncthreads();   // previous layer: output complete, its weights no longer read
-      // stage this layer's weights (zero beyond N / K) and bias
-      for (int i = tid; i < N16 * (K4 >> 2); i += SS_THREADS) {
-        const int n = i / (K4 >> 2), k = (i - n * (K4 >> 2)) << 2;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < N) {
-          const float* src = op.W + (size_t)n * op.ldw + k;
-          if (k + 4 <= K && (op.ldw & 3) == 0) {
-            w = *reinterpret_cast<const float4*>(src);
-          } else {
-            w.x = k < K ? src[0] : 0.f;
-            w.y = k + 1 < K ? src[1] : 0.f;
-            w.z = k + 2 < K ? src[2] : 0.f;
-            w.w = k + 3 < K ? src[3] : 0.f;
-          }
+      cp_async_wait_all();
+      __syncthreads();   // this layer's weights (and, for the first layer, the tile's rows) have landed; the previous
+                         // layer's output is complete and its weights are no longer read
+      {
+        // next in line: the next layer of this tile, or the first layer + the input rows of this CTA's next tile
+        const bool last_op = oi + 1 == args.n_ops;
+        const int64_t next_tile = tile + gridDim.x;
+        if (!last_op) {
+          if (!args.resident) stage_op(args.ops[oi + 1], sbuf ? wb0 : wb1, sbuf ? bb0 : bb1, tid);
+        } else if (next_tile < n_tiles) {
+          if (!args.resident) stage_op(args.ops[0], sbuf ? wb0 : wb1, sbuf ? bb0 : bb1, tid);
+          stage_x(args, next_tile, xsel ? xb0 : xb1, tid);
         }
-        *reinterpret_cast<float4*>(wbuf + n * ldw + k) = w;
+        cp_async_commit();
       }
-      for (int i = tid; i < N16; i += SS_THREADS) bbuf[i] = (i < N && op.bias != nullptr) ? op.bias[i] : 0.f;
-      __syncthreads();
-
-      const float* in = (op.kind == SS_AFFINE || op.kind == SS_FINAL || op.first) ? act[cur] : hid[hp];
+      float* const actc = cur ? act1 : act0;
+      const int N = op.N, K4 = (op.K + 3) & ~3, ldw = K4 + 4, N16 = (N + 15) & ~15;
+      const float* wbuf = args.resident ? wb0 + op.woff : (sbuf ? wb1 : wb0);
+      const float* bbuf = args.resident ? wbuf + N16 * ldw : (sbuf ? bb1 : bb0);
+      const float* in;
+      int ldi = lda;
+      if (oi == 0) { in = xsel ? xb1 : xb0; ldi = args.ldxs; }
+      else if (op.kind == SS_AFFINE || op.kind == SS_FINAL || op.first) in = actc;
+      else { in = hp ? hid1 : hid0; ldi = ldh; }
       const int jn = N16 >> 4;   // 16-column groups of this layer (<= 8), uniform over the CTA
       float acc[4][8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-      const float* arow = in + (ty * 4) * lda;
+      const float* arow = in + (ty * 4) * ldi;
       const float* wrow = wbuf + tx * ldw;
       for (int k = 0; k < K4; k += 4) {
         float4 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * lda + k);
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * ldi + k);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j < jn) {
@@ -150,7 +233,9 @@ __global__ void __launch_bounds__(SS_THREADS) usf_small_stack_kernel(const __gri
       }
 
       if (op.kind == SS_AFFINE || op.kind == SS_HIDDEN) {
-        float* out = op.kind == SS_AFFINE ? act[cur ^ 1] : hid[op.first ? 0 : (hp ^ 1)];
+        // (the first layer of a stack without affine run would read the input buffer: the compiler always emits one)
+        float* out = op.kind == SS_AFFINE ? (cur ? act0 : act1) : ((op.first || hp) ? hid0 : hid1);
+        const int ldo = op.kind == SS_AFFINE ? lda : ldh;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j < jn) {
@@ -160,35 +245,37 @@ __global__ void __launch_bounds__(SS_THREADS) usf_small_stack_kernel(const __gri
             for (int i = 0; i < 4; ++i) {
               float v = acc[i][j] + b;
               if (op.kind == SS_HIDDEN) v = fmaxf(v, 0.f);
-              out[(ty * 4 + i) * lda + n] = v;
+              out[(ty * 4 + i) * ldo + n] = v;
             }
           }
         }
         if (op.kind == SS_AFFINE) cur ^= 1;
-        else hp = op.first ? 0 : (hp ^ 1);
+        else hp = (op.first || hp) ? 0 : 1;
       } else if (op.kind == SS_COUPLING) {
-        // affine: columns tx + 16 j, j < 4 are s of coordinate c = tx + 16 j and j + 4 its t; additive: all 8 are t
-        float* u_base = act[cur] + op.b_off;
+        // staged columns: [s of coordinates 0..Db16) | t of the same] (affine) or [t] (additive); this thread's
+        // coordinates are c = tx + 16 j
+        float* u_base = actc + op.b_off;
         float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-        const int jc = op.affine ? 4 : 8;
+        const int jh = op.affine ? (jn >> 1) : jn;    // column groups of one parameter
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < jc) {
+        for (int j = 0; j < 4; ++j) {
+          if (j < jh) {
             const int c = tx + 16 * j;
             if (c < op.Db) {
-              const float bs = op.affine ? bbuf[c] : 0.f;
-              const float bt = op.affine ? bbuf[64 + c] : bbuf[c];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float* up = u_base + (ty * 4 + i) * lda + c;
                 const float u = *up;
-                // (j + 4) & 7 keeps the index in range when this branch is compiled for the additive case
-                const float t = (op.affine ? acc[i][(j + 4) & 7] : acc[i][j]) + bt;
                 if (op.affine) {
-                  const float ls = op.clamp * tanhf(acc[i][j] + bs);
+                  // the shift of coordinate group j is accumulator group j + jh (jh = 1 .. 4)
+                  const float tj = jh == 1 ? acc[i][(j + 1) & 7]
+                                           : (jh == 2 ? acc[i][(j + 2) & 7] : (jh == 3 ? acc[i][(j + 3) & 7] : acc[i][(j + 4) & 7]));
+                  const float t = tj + bbuf[jh * 16 + c];
+                  const float ls = op.clamp * tanhf(acc[i][j] + bbuf[c]);
                   lsum[i] += ls;
                   *up = args.inverse ? (u - t) * expf(-ls) : fmaf(u, expf(ls), t);
                 } else {
+                  const float t = acc[i][j] + bbuf[c];
                   *up = args.inverse ? u - t : u + t;
                 }
               }
@@ -206,13 +293,11 @@ __global__ void __launch_bounds__(SS_THREADS) usf_small_stack_kernel(const __gri
       } else {  // SS_FINAL: natural column order, optional store, optional base log-density
         float lsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           if (j < jn) {
             const int n = tx + 16 * j;
             if (n < args.D) {
-              const float b = bbuf[n];
-              const float lc = args.base_kind >= 0 ? args.loc[n] : 0.f;
-              const float is = args.base_kind >= 0 ? args.inv_scale[n] : 0.f;
+              const float b = bbuf[n], lc = locs[n], is = iscs[n];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int r = ty * 4 + i;
@@ -232,13 +317,16 @@ __global__ void __launch_bounds__(SS_THREADS) usf_small_stack_kernel(const __gri
           }
         }
       }
+      sbuf ^= 1;
     }
+    xsel ^= 1;
     __syncthreads();
     if (tid < nrows) {
       if (args.out_lp != nullptr) args.out_lp[row0 + tid] = racc[tid];
       if (args.out_ladj != nullptr) args.out_ladj[row0 + tid] = racc[tid];
     }
   }
+  cp_async_wait_all();
 }
 
 bool small_enabled() {
@@ -250,40 +338,60 @@ bool small_enabled() {
 // Fills `a` from the descriptor; false when the stack is not one this kernel runs.
 bool build_args(const usf_stack_desc* st, SsArgs* a) {
   if (st == nullptr || st->D <= 0 || st->D + st->ctx_dim > 64 || st->n_blocks < 0) return false;
-  int n = 0, maxw = (st->D + st->ctx_dim + 3) & ~3, maxwb = 0;
-  auto push = [&](const usf_linear_desc& L, int N, int kind, int first, const usf_block_desc* blk) -> bool {
-    if (n >= SS_MAX_OPS || L.W == nullptr || N <= 0 || N > SS_MAXW || L.K <= 0 || L.K > SS_MAXW || L.ldw < L.K) return false;
+  int n = 0, maxa = 16, maxh = 16, maxwb = 0, total = 0;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // stored: 0 = the output stays in registers (coupling, final), 1 = activation buffer, 2 = hidden buffer;
+  // in_hidden: the layer reads the hidden buffer
+  auto push = [&](const usf_linear_desc& L, int N, int kind, int first, const usf_block_desc* blk, int stored, bool in_hidden) -> bool {
+    if (n >= SS_MAX_OPS || L.W == nullptr || !aligned(L.W) || (L.ldw & 3) != 0 || N <= 0 || N > SS_MAXW || L.K <= 0 ||
+        L.K > SS_MAXW || L.ldw < ((L.K + 3) & ~3))
+      return false;
     SsOp& o = a->ops[n++];
     o.W = L.W; o.bias = L.bias; o.N = N; o.K = L.K; o.ldw = L.ldw; o.kind = kind; o.first = first;
     o.b_off = blk ? blk->b_off : 0; o.Db = blk ? blk->Db : 0; o.affine = blk ? blk->affine : 0; o.clamp = blk ? blk->clamp : 0.f;
+    o.t_row = 64;
     const int n16 = (N + 15) & ~15, k4 = (L.K + 3) & ~3;
-    if (n16 > maxw) maxw = n16;
-    if (k4 > maxw) maxw = k4;
+    if (stored == 1 && n16 > maxa) maxa = n16;
+    if (stored == 2 && n16 > maxh) maxh = n16;
+    if (in_hidden) { if (k4 > maxh) maxh = k4; } else { if (k4 > maxa) maxa = k4; }
     if (n16 * (k4 + 4) > maxwb) maxwb = n16 * (k4 + 4);
+    o.woff = total;
+    total += n16 * (k4 + 4) + n16;
     return true;
   };
   for (int b = 0; b < st->n_blocks; ++b) {
     const usf_block_desc& blk = st->blocks[b];
     if (blk.n_mlp < 1 || blk.n_mlp > USF_MAX_MLP) return false;
-    if (!push(blk.G, blk.G.N, SS_AFFINE, 0, &blk)) return false;
-    if (blk.b_off + blk.Db > blk.G.N || blk.Db <= 0 || blk.mlp[0].K > blk.b_off) return false;
+    if (!push(blk.G, blk.G.N, SS_AFFINE, 0, &blk, 1, false)) return false;
+    if (blk.b_off + blk.Db > blk.G.N || blk.Db <= 0 || blk.Db > 64 || blk.mlp[0].K > blk.b_off) return false;
     for (int l = 0; l < blk.n_mlp; ++l) {
       const bool last = l == blk.n_mlp - 1;
-      // the coupling tile must be the single [s(64) | t(64)] / [t(128)] tile of the fp32 packing
-      if (last && (blk.mlp[l].N != 128 || blk.C != (blk.affine ? 64 : 128) || blk.Db > blk.C)) return false;
-      if (!push(blk.mlp[l], blk.mlp[l].N, last ? SS_COUPLING : SS_HIDDEN, l == 0 ? 1 : 0, &blk)) return false;
+      if (!last) {
+        if (!push(blk.mlp[l], blk.mlp[l].N, SS_HIDDEN, l == 0 ? 1 : 0, &blk, 2, l > 0)) return false;
+        continue;
+      }
+      // the coupling tile must be the single [s(64) | t(64)] / [t(128)] tile of the fp32 packing; only the
+      // round_up(Db, 16) columns of each parameter that carry coordinates are computed
+      if (blk.mlp[l].N != 128 || blk.C != (blk.affine ? 64 : 128)) return false;
+      const int db16 = (blk.Db + 15) & ~15;
+      if (!push(blk.mlp[l], blk.affine ? 2 * db16 : db16, SS_COUPLING, l == 0 ? 1 : 0, &blk, 0, l > 0)) return false;
     }
   }
   if (st->G_final.N < st->D) return false;
-  if (!push(st->G_final, st->D, SS_FINAL, 0, nullptr)) return false;
+  if (!push(st->G_final, st->D, SS_FINAL, 0, nullptr, 0, false)) return false;
   a->n_ops = n;
-  a->lda = maxw + 4;
-  a->wbuf_floats = (maxwb + 3) & ~3;
+  a->lda = maxa + 4;
+  a->ldh = maxh + 4;
+  a->ldxs = ((st->D + st->ctx_dim + 3) & ~3) + 4;
+  // all layers resident when they fit beside the row buffers (then no weight travels per row tile)
+  a->resident = (size_t)total * sizeof(float) <= 96 * 1024 ? 1 : 0;
+  a->wbuf_floats = a->resident ? ((total + 3) & ~3) : ((maxwb + 3) & ~3);
   return true;
 }
 
 size_t smem_bytes(const SsArgs& a) {
-  return sizeof(float) * ((size_t)4 * SS_ROWS * a.lda + a.wbuf_floats + SS_MAXW + SS_ROWS);
+  return sizeof(float) * ((size_t)2 * SS_ROWS * a.lda + (size_t)2 * SS_ROWS * a.ldh + (size_t)2 * SS_ROWS * a.ldxs +
+                          (size_t)(a.resident ? 1 : 2) * a.wbuf_floats + 2 * SS_MAXW + SS_ROWS + 128);
 }
 
 }  // namespace
@@ -291,7 +399,7 @@ size_t smem_bytes(const SsArgs& a) {
 bool small_stack_supported(const usf_stack_desc* st, int precision) {
   if (precision != USF_PREC_FP32 || !small_enabled()) return false;
   static thread_local SsArgs probe;
-  return build_args(st, &probe) && smem_bytes(probe) <= 220 * 1024;
+  return build_args(st, &probe) && smem_bytes(probe) <= 227 * 1024;
 }
 
 int small_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t B, float* out_logprob, float* out_y,
@@ -305,6 +413,7 @@ int small_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64
   a.B = B;
   a.x = x;
   a.ldx = ldx;
+  a.x_vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (a.d_in & 3) == 0) ? 1 : 0;
   a.out_lp = out_logprob;
   a.out_y = out_y;
   a.ldy = ldy;
@@ -313,10 +422,10 @@ int small_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64
   a.loc = st->loc;
   a.inv_scale = st->inv_scale;
   const size_t smem = smem_bytes(a);
-  static thread_local size_t attr_bytes = 0;
-  if (smem > 48 * 1024 && smem > attr_bytes) {
-    USF_CUDA(cudaFuncSetAttribute(usf_small_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    attr_bytes = 220 * 1024;
+  static thread_local bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    USF_CUDA(cudaFuncSetAttribute(usf_small_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    attr_set = true;
   }
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, usf_small_stack_kernel, SS_THREADS, smem) != cudaSuccess || per_sm < 1) {

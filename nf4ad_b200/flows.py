@@ -31,10 +31,14 @@ def _on_device(method):
 
     @functools.wraps(method)
     def wrapped(self, x=None, *args, **kwargs):
-        if isinstance(x, torch.Tensor) and x.is_cuda and x.device.index != torch.cuda.current_device():
-            with torch.cuda.device(x.device):
-                return method(self, x, *args, **kwargs)
-        return method(self, x, *args, **kwargs)
+        self.__dict__["_key_now"] = None          # the weights key is computed at most once per public call
+        try:
+            if isinstance(x, torch.Tensor) and x.is_cuda and x.device.index != torch.cuda.current_device():
+                with torch.cuda.device(x.device):
+                    return method(self, x, *args, **kwargs)
+            return method(self, x, *args, **kwargs)
+        finally:
+            self.__dict__["_key_now"] = False
     return wrapped
 
 
@@ -158,14 +162,21 @@ class Flow(torch.nn.Module):
         self._key_slots = None
         self.__dict__.pop("_ctx_dim", None)
         self.__dict__.pop("_tier_cache", None)
+        self.__dict__.pop("_small_cache", None)
 
     def _weights_key(self):
+        memo = self.__dict__.get("_key_now", False)
+        if memo:                         # inside one public call (log_prob / backward / latent_to_data): computed already
+            return memo
         slots = self.__dict__.get("_key_slots") or self._scan_key_slots()
         key = [_lib.weights_epoch()]     # raw-pointer / graph-replayed optimizer steps (optim.FusedAdam, DataParallelTrainer)
         for d, k in slots:
             t = d.get(k)
             key.append((id(t), t._version if t is not None else -1))
-        return tuple(key)
+        key = tuple(key)
+        if memo is None:
+            self.__dict__["_key_now"] = key
+        return key
 
     def train(self, mode: bool = True):
         if mode != self.training:
@@ -187,12 +198,33 @@ class Flow(torch.nn.Module):
     BF16_MIN_DIM = 128
     SMALL_MAX_DIM = 64
 
-    def _small_ok(self, device):
-        """Does the one-kernel path take this stack (both directions share the shapes)?"""
+    SMALL_ALWAYS = False        # (measurement switch: take the one-kernel path whenever the stack is eligible)
+
+    def _small_ok(self, device, rows=None):
+        """Does the one-kernel path take this stack (both directions share the shapes), and does it pay at this batch
+        size?  Measured against the 3xTF32 launch chain (scripts/bench_small.py, profiles/r2/small_stack.txt): one kernel
+        instead of 12 launches wins at every batch size while the layers are at most 32 wide (D = 6: 1.1-1.6x, D = 20:
+        1.0-1.7x) and up to ~8k rows for wider layers (D = 32 / 64 with 64-128 wide layers: 1.2-1.5x; at 65536 rows its
+        fp32 FFMA arithmetic, paced by shared-memory reads, loses 0.55-0.73x to the tensor-core chain)."""
         if self.event_dim + self.context_dim() > self.SMALL_MAX_DIM or len(self.event_shape) != 1:
             return False
-        cs = self._stack(True, device, "fp32")
-        return cs is not None and cs.single_kernel
+        key = self._weights_key()
+        hit = self.__dict__.get("_small_cache")
+        if hit is None or hit[0] != key:
+            cs = self._stack(True, device, "fp32")
+            if cs is None or not cs.single_kernel:
+                hit = (key, False, 0)
+            else:
+                widest = 0
+                for j in range(cs.desc.n_blocks):
+                    blk = cs.blocks[j]
+                    widest = max([widest, blk.G.N] + [blk.mlp[l].N for l in range(blk.n_mlp - 1)])
+                hit = (key, True, widest)
+            self.__dict__["_small_cache"] = hit
+        _, eligible, widest = hit
+        if not eligible:
+            return False
+        return rows is None or self.SMALL_ALWAYS or rows <= 8192 or widest <= 32
 
     def _tier(self, x2=None, context_rows=None):
         want = self.precision
@@ -203,15 +235,16 @@ class Flow(torch.nn.Module):
             self.effective_precision = want
             return want
         key = self._weights_key()
+        device = x2.device if x2 is not None else next(self.parameters()).device
+        if self._small_ok(device, None if x2 is None else x2.shape[0]):     # (depends on the batch size: not cached below)
+            self.effective_precision = "fp32"
+            return "fp32"
         hit = self.__dict__.get("_tier_cache")
         if hit is not None and hit[0] == (key, want) and (hit[2] or x2 is None):
             self.effective_precision = hit[1]
             return hit[1]
-        device = x2.device if x2 is not None else next(self.parameters()).device
         tier, calibrated, err = want, False, None
-        if self._small_ok(device):
-            tier, calibrated = "fp32", True
-        elif want == "tf32x3":
+        if want == "tf32x3":
             calibrated = True
         elif self.event_dim < self.BF16_MIN_DIM:
             tier, calibrated = "tf32x3", True

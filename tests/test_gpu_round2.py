@@ -381,5 +381,10 @@ def test_small_stack_single_kernel(O, P, cfg):
     with torch.no_grad():
         big = torch.randn(70000, D, generator=g).cuda()
         lp = fp.log_prob(big)
-        assert torch.equal(lp[12345:12400], fp.log_prob(big[12345:12400].contiguous()))
+        big_tier = fp.effective_precision        # wide layers at this batch size go to the 3xTF32 chain (Flow._small_ok)
+        part = fp.log_prob(big[12345:12400].contiguous())
+        if big_tier == "fp32":
+            assert fp.last_launches == 1 and torch.equal(lp[12345:12400], part)
+        else:
+            assert big_tier == "tf32x3" and float(lp_err(lp[12345:12400], part).max()) < 2e-4
         assert bool(torch.isfinite(lp).all())
