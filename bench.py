@@ -363,7 +363,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import nf4ad_b200
     from nf4ad_b200 import _lib
-    from nf4ad_b200.parallel import ShardedScorer
+    from nf4ad_b200.parallel import ShardedScorer, bind_to_gpu_numa
+    # multi-rank host: pin this rank to its GPU's NUMA node BEFORE the first host buffer exists (parallel.bind_to_gpu_numa)
+    numa = bind_to_gpu_numa(local, local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if world > 1 else {"bound": False}
     P = nf4ad_b200.namespace()
     flow = build_config_flow(P, args.config, dev)
     flow.precision = args.precision
@@ -676,7 +678,7 @@ def main():
                     "api": "ShardedScorer.predict_score_host(pinned fp32 rows): the ADBenchFlow.predict_score call sequence",
                     "host_input_bytes_per_step": B * D * 4,
                     "host_narrowing": bool(scorer.host_bf16 and eff == "bf16"),
-                    "host_threads": int(scorer.host_threads),
+                    "host_threads": int(scorer.host_threads), "numa": numa,
                     "fp32_head_rows": (scorer._tune.get((B, D), {}).get("best", None) if scorer.host_bf16 else None)},
             "e2e_pageable": {"value": B * world * args.steps / (pageable_ms * 1e-3), "unit": "samples/s",
                              "ms_per_step": pageable_ms / args.steps, "h2d_bytes_per_step": pageable_h2d,

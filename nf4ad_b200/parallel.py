@@ -44,6 +44,71 @@ def shared_permutation(n, device, generator, shuffle=True, group=None):
     return perm
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(index):
+    """NUMA node of the host memory closest to GPU `index` (sysfs), or None when the platform does not say."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(index, local_rank=0, local_world=1):
+    """Multi-rank hosts: every rank streams hundreds of MB per scoring call out of host DRAM (205 MB of fp32 rows per 65536 x
+    784 call), and a rank whose pinned staging buffers / input pages sit on the other socket pulls them across the
+    inter-socket link -- with 8 ranks on one host that, not PCIe, set the end-to-end rate in round 1 (21 GB/s per GPU at
+    N = 8, and N = 4 slower per GPU than N = 8).  Before it allocates any host buffer a rank therefore pins itself to the CPUs
+    of its GPU's NUMA node (first-touch then places its pages there), sharing them with the other local ranks of that node.
+    Returns a dict describing what was done (for the bench record); a no-op where sysfs does not expose the topology or
+    USF_NUMA_BIND=0."""
+    global _NUMA_DONE
+    if _NUMA_DONE is not None:          # once per process: a second call would split the already split CPU set again
+        return _NUMA_DONE
+    _NUMA_DONE = _bind_to_gpu_numa(index, local_rank, local_world)
+    return _NUMA_DONE
+
+
+_NUMA_DONE = None
+
+
+def _bind_to_gpu_numa(index, local_rank, local_world):
+    info = {"bound": False}
+    if os.environ.get("USF_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return info
+    node = gpu_numa_node(index)
+    if node is None:
+        return info
+    try:
+        node_cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0) & node_cpus
+        if len(allowed) < 2:
+            return dict(info, node=node, reason="fewer than 2 allowed CPUs on the GPU's node")
+        # the local ranks whose GPUs hang off the same node share its CPUs evenly
+        peers = [r for r in range(local_world) if gpu_numa_node(r) == node] or [local_rank]
+        mine = sorted(allowed)
+        if len(peers) > 1 and len(mine) >= 2 * len(peers):
+            k = peers.index(local_rank) if local_rank in peers else 0
+            per = len(mine) // len(peers)
+            mine = mine[k * per:(k + 1) * per]
+        os.sched_setaffinity(0, set(mine))
+        torch.set_num_threads(max(1, len(mine)))
+        return {"bound": True, "node": node, "cpus": len(mine), "peers_on_node": len(peers)}
+    except Exception as e:            # never fail a scoring call over a placement hint
+        return dict(info, node=node, reason=repr(e))
+
+
 def _world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -86,12 +151,18 @@ class ShardedScorer:
         # fp32, twice the PCIe rate, and the call gets 1.35x faster; with 8 threads the conversion is the bottleneck, and
         # two ranks with 12 threads each contend for host DRAM (5.3 vs 4.3 ms) -- so it is on by default only for a single
         # rank per host with >= 16 host threads (USF_HOST_BF16=1/0 forces it).
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self.numa = {"bound": False}
+        if local_world > 1 and torch.cuda.is_available():
+            # before any pinned buffer exists: this rank's host pages belong next to its GPU (bind_to_gpu_numa)
+            self.numa = bind_to_gpu_numa(torch.cuda.current_device(), int(os.environ.get("LOCAL_RANK", "0")), local_world)
         try:
             avail = len(os.sched_getaffinity(0))
         except AttributeError:
             avail = os.cpu_count() or 1
-        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-        self.host_threads = int(os.environ.get("USF_HOST_THREADS", "0")) or max(1, avail // local_world)
+        # after the binding the affinity mask IS this rank's share of the host
+        share = avail if self.numa.get("bound") else max(1, avail // local_world)
+        self.host_threads = int(os.environ.get("USF_HOST_THREADS", "0")) or share
         want = os.environ.get("USF_HOST_BF16")
         self.host_bf16 = score_fn is None and (want == "1" or (want is None and local_world == 1 and self.host_threads >= 16))
         # Pageable rows (the numpy arrays the reference's callers pass): always staged through the pinned ring by the host
@@ -261,9 +332,16 @@ class ShardedScorer:
 
 
 class DataParallelTrainer:
-    """Data-parallel NLL training step (`adbench_wrapper.py:375-392`): per-rank micro-batch,
-    gradients summed with ONE flat all-reduce and divided by the world size (loss is a per-rank mean),
-    global-norm clipping after the reduction, identical optimizer step on every rank.
+    """Data-parallel NLL training step (`adbench_wrapper.py:375-392`): per-rank micro-batch, gradients averaged over the
+    ranks (loss is a per-rank mean), global-norm clipping after the reduction, identical optimizer step on every rank.
+
+    Gradient exchange (world > 1).  Every parameter's `.grad` is a view into ONE persistent flat fp32 buffer laid out in
+    parameter order, so there is nothing to flatten, scale or copy back: NCCL averages (`ReduceOp.AVG`) the buffer in place,
+    in buckets of >= `USF_DP_BUCKET_MB` (default 8 MB).  The backward pass finishes the blocks of the stack in parameter
+    order (log_prob walks the layers last -> first, its backward first -> last), so a bucket is handed to NCCL on a side
+    stream the moment autograd has accumulated its last gradient (`register_post_accumulate_grad_hook`) and travels over
+    NVLink while the remaining blocks' backward kernels run; the step joins the side stream before clipping / the
+    optimizer.  All of it -- kernels, side-stream forks, collectives -- is captured in the step's CUDA graph.
 
     CUDA-graph replay.  At the reference's own batch sizes (32-64) the step is bound by the
     host: ~300 autograd nodes and kernel launches cost 5-16 ms per step while the kernels need a fraction of
@@ -295,6 +373,108 @@ class DataParallelTrainer:
         self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss, hyper-parameter signature]
         self.graph_replays = 0
         self.graph_error = None     # the exception that switched graph replay off, if any
+        self._flat = None
+        self._hooks = []
+        self.bucket_bytes = int(float(os.environ.get("USF_DP_BUCKET_MB", "8")) * (1 << 20))
+        self.overlap = os.environ.get("USF_DP_OVERLAP", "1") != "0"
+        if self.world > 1 and self.params:
+            self._setup_flat_gradients()
+
+    # ------------------------------------------------------------------ flat gradient buffer + bucketed exchange
+    def _setup_flat_gradients(self):
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self._flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._bucket_of, self._buckets = {}, []            # param id -> bucket; bucket = [start, end, n_params]
+        off, start, count = 0, 0, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            p.grad = self._flat[off:off + n].view_as(p)
+            self._bucket_of[id(p)] = len(self._buckets)
+            off += n
+            count += 1
+            if (off - start) * 4 >= self.bucket_bytes or i == len(self.params) - 1:
+                self._buckets.append([start, off, count])
+                start, count = off, 0
+        self._pending = [b[2] for b in self._buckets]
+        self._sent = [False] * len(self._buckets)
+        self._syncing = False
+        self._comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        self._nccl = dev.type == "cuda" and dist.get_backend(self.group) == "nccl"
+        if self.overlap:
+            self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def close(self):
+        """Detach the gradient hooks (a trainer lives for one `fit`; the flow outlives it)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _on_grad(self, p):
+        if not self._syncing:
+            return
+        b = self._bucket_of.get(id(p))
+        if b is None:
+            return
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._send_bucket(b)
+
+    def _send_bucket(self, b):
+        if self._sent[b]:
+            return
+        self._sent[b] = True
+        start, end, _ = self._buckets[b]
+        chunk = self._flat[start:end]
+        if self._comm_stream is not None:
+            cur = torch.cuda.current_stream(chunk.device)
+            self._comm_stream.wait_stream(cur)            # the gradients of this bucket are complete on `cur`
+            with torch.cuda.stream(self._comm_stream):
+                self._reduce(chunk)
+        else:
+            self._reduce(chunk)
+
+    def _reduce(self, chunk):
+        if self._nccl:
+            dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                              # gloo (CPU tests): no AVG
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.div_(self.world)
+
+    def _begin_sync(self):
+        """Zero the flat buffer (autograd accumulates into the views in place) and arm the bucket counters."""
+        self._flat.zero_()
+        for p, (s0, e0) in zip(self.params, self._param_ranges()):
+            if p.grad is None or p.grad.data_ptr() != self._flat.data_ptr() + 4 * s0:
+                p.grad = self._flat[s0:e0].view_as(p)      # someone set it to None / replaced it: re-attach the view
+        self._pending = [b[2] for b in self._buckets]
+        self._sent = [False] * len(self._buckets)
+        self._syncing = True
+
+    def _param_ranges(self):
+        r = self.__dict__.get("_ranges")
+        if r is None:
+            r, off = [], 0
+            for p in self.params:
+                r.append((off, off + p.numel()))
+                off += p.numel()
+            self._ranges = r
+        return r
+
+    def _finish_sync(self):
+        """Buckets whose parameters saw no gradient this step (or all of them, without the hooks) go out now, in order;
+        then the step joins the side stream."""
+        self._syncing = False
+        for b in range(len(self._buckets)):
+            self._send_bucket(b)
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self._flat.device).wait_stream(self._comm_stream)
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -304,14 +484,11 @@ class DataParallelTrainer:
                 dist.broadcast(b.data, src, group=self.group)
 
     def allreduce_gradients(self):
-        grads = [p.grad for p in self.params if p.grad is not None]
-        if self.world == 1 or not grads:
+        """Averages the gradients over the ranks (world > 1): sends whatever buckets the backward hooks have not sent yet
+        and waits for all of them."""
+        if self.world == 1 or self._flat is None:
             return
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(self.world)
-        for g, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(new)
+        self._finish_sync()
 
     def _clip(self):
         """Global-norm clipping (`adbench_wrapper.py:388-389`).  With `FusedAdam` the coefficient goes into the update
@@ -329,8 +506,14 @@ class DataParallelTrainer:
             self.opt.clip_coef = torch.ones((), device=grads[0].device, dtype=torch.float32)
         self.opt.clip_coef.copy_(coef)
 
+    def _zero_grad(self):
+        if self._flat is not None:
+            self._begin_sync()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+
     def _eager_step(self, batch):
-        self.opt.zero_grad(set_to_none=True)
+        self._zero_grad()
         loss = self.loss_fn(batch)
         loss.backward()
         self.allreduce_gradients()
@@ -342,9 +525,12 @@ class DataParallelTrainer:
     def _capture(self, batch):
         static_x = batch.detach().clone()
         graph = torch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
+        if self._flat is None:
+            self.opt.zero_grad(set_to_none=True)
         # thread_local: NCCL's watchdog thread may query events while this thread captures
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            if self._flat is not None:
+                self._begin_sync()          # the memset of the flat gradient buffer is part of the replayed step
             loss = self.loss_fn(static_x)
             loss.backward()
             self.allreduce_gradients()

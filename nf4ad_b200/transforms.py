@@ -159,7 +159,9 @@ class LUTransform(BaseTransform):
                 torch.cuda.current_stream(y2.device).wait_stream(side)
             else:
                 A = ops.LUInverseFn.apply(self.L_raw, self.U_raw)
-            x = ops.linear_fn(y2, A, -(A @ self.bias), False)
+            # the shift -A b through the library's own GEMM (a 1 x D x D product; no cuBLAS call on the training path)
+            shift = ops.LinearFn.apply(self.bias.unsqueeze(0), A, None, False).squeeze(0)
+            x = ops.linear_fn(y2, A, -shift, False)
         else:
             x = ops.LUSolveFn.apply(y2, self.L_raw, self.U_raw, self.bias)
         return _restore(x, squeeze)

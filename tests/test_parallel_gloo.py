@@ -48,17 +48,47 @@ def _worker(rank, world, port, tmp):
         # ---- data-parallel step == single-process step on the concatenated batch
         import copy
         single = copy.deepcopy(flow)
-        opt_s = torch.optim.SGD(single.parameters(), lr=1e-2)
+        opt_s = torch.optim.SGD(single.parameters(), lr=1e-5)
         opt_s.zero_grad()
         (-single.log_prob(X[:64]).mean()).backward()
         opt_s.step()
-        opt = torch.optim.SGD(flow.parameters(), lr=1e-2)
+        opt = torch.optim.SGD(flow.parameters(), lr=1e-5)
+        os.environ["USF_DP_BUCKET_MB"] = "0.0002"          # ~50 floats per bucket: many buckets, sent from the hooks
         tr = DataParallelTrainer(flow, opt)
+        assert len(tr._buckets) > 3 and tr._buckets[0][0] == 0 and tr._buckets[-1][1] == tr._flat.numel()
+        assert all(a[1] == b[0] for a, b in zip(tr._buckets, tr._buckets[1:]))
         tr.broadcast_parameters()
         lo, hi = (0, 32) if rank == 0 else (32, 64)
         tr.step(X[lo:hi])
+        assert all(tr._sent) and not tr._syncing
         for (n, a), (_, b) in zip(flow.named_parameters(), single.named_parameters()):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), n
+        # every .grad is a view into the one flat buffer (nothing to flatten / copy back), and a second step with the
+        # hooks switched off (all buckets sent after backward) gives the same update as the single process
+        base = tr._flat.data_ptr()
+        off = 0
+        for p in tr.params:
+            assert p.grad.data_ptr() == base + 4 * off and p.grad.shape == p.shape
+            off += p.numel()
+        tr.close()
+        os.environ["USF_DP_OVERLAP"] = "0"
+        tr2 = DataParallelTrainer(flow, opt)
+        assert not tr2._hooks
+        opt_s.zero_grad()
+        (-single.log_prob(X[:64]).mean()).backward()
+        opt_s.step()
+        tr2.step(X[lo:hi])
+        for (n, a), (_, b) in zip(flow.named_parameters(), single.named_parameters()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (n, float((a - b).abs().max()), float(b.abs().max()))
+        # rank-sharded batches of `fit`: both ranks' shards of one global batch make the single-process batch
+        from nf4ad_b200.parallel import rank_batches, shared_permutation
+        perm = shared_permutation(101, "cpu", torch.Generator().manual_seed(5 + rank))     # rank 0's draw wins
+        mine = list(rank_batches(perm, 32, rank, world))
+        gathered = [None, None]
+        dist.all_gather_object(gathered, [b.tolist() for b in mine])
+        for step in range(len(mine)):
+            glob = gathered[0][step] + gathered[1][step]
+            assert glob == perm[step * 32: step * 32 + len(glob)].tolist()
         if rank == 0:
             open(tmp, "w").write("ok")
     finally:
