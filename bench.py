@@ -315,6 +315,10 @@ def main():
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the batch-size sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # a run that stops making progress (a collective waiting for a rank that died, a hung teardown) must not sit on the
+    # GPUs: after USF_BENCH_TIMEOUT_S seconds every thread's stack goes to stderr and the process exits non-zero
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("USF_BENCH_TIMEOUT_S", "1500")), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -532,15 +536,19 @@ def main():
                 f_ = build_config_flow(P, name, dev)
                 f_.precision = args.precision
                 xs = torch.randn(ROWS_PER_GPU, d_, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
-                for _ in range(5):
-                    f_.log_prob(xs)
-                torch.cuda.synchronize()
+                # warm-up with the call pattern of the timed steps (the result of the previous step is still alive when the
+                # next one allocates its output: two alternating output buffers = two launch-chain graphs to capture)
+                timed_steps_with_flush(lambda: f_.log_prob(xs), 8, dev)
+                g0 = (ctypes.c_longlong * 4)()
+                _lib.lib().usf_debug_graph_stats(g0, None, 0)
                 ms_c, _ = timed_steps_with_flush(lambda: f_.log_prob(xs), 20, dev)
+                g1 = (ctypes.c_longlong * 4)()
+                _lib.lib().usf_debug_graph_stats(g1, None, 0)
                 times[i] = ms_c / 20
                 cs_ = f_._stack(True, dev, f_.effective_precision)
                 fl_ = cs_.flops_per_row() if cs_ is not None else {}
                 meta.append((f_.last_launches, f_.effective_precision, sum(v[1] for v in fl_.values()),
-                             sum(v[0] for v in fl_.values())))
+                             sum(v[0] for v in fl_.values()), int(g1[0] - g0[0]), int(g1[3] - g0[3])))
                 del f_, xs, cs_
         if world > 1:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -549,9 +557,10 @@ def main():
         for i, name in enumerate(names):
             kind_, d_, k_, cond_, base_, gain_, kw_, alg_, bound_ = CONFIGS[name]
             ms_c = float(times[i])
-            launches_, eff_, useful_, executed_ = meta[i]
+            launches_, eff_, useful_, executed_, replays_, eager_ = meta[i]
             entry = {"value": ROWS_PER_GPU * world / (ms_c * 1e-3), "unit": "samples/s", "ms_per_step": ms_c,
                      "rows_per_gpu": ROWS_PER_GPU, "launches_per_step": launches_, "effective_precision": eff_,
+                     "graph_replays_of_20": replays_, "eager_chains_of_20": eager_,
                      "alg_mflop_per_sample": alg_, "bound": bound_}
             if bound_ == "tensor":
                 ach = useful_ * ROWS_PER_GPU / (ms_c * 1e-3) / 1e12
@@ -738,9 +747,16 @@ def main():
                 ref = fo.log_prob(x_host[:256].double())
                 got = flow.log_prob(x[:256]).double().cpu()
             line["cpu_baseline"]["gpu_vs_oracle_fp64_max_rel_err"] = float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max())
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # every rank has contributed to the line above (the max-over-ranks all_reduce); leave together, and leave through
+        # os._exit: interpreter teardown with CUDA graphs that hold NCCL kernels alive next to a destroyed process group
+        # hung a 2-GPU run of this file once (the line was printed, the processes never exited)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
