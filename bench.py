@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32x3", "fp32", "auto"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x2", "tf32x3", "fp32", "auto"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm-s", type=float, default=1.0, help="untimed clock pre-warm (0 for profiler runs)")
@@ -460,6 +460,22 @@ def main():
         barrier()
         e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0)
 
+        # ---- what the link alone allows: the same pinned rows copied to the device, nothing else (all ranks at once).  When
+        # this is as slow as the end-to-end call, the call is bound by the host -> device feed (PCIe / host DRAM shared by
+        # the ranks of one host), not by the scoring pipeline.
+        x_land = torch.empty_like(x)
+        for _ in range(2):
+            x_land.copy_(x_host, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(args.steps):
+            x_land.copy_(x_host, non_blocking=True)
+        c1.record()
+        barrier()
+        h2d_only_ms = c0.elapsed_time(c1)
+        del x_land
+
         # ---- the same call as the reference's callers make it: a PAGEABLE numpy array through
         # ADBenchFlow.predict_score (adbench_wrapper.py:406-433: torch.FloatTensor(X).to(device) ... .cpu().numpy());
         # host wall clock around the blocking calls (the result is a host array)
@@ -499,7 +515,8 @@ def main():
     if rank == 0 and args.sweep:
         with torch.no_grad():
             for rows_s in (64, 1024, 16384, 262144):
-                for prec in ("bf16", "tf32x3", "fp32"):
+                for prec in ("bf16", "bf16x2", "tf32x3", "fp32"):
+                    # bf16x2 = what the default precision ("auto") runs for D >= 128; fp32 FFMA only at small sizes
                     if (prec == "fp32" and rows_s > 16384) or (prec == "tf32x3" and rows_s < 16384):
                         continue
                     flow.precision = prec
@@ -607,10 +624,10 @@ def main():
                 train32_ms = g0.elapsed_time(g1)
             assert bool(torch.isfinite(loss))
             del tflow, opt, trainer
-    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms = (float(v) for v in t)
+    ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms = (float(v) for v in t)
 
     if rank == 0:
         steps_prof = 3
@@ -628,14 +645,13 @@ def main():
                     5: "fused_conditioner+coupling", 6: "whole_stack_kernel"}
         eff, fpr = eff_main, fpr_main
         dram, dram_src = ncu_dram_bytes()
-        kernel_of = {"affine_gemm": "usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"),
-                     "final_gemm+base": "usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"),
-                     "conditioner+coupling": "usf_tc_mlp_coupling_kernel" if 5 in per_tag else
-                                             ("usf_tc_gemm_kernel" if eff == "bf16" else ("usf_tc3_gemm_kernel" if eff == "tf32x3" else "usf_simt_gemm_kernel"))}
+        gemm_name = {"bf16": "usf_tc_gemm_kernel", "tf32x3": "usf_tc3_gemm_kernel", "bf16x2": "usf_tcb2_gemm_kernel",
+                     "fp32": "usf_simt_gemm_kernel"}[eff]
+        kernel_of = {"affine_gemm": gemm_name, "final_gemm+base": gemm_name,
+                     "conditioner+coupling": "usf_tc_mlp_coupling_kernel" if 5 in per_tag else gemm_name}
         by_kind, kind_ms = {}, {}
         for tg, v in per_tag.items():
             kind_ms.setdefault(tag_kind[tg], []).extend(v)
-        tc_peak = peak if eff == "bf16" else (peak / 6.0 if eff == "tf32x3" else None)
         for kind, v in kind_ms.items():
             n_launch = len(v) / steps_prof
             avg_ms = sum(v) / len(v)
@@ -678,7 +694,8 @@ def main():
             "metric": "log_prob samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3 (fp32 operands as hi+lo on tcgen05)", "fp32": "f32"}[eff],
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3 (fp32 operands as hi+lo on tcgen05)", "fp32": "f32",
+                      "bf16x2": "bf16x2 (bf16 hi+lo operand pairs on tcgen05, fp32-grade)"}[eff],
             "requested_precision": args.precision, "effective_precision": eff,
             "bf16_calibration_err": cal_err, "data": "synthetic", "config": config,
             "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms, "graph": graph_info,
@@ -686,6 +703,10 @@ def main():
                     "d2h_bytes_per_step": B * 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "ShardedScorer.predict_score_host(pinned fp32 rows): the ADBenchFlow.predict_score call sequence",
                     "host_input_bytes_per_step": B * D * 4,
+                    "h2d_copy_only": {"ms_per_step": h2d_only_ms / args.steps,
+                                      "gbs_per_gpu": B * D * 4 / (h2d_only_ms / args.steps * 1e-3) / 1e9,
+                                      "note": "the same pinned fp32 rows copied to the device and nothing else, all ranks "
+                                              "at once: the floor the host -> device feed sets for one call"},
                     "host_narrowing": bool(scorer.host_bf16 and eff == "bf16"),
                     "host_threads": int(scorer.host_threads), "numa": numa,
                     "fp32_head_rows": (scorer._tune.get((B, D), {}).get("best", None) if scorer.host_bf16 else None)},
@@ -703,7 +724,8 @@ def main():
                          "unit": "GB/s" if dk.get("bound") == "hbm" else "TFLOP/s", "frac": dk["frac"],
                          "flop_basis": "executed useful FLOPs of this kernel per launch (GEMM shapes of the packed descriptors "
                                        "without tile padding) / its mean CUDA-event time",
-                         "peak_source": peak_src + (" -- bf16 figure; this run executed 3xTF32 MMAs (1/6 of it)" if eff == "tf32x3" else ""),
+                         "peak_source": peak_src + {"tf32x3": " -- bf16 figure; this run executed 3xTF32 MMAs (1/6 of it)",
+                                                    "bf16x2": " -- bf16 figure; this run executed 3 bf16 MMAs per product (1/3 of it)"}.get(eff, ""),
                          "traffic": dram.get(dominant), "traffic_source": dram_src,
                          "by_kind": by_kind,
                          "step": {"flop_useful_per_sample": useful_per_row, "flop_executed_padded_per_sample": exec_per_row,

@@ -204,6 +204,10 @@ int usf_pack_matrix(const float* src, int64_t lds, const int32_t* row_idx, const
 #define USF_PREC_TF32X3 2 /* tcgen05 3xTF32 GEMMs (fp32 operands as hi + lo parts), fp32 activations: the <= 1e-4 tier on
                              tensor cores.  usf_linear_desc.W then holds 2N rows: the N fp32 rows followed by their N
                              low-part rows (W - tf32(W)); tile geometry (C) as for USF_PREC_BF16; every N <= 1024 */
+#define USF_PREC_BF16X2 3 /* tcgen05 bf16 GEMMs on (hi, lo) bf16 operand pairs, 3 MMAs per K step (16 mantissa bits per
+                             operand): the <= 1e-4 tier at a third of the bf16 rate -- twice the 3xTF32 rate on half its
+                             operand bytes.  usf_linear_desc.Wb then holds 2N rows: the N bf16 rows followed by their N
+                             low-part rows bf16(W - hi); activations travel as two bf16 buffers; every N <= 1024 */
 
 #define USF_MAX_MLP 8
 

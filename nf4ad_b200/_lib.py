@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libusflow_b200.so")
 USF_PREC_FP32 = 0
 USF_PREC_BF16 = 1
 USF_PREC_TF32X3 = 2
+USF_PREC_BF16X2 = 3
 USF_MAX_MLP = 8
 
 _i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t

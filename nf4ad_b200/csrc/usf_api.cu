@@ -80,8 +80,8 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan* p) {
   USF_CHECK_ARG(st != nullptr && st->D > 0 && st->n_blocks >= 0 && st->ctx_dim >= 0, "stack: bad descriptor");
   USF_CHECK_ARG(st->n_blocks == 0 || st->blocks != nullptr, "stack: blocks pointer is null");
-  USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16 || precision == USF_PREC_TF32X3,
-                "stack: unknown precision %d", precision);
+  USF_CHECK_ARG(precision == USF_PREC_FP32 || precision == USF_PREC_BF16 || precision == USF_PREC_TF32X3 ||
+                    precision == USF_PREC_BF16X2, "stack: unknown precision %d", precision);
   int64_t wmax = st->D + st->ctx_dim, hmax = 16, nmax = st->G_final.N;
   for (int b = 0; b < st->n_blocks; ++b) {
     const usf_block_desc& blk = st->blocks[b];
@@ -95,15 +95,15 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
     }
   }
   if (st->G_final.K > wmax) wmax = st->G_final.K;
-  const size_t esz = precision == USF_PREC_BF16 ? 2 : 4;
+  const size_t esz = (precision == USF_PREC_BF16 || precision == USF_PREC_BF16X2) ? 2 : 4;
   p->ld_act = round_up(wmax, 16);
   p->ld_hid = round_up(hmax, 16);
   p->act_bytes = align256((size_t)rows * p->ld_act * esz);
   p->hid_bytes = align256((size_t)rows * p->ld_hid * esz);
   p->acc_bytes = align256((size_t)rows * sizeof(float));
   p->small_bytes = (precision == USF_PREC_FP32 && rows <= kSmallRows) ? align256((size_t)rows * (size_t)nmax * sizeof(float)) : 0;
-  // 3xTF32: every activation buffer has a low-part twin
-  const size_t twins = precision == USF_PREC_TF32X3 ? 2 : 1;
+  // 3xTF32 / bf16x2: every activation buffer has a low-part twin
+  const size_t twins = (precision == USF_PREC_TF32X3 || precision == USF_PREC_BF16X2) ? 2 : 1;
   p->total = twins * (2 * p->act_bytes + 2 * p->hid_bytes) + p->acc_bytes + p->small_bytes + 256;
   return USF_OK;
 }
@@ -243,18 +243,19 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
   }
   cudaStream_t s = as_stream(stream);
   const bool bf16 = precision == USF_PREC_BF16;
-  const size_t esz = bf16 ? 2 : 4;
+  const bool b2 = precision == USF_PREC_BF16X2;      // bf16 (hi, lo) operand pairs
+  const size_t esz = (bf16 || b2) ? 2 : 4;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   uint8_t* act[2] = {base, base + p.act_bytes};
   uint8_t* hid[2] = {base + 2 * p.act_bytes, base + 2 * p.act_bytes + p.hid_bytes};
   float* small = p.small_bytes ? reinterpret_cast<float*>(base + 2 * p.act_bytes + 2 * p.hid_bytes + p.acc_bytes) : nullptr;
   const bool t3 = precision == USF_PREC_TF32X3;
-  // low-part twins of the activation / hidden buffers (3xTF32 only), placed after the accumulator region
+  // low-part twins of the activation / hidden buffers (3xTF32 / bf16x2), placed after the accumulator region
   uint8_t* lo_base = base + 2 * p.act_bytes + 2 * p.hid_bytes + p.acc_bytes + p.small_bytes;
   uint8_t* act_lo[2] = {lo_base, lo_base + p.act_bytes};
   uint8_t* hid_lo[2] = {lo_base + 2 * p.act_bytes, lo_base + 2 * p.act_bytes + p.hid_bytes};
   auto lo_of = [&](const void* hi) -> float* {   // the twin of one of the four hi buffers (or of a pointer into it)
-    if (!t3) return nullptr;
+    if (!t3 && !b2) return nullptr;
     const uint8_t* h = reinterpret_cast<const uint8_t*>(hi);
     return reinterpret_cast<float*>(lo_base + (h - base));
   };
@@ -275,6 +276,16 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       USF_CHECK_ARG(L.Wb != nullptr, "usf_stack_run: bf16 weights missing in descriptor");
       next_order();
       return tc_gemm(reinterpret_cast<const uint16_t*>(A), lda, L.Wb, L.ldw, rows, L.N, L.K, bn, ep, s);
+    }
+    if (b2) {
+      USF_CHECK_ARG(L.Wb != nullptr, "usf_stack_run: bf16 (hi, lo) weights missing in descriptor");
+      const uint16_t* Ab = reinterpret_cast<const uint16_t*>(A);
+      uint16_t* ub_lo = ep.ub != nullptr ? reinterpret_cast<uint16_t*>(lo_of(ep.ub)) : nullptr;
+      uint16_t* out_lo = (ep.out != nullptr && (ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) &&
+                          reinterpret_cast<uint8_t*>(ep.out) >= base && reinterpret_cast<uint8_t*>(ep.out) < lo_base)
+                             ? reinterpret_cast<uint16_t*>(lo_of(ep.out)) : nullptr;
+      return tcb2_gemm(Ab, reinterpret_cast<const uint16_t*>(lo_of(Ab)), lda, L.Wb, L.Wb + (size_t)L.N * (size_t)L.ldw, L.ldw,
+                       rows, L.N, L.K, bn, ep, out_lo, ub_lo, s);
     }
     USF_CHECK_ARG(L.W != nullptr, "usf_stack_run: fp32 weights missing in descriptor");
     if (t3) {
@@ -301,7 +312,10 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
     flip = 1;
     {
       ProfScope ps(s, 0);
-      if (x_bf16)
+      if (b2)
+        rc = launch_split_rows_bf16x2(x + r0 * ldx, ldx, reinterpret_cast<uint16_t*>(act[0]),
+                                      reinterpret_cast<uint16_t*>(lo_of(act[0])), p.ld_act, rows, d_in, row_acc, acc_init, s);
+      else if (x_bf16)
         rc = launch_copy_rows_bf16(reinterpret_cast<const uint16_t*>(x) + r0 * ldx, ldx, reinterpret_cast<uint16_t*>(act[0]),
                                    p.ld_act, rows, d_in, row_acc, acc_init, s);
       else
@@ -327,10 +341,10 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
         ep.bias = blk.G.bias;
         ep.out = act[cur ^ 1];
         ep.ldo = p.ld_act;
-        ep.out_bf16 = bf16;
+        ep.out_bf16 = bf16 || b2;
         {
           ProfScope ps(s, 1);
-          rc = gemm(act[cur], p.ld_act, blk.G, (bf16 || t3) ? tc_pick_bn(blk.G.N) : 0, ep, rows);
+          rc = gemm(act[cur], p.ld_act, blk.G, (bf16 || t3 || b2) ? tc_pick_bn(blk.G.N) : 0, ep, rows);
         }
         if (rc) return rc;
         ++launches;
@@ -382,19 +396,19 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.mode = EPI_BIAS_RELU;
           ep.out = hid[l & 1];
           ep.ldo = p.ld_hid;
-          ep.out_bf16 = bf16;
-          if (bf16 || t3) bn = tc_pick_bn(L.N);
+          ep.out_bf16 = bf16 || b2;
+          if (bf16 || t3 || b2) bn = tc_pick_bn(L.N);
         } else {
           if (blk.affine) ep.mode = st->inverse ? EPI_COUPLING_INV : EPI_COUPLING_FWD;
           else ep.mode = st->inverse ? EPI_ADD_INV : EPI_ADD_FWD;
           ep.ub = act[cur] + (size_t)blk.b_off * esz;
           ep.ldub = p.ld_act;
-          ep.ub_bf16 = bf16;
+          ep.ub_bf16 = bf16 || b2;
           ep.Db = blk.Db;
           ep.C = blk.C;
           ep.clamp = blk.clamp;
           ep.row_acc = row_acc;
-          if (bf16 || t3) bn = blk.affine ? 2 * blk.C : blk.C;
+          if (bf16 || t3 || b2) bn = blk.affine ? 2 * blk.C : blk.C;
         }
         {
           ProfScope ps(s, l + 1 < blk.n_mlp ? 2 : 3);
@@ -425,10 +439,10 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
       }
       // fp32 path: the SIMT kernel stores exactly N = D columns
       usf_linear_desc Lf = st->G_final;
-      if (!bf16 && !t3) Lf.N = st->D;
+      if (!bf16 && !t3 && !b2) Lf.N = st->D;
       {
         ProfScope ps(s, 4);
-        rc = gemm(act[cur], p.ld_act, Lf, (bf16 || t3) ? tc_pick_bn(Lf.N) : 0, ep, rows);
+        rc = gemm(act[cur], p.ld_act, Lf, (bf16 || t3 || b2) ? tc_pick_bn(Lf.N) : 0, ep, rows);
       }
       if (rc) return rc;
       ++launches;

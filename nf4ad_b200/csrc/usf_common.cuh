@@ -94,6 +94,11 @@ void tc_set_tile_order(int reverse);   // tile walk of the next tcgen05 launches
 // 3xTF32 GEMM (fp32 operands as hi + lo parts, fp32-grade accuracy on the tensor cores), see usf_tc3_gemm_kernel
 int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, const float* Wlo, int64_t ldw, int64_t M,
              int64_t N, int64_t K, int bn, const EpiParams& ep, float* out_lo, float* ub_lo, cudaStream_t stream);
+// bf16x2 GEMM (operands as bf16 hi + lo pairs: fp32-grade at a third of the bf16 rate), see usf_tcb2_gemm_kernel
+int tcb2_gemm(const uint16_t* A, const uint16_t* Alo, int64_t lda, const uint16_t* W, const uint16_t* Wlo, int64_t ldw, int64_t M,
+              int64_t N, int64_t K, int bn, const EpiParams& ep, uint16_t* out_lo, uint16_t* ub_lo, cudaStream_t stream);
+int launch_split_rows_bf16x2(const float* x, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldy, int64_t B, int64_t D,
+                             float* row_init, float init_value, cudaStream_t stream);
 // hi == NULL: lo against the truncated read of x; hi != NULL (may alias x): hi = x rounded to tf32, lo = x - hi
 int launch_split_lo(const float* x, int64_t ldx, float* hi, float* lo, int64_t ldl, int64_t rows, int64_t cols, cudaStream_t stream);
 bool tc_mlp_supported(int n_layers, const int* N, const int* K, int Da);

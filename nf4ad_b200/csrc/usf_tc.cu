@@ -1487,6 +1487,313 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ================================================================================================
+// bf16x2 GEMM: fp32-grade accuracy at the bf16 tensor-core rate / 3 (twice the 3xTF32 rate, half its operand bytes).
+// Every operand is a pair of bf16 values hi + lo, hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits together.
+//     a w ~= a_hi w_hi + a_hi w_lo + a_lo w_hi           (the dropped a_lo w_lo term is ~2^-16 relative)
+// three tcgen05.mma.kind::f16 per K=16 step into one fp32 TMEM accumulator; same CTA-pair pipeline as the 3xTF32 kernel
+// (a stage = [A_hi | A_lo | W_hi | W_lo] of one 64-column k-block); epilogues write (hi, lo) bf16 pairs for the next GEMM.
+// ================================================================================================
+struct Tcb2Args {
+  int64_t M, N, K;
+  int bn, n_tiles, m_tiles, n_valid, stages;
+  uint32_t stage_bytes, w_bytes;
+  uint32_t backoff_ns;
+  EpiParams ep;
+  uint16_t* out_lo;   // EPI_BIAS*: low part of the bf16 output (same leading dimension as ep.out); NULL: fp32 output
+  uint16_t* ub_lo;    // coupling modes: low part of the transformed columns
+};
+
+// (a, b) -> packed bf16x2 of the high parts and of the low parts
+__device__ __forceinline__ void split_bf16x2_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+usf_tcb2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, Tcb2Args args) {
+  const int STAGES = args.stages;
+  const uint32_t STAGE_BYTES = args.stage_bytes;
+  extern __shared__ uint8_t smem_raw[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), num_units = (int)(gridDim.x >> 1);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t epi_base = bar_base + TC_BAR_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int total_tiles = args.m_tiles * args.n_tiles;
+  const int num_kb = (int)((args.K + TC_BK - 1) / TC_BK);
+  const uint32_t w_rows_bytes = (uint32_t)(args.bn >> 1) * 128u;
+  const uint32_t stage_tx = 2u * (2u * TC_A_BYTES + 2u * w_rows_bytes);
+  const uint32_t off_alo = TC_A_BYTES, off_w = 2u * TC_A_BYTES, off_wlo = 2u * TC_A_BYTES + args.w_bytes;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int t = unit; t < total_tiles && ok; t += num_units) {
+      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      int width = (int)(args.N - (int64_t)nt * args.bn);
+      if (width > args.bn) width = args.bn;
+      const int w_row = nt * args.bn + (int)cta_rank * (width >> 1);
+      const int a_row = (mt * 2 + (int)cta_rank) * TC_BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ok = mbar_wait(empty_bar(s), ph ^ 1u, args.backoff_ns);
+        if (!ok) break;
+        const uint32_t dst = smem_base + s * STAGE_BYTES;
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+          tma_load_2d_2sm(dst, &tmA, full_bar(s), kb * TC_BK, a_row);
+          tma_load_2d_2sm(dst + off_alo, &tmAlo, full_bar(s), kb * TC_BK, a_row);
+          tma_load_2d_2sm(dst + off_w, &tmW, full_bar(s), kb * TC_BK, w_row);
+          tma_load_2d_2sm(dst + off_wlo, &tmWlo, full_bar(s), kb * TC_BK, w_row);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta_rank == 0) {
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      bool ok = true;
+      const int tail_steps = ((int)args.K - (num_kb - 1) * TC_BK + TC_UMMA_K - 1) / TC_UMMA_K;
+      const uint64_t desc_hi = make_smem_desc(0);
+      const uint32_t lo0 = (smem_base & 0x3FFFFu) >> 4, stage16 = STAGE_BYTES >> 4;
+      for (int t = unit; t < total_tiles && ok; t += num_units) {
+        const int nt = t % args.n_tiles;
+        int width = (int)(args.N - (int64_t)nt * args.bn);
+        if (width > args.bn) width = args.bn;
+        const uint32_t idesc = make_idesc((uint32_t)width, 2 * TC_BM);
+        ok = mbar_wait(tempty_bar(a), aph ^ 1u);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAX_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ok = mbar_wait(full_bar(s), ph);
+          if (!ok) break;
+          if (elect_one()) {
+            const uint64_t ah = desc_hi | (uint64_t)(lo0 + (uint32_t)s * stage16);
+            const uint64_t al = ah + (off_alo >> 4), wh = ah + (off_w >> 4), wl = ah + (off_wlo >> 4);
+            const int ksteps = kb + 1 < num_kb ? TC_BK / TC_UMMA_K : tail_steps;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16_2sm(d_tmem, ah + 2u * k, wh + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, ah + 2u * k, wl + 2u * k, idesc, 1u);
+              umma_bf16_2sm(d_tmem, al + 2u * k, wh + 2u * k, idesc, 1u);
+            }
+            umma_commit_2sm(empty_bar(s));
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        if (elect_one()) umma_commit_2sm(tfull_bar(a));
+        a ^= 1;
+        if (a == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;
+    const EpiParams& ep = args.ep;
+    float* epi = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));
+    const int mode = ep.mode;
+    const bool is_cpl = mode == EPI_COUPLING_INV || mode == EPI_COUPLING_FWD;
+    const bool is_add = mode == EPI_ADD_INV || mode == EPI_ADD_FWD;
+    const bool is_base = mode == EPI_BASE_NORMAL || mode == EPI_BASE_LAPLACE;
+    // column vectors resident for the whole kernel (host guarantees N <= TC_EPI_COLS)
+    for (int i = et; i < (int)args.N; i += 256) {
+      epi[i] = ep.bias != nullptr ? ep.bias[i] : 0.f;
+      if (is_base) {
+        const bool v2 = i < args.n_valid && ep.loc != nullptr;
+        epi[TC_EPI_COLS + i] = v2 ? ep.loc[i] : 0.f;
+        epi[2 * TC_EPI_COLS + i] = v2 ? ep.inv_scale[i] : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int a = 0;
+    uint32_t aph = 0;
+    for (int t = unit; t < total_tiles; t += num_units) {
+      const int mt = t / args.n_tiles, nt = t - mt * args.n_tiles;
+      const int64_t row = (int64_t)(mt * 2 + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
+      const bool rvalid = row < args.M;
+      const int64_t n0 = (int64_t)nt * args.bn;
+      int width = (int)(args.N - n0);
+      if (width > args.bn) width = args.bn;
+      const float* ev = epi + n0;
+      const bool ok = mbar_wait(tfull_bar(a), aph, args.backoff_ns);
+      if (ok) {
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+        if (mode == EPI_BIAS || mode == EPI_BIAS_RELU) {
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                v[j] += ev[c + j];
+                if (mode == EPI_BIAS_RELU) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (args.out_lo != nullptr) {
+                // the output travels as a (hi, lo) pair of bf16 rows, hi + lo = v to 16 mantissa bits: the next GEMM's A
+                uint16_t* dh = reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c;
+                uint16_t* dl = args.out_lo + row * ep.ldo + n0 + c;
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_bf16x2_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+                st_global_256(dh, make_uint4(ph[0], ph[1], ph[2], ph[3]), make_uint4(ph[4], ph[5], ph[6], ph[7]));
+                st_global_256(dl, make_uint4(pl[0], pl[1], pl[2], pl[3]), make_uint4(pl[4], pl[5], pl[6], pl[7]));
+              } else {
+                float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + n0 + c;
+                if (n0 + c + 16 <= args.n_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                  st16_f32(dst, v);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (n0 + c + j < args.n_valid) dst[j] = v[j];
+                }
+              }
+            }
+          }
+        } else if (is_cpl || is_add) {
+          const int C = ep.C;
+          float lsum = 0.f;
+          for (int c = half * 16; c < C; c += 32) {
+            float sv[16], tv[16];
+            if (is_cpl) {
+              tmem_ld16(t_base + c, sv);
+              tmem_ld16(t_base + C + c, tv);
+            } else {
+              tmem_ld16(t_base + c, tv);
+            }
+            tmem_ld_wait();
+            const int coord0 = nt * C + c;
+            if (rvalid && coord0 < ep.Db) {
+              uint16_t* up = reinterpret_cast<uint16_t*>(ep.ub) + row * ep.ldub + coord0;
+              uint16_t* ulo = args.ub_lo + row * ep.ldub + coord0;
+              const float* bt = is_cpl ? ev + C + c : ev + c;
+              const bool full = coord0 + 16 <= ep.Db;
+              float u[16];
+              if (full) {     // 16 coordinates = 32 bytes of this thread's row per array: one 256-bit load each; u = hi + lo
+                uint4 q0, q1, l0, l1;
+                float uh[16], ul[16];
+                ld_global_256(up, q0, q1);
+                ld_global_256(ulo, l0, l1);
+                unpack_bf16x8(q0, uh);
+                unpack_bf16x8(q1, uh + 8);
+                unpack_bf16x8(l0, ul);
+                unpack_bf16x8(l1, ul + 8);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) u[j] = uh[j] + ul[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  u[j] = coord0 + j < ep.Db ? __uint_as_float((uint32_t)up[j] << 16) + __uint_as_float((uint32_t)ulo[j] << 16) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float tt = tv[j] + bt[j];
+                if (is_cpl) {
+                  const float ls = ep.clamp * tanh_mufu(sv[j] + ev[c + j]);   // padded coordinates: s = 0 -> ls = 0
+                  const float e = ex2_fast((mode == EPI_COUPLING_INV ? -ls : ls) * 1.4426950408889634f);
+                  u[j] = mode == EPI_COUPLING_INV ? (u[j] - tt) * e : fmaf(u[j], e, tt);
+                  lsum += ls;
+                } else {
+                  u[j] = mode == EPI_ADD_INV ? u[j] - tt : u[j] + tt;
+                }
+              }
+              if (full) {
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_bf16x2_pair(u[2 * j], u[2 * j + 1], ph[j], pl[j]);
+                st_global_256(up, make_uint4(ph[0], ph[1], ph[2], ph[3]), make_uint4(ph[4], ph[5], ph[6], ph[7]));
+                st_global_256(ulo, make_uint4(pl[0], pl[1], pl[2], pl[3]), make_uint4(pl[4], pl[5], pl[6], pl[7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (coord0 + j < ep.Db) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(u[j]);
+                    up[j] = __bfloat16_as_ushort(h);
+                    ulo[j] = __bfloat16_as_ushort(__float2bfloat16_rn(u[j] - __bfloat162float(h)));
+                  }
+              }
+            }
+          }
+          if (is_cpl && rvalid && ep.row_acc != nullptr)
+            atomicAdd(ep.row_acc + row, mode == EPI_COUPLING_INV ? -lsum : lsum);
+        } else {   // base density
+          float lsum = 0.f;
+          const float* ev_loc = ev + TC_EPI_COLS;
+          const float* ev_isc = ev + 2 * TC_EPI_COLS;
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float z = v[j] + ev[c + j];
+                if (ep.out != nullptr && n0 + c + j < args.n_valid)
+                  reinterpret_cast<float*>(ep.out)[row * ep.ldo + n0 + c + j] = z;
+                const float d = (z - ev_loc[c + j]) * ev_isc[c + j];
+                lsum += (mode == EPI_BASE_NORMAL) ? -0.5f * d * d : -fabsf(d);
+              }
+            }
+          }
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(tempty_bar(a));
+          else mbar_arrive_cluster(tempty_bar(a), 0);
+        }
+      }
+      a ^= 1;
+      if (a == 0) aph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
 // (hi, lo) split of a (rows x cols) fp32 matrix: hi = x rounded to tf32 (written to `hi`, which may alias x, or skipped
 // when NULL -- then lo is taken against the truncated value the tensor core would read from x itself), lo = x - hi
 __global__ void usf_split_lo_kernel(const float* x, int64_t ldx, float* hi, float* lo, int64_t ldl, int64_t rows, int64_t cols) {
@@ -1774,6 +2081,95 @@ int tc3_gemm(const float* A, const float* Alo, int64_t lda, const float* W, cons
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl() ? 2 : 1;
   USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc3_gemm_kernel, tmA, tmAlo, tmW, tmWlo, args));
+  return USF_OK;
+}
+
+// bf16x2 GEMM launcher (see usf_tcb2_gemm_kernel).  A, Alo: (M, lda) bf16; W, Wlo: (N, ldw) bf16; leading dimensions
+// multiples of 8 (16-byte pitches), N multiple of 16 and <= TC_EPI_COLS.
+int tcb2_gemm(const uint16_t* A, const uint16_t* Alo, int64_t lda, const uint16_t* W, const uint16_t* Wlo, int64_t ldw, int64_t M,
+              int64_t N, int64_t K, int bn, const EpiParams& ep, uint16_t* out_lo, uint16_t* ub_lo, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return USF_OK;
+  USF_CHECK_ARG(A && Alo && W && Wlo, "tcb2_gemm: null operand");
+  USF_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "tcb2_gemm: leading dimensions must be multiples of 8");
+  USF_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Alo) | reinterpret_cast<uintptr_t>(W) |
+                  reinterpret_cast<uintptr_t>(Wlo)) & 15) == 0, "tcb2_gemm: operands must be 16-byte aligned");
+  USF_CHECK_ARG(bn >= 16 && bn <= TC_MAX_BN && (bn % 16) == 0 && (N % 16) == 0 && K > 0 && N <= TC_EPI_COLS,
+                "tcb2_gemm: bad tile/shape (bn=%d N=%lld K=%lld)", bn, (long long)N, (long long)K);
+  const bool cpl = ep.mode == EPI_COUPLING_INV || ep.mode == EPI_COUPLING_FWD;
+  const bool add = ep.mode == EPI_ADD_INV || ep.mode == EPI_ADD_FWD;
+  if (cpl) USF_CHECK_ARG(bn == 2 * ep.C && (N % bn) == 0 && ub_lo != nullptr && ep.ub_bf16, "tcb2_gemm: bad coupling tile");
+  if (add) USF_CHECK_ARG(bn == ep.C && (N % bn) == 0 && ub_lo != nullptr && ep.ub_bf16, "tcb2_gemm: bad additive tile");
+  static bool attr_set = false;
+  if (!attr_set) {
+    USF_CUDA(cudaFuncSetAttribute(usf_tcb2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmAlo, tmW, tmWlo;
+  int rc = make_tmap(&tmA, A, M, K, lda, TC_BM, 2);
+  if (!rc) rc = make_tmap(&tmAlo, Alo, M, K, lda, TC_BM, 2);
+  if (!rc) rc = make_tmap(&tmW, W, N, K, ldw, bn / 2, 2);
+  if (!rc) rc = make_tmap(&tmWlo, Wlo, N, K, ldw, bn / 2, 2);
+  if (rc) return rc;
+  Tcb2Args args;
+  memset(&args, 0, sizeof(args));
+  args.M = M; args.N = N; args.K = K; args.bn = bn;
+  args.n_tiles = (int)ceil_div(N, bn);
+  args.m_tiles = (int)ceil_div(M, 2 * TC_BM);
+  args.n_valid = ep.n_valid > 0 ? ep.n_valid : (int)N;
+  args.ep = ep;
+  args.out_lo = out_lo;
+  args.ub_lo = ub_lo;
+  args.w_bytes = (uint32_t)round_up((int64_t)(bn / 2) * 128, 1024);
+  args.stage_bytes = 2u * TC_A_BYTES + 2u * args.w_bytes;
+  args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES) / args.stage_bytes);
+  if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
+  if (args.stages < 2) { set_error("tcb2_gemm: tile does not fit in shared memory"); return USF_E_ARG; }
+  args.backoff_ns = tc_backoff_ns();
+  const int64_t total = (int64_t)args.m_tiles * args.n_tiles;
+  int64_t pairs = num_sms() / 2;
+  if (pairs > total) pairs = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl() ? 2 : 1;
+  USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tcb2_gemm_kernel, tmA, tmAlo, tmW, tmWlo, args));
+  return USF_OK;
+}
+
+// fp32 rows -> (hi, lo) bf16 pairs in the activation layout (pad columns zero), optional per-row accumulator seed
+__global__ void usf_split_rows_bf16x2_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                             int64_t ldy, int64_t B, int64_t D, float* row_init, float init_value) {
+  const int64_t total = B * ldy;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldy, c = i - r * ldy;
+    const float v = c < D ? x[r * ldx + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (c == 0 && row_init != nullptr) row_init[r] = init_value;
+  }
+}
+
+int launch_split_rows_bf16x2(const float* x, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldy, int64_t B, int64_t D,
+                             float* row_init, float init_value, cudaStream_t stream) {
+  if (B <= 0) return USF_OK;
+  const int64_t total = B * ldy;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  usf_split_rows_bf16x2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                    reinterpret_cast<__nv_bfloat16*>(lo), ldy, B, D, row_init,
+                                                                    init_value);
+  USF_LAUNCH_CHECK("usf_split_rows_bf16x2_kernel");
   return USF_OK;
 }
 

@@ -42,12 +42,14 @@ def _on_device(method):
     return wrapped
 
 
-_PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16, "tf32x3": _lib.USF_PREC_TF32X3}
+_PRECISIONS = {"fp32": _lib.USF_PREC_FP32, "bf16": _lib.USF_PREC_BF16, "tf32x3": _lib.USF_PREC_TF32X3,
+               "bf16x2": _lib.USF_PREC_BF16X2}
 # `flow.precision`:
-#   "auto"   (default) the <= 1e-4 tier on the fastest kernels that hold it: 3xTF32 tensor-core kernels for D >= 128, fp32
+#   "auto"   (default) the <= 1e-4 tier on the fastest kernels that hold it: bf16x2 tensor-core kernels for D >= 128, fp32
 #            FFMA kernels below (the one-kernel path for small event shapes)
 #   "fp32"   fp32 FFMA kernels (the tightest: ~1e-6)
 #   "tf32x3" 3xTF32 tcgen05 kernels (fp32 operands as hi + lo: <= 1e-4)
+#   "bf16x2" bf16 tcgen05 kernels on (hi, lo) bf16 operand pairs, 3 MMAs per K step (<= 1e-4 at twice the 3xTF32 rate)
 #   "bf16"   bf16 tcgen05 kernels, <= 1e-2 -- verified per weight version (Flow._tier)
 _REQUESTS = ("auto",) + tuple(_PRECISIONS)
 
@@ -197,6 +199,10 @@ class Flow(torch.nn.Module):
     BF16_CALIBRATION_TOL = 5e-3
     BF16_MIN_DIM = 128
     SMALL_MAX_DIM = 64
+    # the tensor-core tier that stands in for fp32 ("auto", and where bf16 is not trusted): bf16 (hi, lo) operand pairs.
+    # Measured on every BASELINE shape with D >= 128 (scripts/bf16x2_check.py, profiles/r2/bf16x2.txt): log_prob max-row
+    # error 5e-6 .. 2.8e-5 (3xTF32: 5e-6 .. 5.6e-5) at 2.0-2.5x the 3xTF32 rate (C2: 3.39 vs 6.66 ms per 65536 rows).
+    FP32_GRADE_TC = "bf16x2"
 
     SMALL_ALWAYS = False        # (measurement switch: take the one-kernel path whenever the stack is eligible)
 
@@ -229,7 +235,7 @@ class Flow(torch.nn.Module):
     def _tier(self, x2=None, context_rows=None):
         want = self.precision
         if want == "auto":
-            want = "tf32x3" if self.event_dim >= self.BF16_MIN_DIM else "fp32"
+            want = self.FP32_GRADE_TC if self.event_dim >= self.BF16_MIN_DIM else "fp32"
         if want == "fp32" or (want == "bf16" and self.__dict__.get("bf16_trust", False)) or \
                 (want == "bf16" and os.environ.get("USF_BF16_CALIBRATE", "1") == "0"):
             self.effective_precision = want
@@ -244,14 +250,14 @@ class Flow(torch.nn.Module):
             self.effective_precision = hit[1]
             return hit[1]
         tier, calibrated, err = want, False, None
-        if want == "tf32x3":
+        if want in ("tf32x3", "bf16x2"):
             calibrated = True
         elif self.event_dim < self.BF16_MIN_DIM:
-            tier, calibrated = "tf32x3", True
+            tier, calibrated = self.FP32_GRADE_TC, True
         elif x2 is not None and x2.shape[0] > 0 and not self._needs_grad(x2):
             rows = (x2 if context_rows is None else context_rows)[:256]
             lo = self._stack(True, device, "bf16")
-            hi = self._stack(True, device, "tf32x3") or self._stack(True, device, "fp32")
+            hi = self._stack(True, device, self.FP32_GRADE_TC) or self._stack(True, device, "fp32")
             if lo is None or lo.desc.base_kind < 0 or hi is None:
                 calibrated = True                      # no fused bf16 path at all / nothing to compare with
             else:
@@ -259,12 +265,13 @@ class Flow(torch.nn.Module):
                 b = hi.run(rows.float(), want_logprob=True)[0].double()
                 err = float(((a - b).abs() / b.abs().clamp_min(1.0)).nan_to_num(nan=float("inf")).max())
                 if not err <= self.BF16_CALIBRATION_TOL:
-                    tier = "tf32x3" if hi.precision == _lib.USF_PREC_TF32X3 else "fp32"
+                    tier = self.FP32_GRADE_TC if hi.precision != _lib.USF_PREC_FP32 else "fp32"
                 calibrated = True
                 # the packed weights of the tier that lost are not needed until the weights change again
                 self._compiled.pop((True, lo.precision if tier != "bf16" else hi.precision), None)
-        if tier == "tf32x3" and self._stack(True, device, "tf32x3") is None and self._stack(True, device, "fp32") is not None:
-            tier = "fp32"                              # shapes the 3xTF32 kernels do not take (N > 1024)
+        if tier in ("tf32x3", "bf16x2") and self._stack(True, device, tier) is None and \
+                self._stack(True, device, "fp32") is not None:
+            tier = "fp32"                              # shapes the split-operand kernels do not take (N > 1024)
         self.__dict__["_tier_cache"] = ((key, want), tier, calibrated, err)
         self.effective_precision = tier
         self.bf16_calibration_err = err
@@ -292,7 +299,7 @@ class Flow(torch.nn.Module):
         """Compiled (packed) stack for this direction / precision / weight version, or None."""
         precision = precision or self.precision
         if precision == "auto":
-            precision = "tf32x3" if self.event_dim >= self.BF16_MIN_DIM else "fp32"
+            precision = self.FP32_GRADE_TC if self.event_dim >= self.BF16_MIN_DIM else "fp32"
         prec = _PRECISIONS[precision]
         slot = (bool(inverse), prec)
         key = (self._weights_key(), str(device))

@@ -91,6 +91,7 @@ class CompiledStack:
         self._mlp_widths = {}    # block -> unpadded widths of its conditioner layers
         bf16 = precision == _lib.USF_PREC_BF16
         self._t3 = precision == _lib.USF_PREC_TF32X3      # fp32 weights travel as [W ; W - tf32(W)] (2N rows)
+        self._b2 = precision == _lib.USF_PREC_BF16X2      # bf16 weights travel as [bf16(W) ; bf16(W - bf16(W))] (2N rows)
         runs, couplings = _classify(layers)
         n = len(couplings)
         # conditional flows (USFlows soft training): every conditioner takes `cd` context columns, which then travel
@@ -208,6 +209,11 @@ class CompiledStack:
 
     # -------------------------------------------------------------------------------------------
     def _fill_linear(self, desc, W32, Wb, bias, N, K, ldw):
+        if getattr(self, "_b2", False):
+            if N > 1024:
+                raise Unsupported("bf16x2 path keeps the per-column vectors resident: N <= 1024")
+            lo = (W32 - Wb.float()).to(torch.bfloat16)          # exact difference in fp32, rounded once
+            Wb, W32 = torch.cat([Wb, lo], dim=0).contiguous(), None
         if getattr(self, "_t3", False) and W32 is not None:
             if N > 1024:
                 raise Unsupported("3xTF32 path keeps the per-column vectors resident: N <= 1024")
@@ -225,7 +231,7 @@ class CompiledStack:
         ldw = _round_up(K, 8)
         src_rows = torch.where(in_cols >= 0, in_cols + 1, in_cols).contiguous()
         W32, Wb = ops.pack_matrix(Mt, out_cols, src_rows, N, K, ldw, sub_row0=True, transpose_src=True,
-                                  want_f32=not bf16, want_bf16=bf16)
+                                  want_f32=not bf16, want_bf16=bf16 or self._b2)
         bias, _ = ops.pack_matrix(Mt[:1], None, out_cols, 1, N, N)
         self._fill_linear(desc, W32, Wb, bias.reshape(-1), N, K, ldw)
 
@@ -255,7 +261,7 @@ class CompiledStack:
             cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
             nt = -(-Db // cap)
             Cc = _round_up(-(-Db // nt), 16)
-        elif self._t3:
+        elif self._t3 or self._b2:
             cap = 128      # coords per tile: the epilogues prefetch <= 4 chunks of 16 per warp half
             nt = -(-Db // cap)
             Cc = _round_up(-(-Db // nt), 16)
@@ -293,7 +299,7 @@ class CompiledStack:
                 # no conditioning coordinate (D == 1): the conditioner sees zeros -> constant params
                 K, col_idx = 1, torch.full((1,), -1, dtype=torch.int32, device=dev)
             ldw = _round_up(K, 8)
-            W32, Wb = ops.pack_matrix(Wsrc, row_idx, col_idx, N, K, ldw, want_f32=not bf16, want_bf16=bf16)
+            W32, Wb = ops.pack_matrix(Wsrc, row_idx, col_idx, N, K, ldw, want_f32=not bf16, want_bf16=bf16 or self._b2)
             bias, _ = ops.pack_matrix(bsrc.reshape(-1, 1), row_idx, None, N, 1, 1)
             self._fill_linear(blk.mlp[li], W32, Wb, bias.reshape(-1), N, K, ldw)
 

@@ -654,10 +654,12 @@ def test_full_size_properties_c2(O, P):
         assert float(lp_err(lp32, ref).max()) < FP32_TOL
 
 
-def test_tf32x3_tier(O, P):
-    """`flow.precision = "tf32x3"`: the fused stack on 3xTF32 tensor-core GEMMs (fp32 activations carried as hi + lo).
-    Sits between the tiers: log_prob within 2e-4 of the fp64 oracle on the headline shapes (measured 1e-5 ... 6e-5;
-    the tensor core's accumulate truncates, which FFMA does not), latents / samples within 2e-4 of the row scale."""
+@pytest.mark.parametrize("tier,tol", [("tf32x3", 2e-4), ("bf16x2", 1e-4)])
+def test_split_operand_tiers(O, P, tier, tol):
+    """The fp32-grade tensor-core tiers: `"tf32x3"` (fp32 operands as tf32 hi + lo, three kind::tf32 MMAs per K step) and
+    `"bf16x2"` (bf16 hi + lo pairs, three kind::f16 MMAs per K step at twice that rate; what `"auto"` runs for D >= 128).
+    log_prob, latents and samples against the fp64 oracle: 3xTF32 within 2e-4 (measured 1e-5 ... 6e-5; the tensor core's
+    accumulate truncates, which FFMA does not), bf16x2 within the fp32 tier's 1e-4 (measured 5e-6 ... 3e-5)."""
     for kind, D, K, cond, base, kw in (
             ("NonUSFlow", 784, 2, ("mlp", [256, 256]), "normal", dict(affine_conjugation=True)),
             ("USFlow", 128, 4, ("densenn1", [512, 256]), "normal", dict(affine_conjugation=True, householder=0)),
@@ -667,11 +669,12 @@ def test_tf32x3_tier(O, P):
         x = torch.randn(300, D, generator=torch.Generator().manual_seed(42))
         zs = torch.randn(300, D, generator=torch.Generator().manual_seed(43))
         with torch.no_grad():
-            fp.precision = "tf32x3"
+            fp.precision = tier
+            fp.SMALL_MAX_DIM = 0                  # (the D = 33 stack would otherwise take the one-kernel fp32 path)
             lp, z, xs = fp.log_prob(x.cuda()), fp.backward(x.cuda()), fp.latent_to_data(zs.cuda())
-            assert fp.last_launches > 0
-            assert float(lp_err(lp, fo.log_prob(x.double())).max()) < 2e-4
+            assert fp.last_launches > 1 and fp.effective_precision == tier
+            assert float(lp_err(lp, fo.log_prob(x.double())).max()) < tol
             assert float(row_err(z, fo.backward(x.double())).max()) < 2e-4
             assert float(row_err(xs, fo.latent_to_data(zs.double())).max()) < 2e-4
             # small batch and more than one internal tile
-            assert float(lp_err(fp.log_prob(x[:5].cuda()), fo.log_prob(x[:5].double())).max()) < 2e-4
+            assert float(lp_err(fp.log_prob(x[:5].cuda()), fo.log_prob(x[:5].double())).max()) < tol

@@ -74,7 +74,7 @@ def test_full_depth_configs_max_row(O, P, cfg):
         ref = fo.log_prob(x.double())
         z_ref = fo.backward(x.double())
         xc = x.cuda()
-        for precision, tol in (("fp32", FP32_TOL), ("tf32x3", 2e-4), ("bf16", BF16_TOL)):
+        for precision, tol in (("fp32", FP32_TOL), ("auto", FP32_TOL), ("bf16x2", FP32_TOL), ("tf32x3", 2e-4), ("bf16", BF16_TOL)):
             fp.precision = precision
             lp = fp.log_prob(xc)
             assert fp.last_launches > 0, "fused CUDA path did not run"
@@ -111,7 +111,7 @@ def test_round2_golden(P, name):
             assert relmax(q, g["ladj_quirk"]) < FP32_TOL
         if g["case"].get("context"):
             assert fused, "a conditional flow must run the fused chain (context columns)"
-            for prec, tol in (("tf32x3", 2e-4), ("bf16", BF16_TOL)):
+            for prec, tol in (("bf16x2", FP32_TOL), ("tf32x3", 2e-4), ("bf16", BF16_TOL)):
                 flow.precision = prec
                 assert float(lp_err(flow.log_prob(x, ctx), g["log_prob"]).max()) < tol
             flow.precision = "fp32"
@@ -367,7 +367,7 @@ def test_small_stack_single_kernel(O, P, cfg):
         zs = torch.randn(B, D, generator=g)
         with torch.no_grad():
             ref, z_ref, xs_ref = fo.log_prob(x.double()), fo.backward(x.double()), fo.latent_to_data(zs.double())
-            for precision in ("auto", "fp32", "tf32x3", "bf16"):
+            for precision in ("auto", "fp32", "tf32x3", "bf16x2", "bf16"):
                 fp.precision = precision
                 lp = fp.log_prob(x.cuda())
                 assert fp.last_launches == 1 and fp.effective_precision == "fp32", (precision, fp.last_launches, fp.effective_precision)
@@ -386,5 +386,5 @@ def test_small_stack_single_kernel(O, P, cfg):
         if big_tier == "fp32":
             assert fp.last_launches == 1 and torch.equal(lp[12345:12400], part)
         else:
-            assert big_tier == "tf32x3" and float(lp_err(lp[12345:12400], part).max()) < 2e-4
+            assert big_tier == "bf16x2" and float(lp_err(lp[12345:12400], part).max()) < 2e-4
         assert bool(torch.isfinite(lp).all())
