@@ -257,6 +257,15 @@ int usf_stack_run(const usf_stack_desc* st, const float* x, int64_t ldx, int64_t
                   float* out_y, int64_t ldy, float* out_ladj, void* workspace, size_t workspace_bytes,
                   int precision, int* gpu_launches, usf_stream_t stream);
 
+/* Deterministic mode of the calling thread's later usf_stack_workspace_bytes / usf_stack_run calls (returns the previous
+ * setting).  Off (default): the per-row log-det / log-density terms of the tiles and warps that share a row are added
+ * with fp32 atomics, whose order -- and so the last ulp of log_prob -- varies from run to run.  On: every such partial
+ * sum is stored in its own slot of the workspace and one more kernel at the end of the chain adds the slots in a fixed
+ * order (bit-identical results run to run, as the reference's are; a few MB of extra workspace, one extra launch, and
+ * the fp32 tier's small-batch split-K GEMM form is not used).  The one-kernel path for small event shapes is always
+ * deterministic. */
+int usf_set_deterministic(int on);
+
 /* 1 if usf_stack_run serves this stack at this precision with ONE whole-stack kernel (small event shapes: D + ctx_dim
  * <= 64, every layer width <= 128, fp32 weights; rows stay in shared memory across all layers, deterministic row sums),
  * 0 if it runs the launch chain. */

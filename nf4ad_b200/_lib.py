@@ -76,6 +76,7 @@ _PROTOS = {
     "usf_pack_matrix": (_int, [_vp, _i64, _vp, _vp, _int, _int, _i64, _i64, _vp, _vp, _i64, _vp]),
     "usf_stack_workspace_bytes": (_sz, [C.POINTER(StackDesc), _i64, _int]),
     "usf_stack_is_single_kernel": (_int, [C.POINTER(StackDesc), _int]),
+    "usf_set_deterministic": (_int, [_int]),
     "usf_stack_run": (_int, [C.POINTER(StackDesc), _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _sz, _int,
                              C.POINTER(_int), _vp]),
     "usf_profile_begin": (_int, [_int]),

@@ -69,8 +69,21 @@ struct StackPlan {
   size_t hid_bytes;
   size_t acc_bytes;
   size_t small_bytes;  // fp32 path: split-K accumulator for small batches (rows <= kSmallRows)
+  int det_slots;       // deterministic mode: partial-sum slots of one pass over the chain
+  size_t det_bytes;
   size_t total;
 };
+
+// partial-sum slots one accumulating launch uses (the `sub` range of row_accumulate in its kernel)
+inline int det_slots_of(int precision, int64_t N, int bn, bool fused) {
+  if (fused) return 4;                                                       // MLP_EPI_PARTS warps per row
+  if (precision == USF_PREC_FP32) return (int)ceil_div(N, 128);              // SIMT tile: 128 columns per blockIdx.y
+  return 2 * (int)ceil_div(N, bn);                                           // tcgen05 kernels: 2 epilogue warps per N tile
+}
+
+// Deterministic mode (usf_set_deterministic, per thread): every per-row partial sum of the chain goes to its own slot of
+// a scratch area and one last kernel adds the slots in order, instead of fp32 atomics whose order varies run to run.
+thread_local int g_deterministic = 0;
 
 constexpr int64_t kChunkRows = 131072;  // rows pushed through the stack per pass (bounds the workspace)
 constexpr int64_t kSmallRows = 2048;    // fp32 path: batches up to this size may use the split-K + epilogue-kernel GEMM form
@@ -101,10 +114,25 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
   p->act_bytes = align256((size_t)rows * p->ld_act * esz);
   p->hid_bytes = align256((size_t)rows * p->ld_hid * esz);
   p->acc_bytes = align256((size_t)rows * sizeof(float));
-  p->small_bytes = (precision == USF_PREC_FP32 && rows <= kSmallRows) ? align256((size_t)rows * (size_t)nmax * sizeof(float)) : 0;
+  p->small_bytes = (precision == USF_PREC_FP32 && rows <= kSmallRows && !g_deterministic)
+                       ? align256((size_t)rows * (size_t)nmax * sizeof(float)) : 0;   // (split-K sums atomically: not in deterministic mode)
+  p->det_slots = 0;
+  if (g_deterministic) {
+    const bool tc = precision != USF_PREC_FP32;
+    for (int b = 0; b < st->n_blocks; ++b) {
+      const usf_block_desc& blk = st->blocks[b];
+      if (!blk.affine) continue;                                  // additive couplings add nothing to the row sums
+      const usf_linear_desc& L = blk.mlp[blk.n_mlp - 1];
+      p->det_slots += tc ? (2 * (int)ceil_div(L.N, 2 * blk.C) > 4 ? 2 * (int)ceil_div(L.N, 2 * blk.C) : 4)
+                         : det_slots_of(precision, L.N, 0, false);
+    }
+    p->det_slots += tc ? det_slots_of(precision, st->G_final.N, tc_pick_bn(st->G_final.N), false)
+                       : det_slots_of(precision, st->D, 0, false);
+  }
+  p->det_bytes = align256((size_t)p->det_slots * (size_t)rows * sizeof(float));
   // 3xTF32 / bf16x2: every activation buffer has a low-part twin
   const size_t twins = (precision == USF_PREC_TF32X3 || precision == USF_PREC_BF16X2) ? 2 : 1;
-  p->total = twins * (2 * p->act_bytes + 2 * p->hid_bytes) + p->acc_bytes + p->small_bytes + 256;
+  p->total = twins * (2 * p->act_bytes + 2 * p->hid_bytes) + p->acc_bytes + p->small_bytes + p->det_bytes + 256;
   return USF_OK;
 }
 
@@ -260,6 +288,18 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
     return reinterpret_cast<float*>(lo_base + (h - base));
   };
   (void)act_lo; (void)hid_lo;
+  // deterministic mode: slot area for the per-row partial sums, after everything else
+  const size_t twins_n = (t3 || b2) ? 2 : 1;
+  float* det = p.det_slots > 0 ? reinterpret_cast<float*>(lo_base + (twins_n - 1) * (2 * p.act_bytes + 2 * p.hid_bytes)) : nullptr;
+  int det_cursor = 0;
+  // points an accumulating launch at its slots (n of them) instead of the atomics
+  auto det_assign = [&](EpiParams& ep, int n, int64_t rows) {
+    if (det == nullptr || ep.row_acc == nullptr) return;
+    ep.row_part = det;
+    ep.part_ld = rows;
+    ep.part_slot = det_cursor;
+    det_cursor += n;
+  };
 
   int launches = 0;
   // Serpentine tile order (bf16 tier): every tensor-core kernel of the chain walks the row tiles in the opposite
@@ -310,6 +350,9 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
     // stage 0: bring x into the activation layout (bf16, or padded fp32) and seed the per-row accumulator
     int cur = 0;
     flip = 1;
+    det_cursor = 0;
+    if (det != nullptr && row_acc != nullptr)
+      USF_CUDA(cudaMemsetAsync(det, 0, (size_t)p.det_slots * (size_t)rows * sizeof(float), s));
     {
       ProfScope ps(s, 0);
       if (b2)
@@ -374,6 +417,7 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.C = blk.C;
           ep.clamp = blk.clamp;
           ep.row_acc = row_acc;
+          if (blk.affine) det_assign(ep, 2 * (int)ceil_div(blk.mlp[blk.n_mlp - 1].N, 2 * blk.C) > 4 ? 2 * (int)ceil_div(blk.mlp[blk.n_mlp - 1].N, 2 * blk.C) : 4, rows);
           next_order();
           {
             ProfScope ps(s, 5);
@@ -409,6 +453,9 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
           ep.clamp = blk.clamp;
           ep.row_acc = row_acc;
           if (bf16 || t3 || b2) bn = blk.affine ? 2 * blk.C : blk.C;
+          if (blk.affine)      // (the same slot count as the fused form of this block would take: see plan_stack)
+            det_assign(ep, (bf16 || t3 || b2) ? (2 * (int)ceil_div(L.N, 2 * blk.C) > 4 ? 2 * (int)ceil_div(L.N, 2 * blk.C) : 4)
+                                             : det_slots_of(precision, L.N, 0, false), rows);
         }
         {
           ProfScope ps(s, l + 1 < blk.n_mlp ? 2 : 3);
@@ -433,6 +480,8 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
         ep.loc = st->loc;
         ep.inv_scale = st->inv_scale;
         ep.row_acc = row_acc;
+        det_assign(ep, (bf16 || t3 || b2) ? det_slots_of(precision, st->G_final.N, tc_pick_bn(st->G_final.N), false)
+                                          : det_slots_of(precision, st->D, 0, false), rows);
       } else {
         USF_CHECK_ARG(out_y != nullptr, "usf_stack_run: nothing to compute (no output requested)");
         ep.mode = EPI_BIAS;
@@ -444,6 +493,12 @@ static int stack_run_eager(const usf_stack_desc* st, const float* x, int64_t ldx
         ProfScope ps(s, 4);
         rc = gemm(act[cur], p.ld_act, Lf, (bf16 || t3 || b2) ? tc_pick_bn(Lf.N) : 0, ep, rows);
       }
+      if (rc) return rc;
+      ++launches;
+    }
+    // deterministic mode: the slots, added in slot order, on top of the seeded accumulator
+    if (det != nullptr && row_acc != nullptr && det_cursor > 0) {
+      rc = launch_sum_row_parts(row_acc, det, rows, det_cursor, rows, s);
       if (rc) return rc;
       ++launches;
     }
@@ -515,7 +570,7 @@ static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ld
   const uint64_t extra[9] = {(uint64_t)(uintptr_t)x, (uint64_t)ldx, (uint64_t)B, (uint64_t)(uintptr_t)out_logprob,
                              (uint64_t)(uintptr_t)out_y, (uint64_t)ldy, (uint64_t)(uintptr_t)out_ladj,
                              (uint64_t)(uintptr_t)workspace,
-                             (uint64_t)workspace_bytes * 8u + (uint64_t)precision + (x_bf16 ? 4u : 0u)};
+                             (uint64_t)workspace_bytes * 16u + (uint64_t)precision + (x_bf16 ? 4u : 0u) + (g_deterministic ? 8u : 0u)};
   const size_t nb_bytes = st->n_blocks > 0 ? sizeof(usf_block_desc) * (size_t)st->n_blocks : 0;
   thread_local std::vector<unsigned char> kb;
   kb.resize(sizeof(*st) + nb_bytes + sizeof(extra));
@@ -588,6 +643,12 @@ static int stack_run_cached(const usf_stack_desc* st, const float* x, int64_t ld
   USF_CUDA(cudaGraphLaunch(exec, s));
   if (gpu_launches) *gpu_launches = launches;
   return USF_OK;
+}
+
+extern "C" int usf_set_deterministic(int on) {
+  const int prev = g_deterministic;
+  g_deterministic = on ? 1 : 0;
+  return prev;
 }
 
 extern "C" int usf_stack_is_single_kernel(const usf_stack_desc* st, int precision) {

@@ -70,7 +70,20 @@ struct EpiParams {
   float* row_acc;        // (M) per-row accumulator (log-det / log-density), atomically updated; may be NULL
   const float* loc;      // BASE: per output column
   const float* inv_scale;
+  // deterministic mode (usf_set_deterministic): instead of an atomic add into row_acc -- whose order over the tiles /
+  // warps that share a row is not fixed -- contributor `sub` of this launch stores its partial sum into its own slot
+  // row_part[(part_slot + sub) * part_ld + row]; the chain ends with a kernel that adds the slots in slot order.
+  float* row_part;
+  int64_t part_ld;
+  int part_slot;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void row_accumulate(const EpiParams& ep, int64_t row, int sub, float v) {
+  if (ep.row_part != nullptr) ep.row_part[(int64_t)(ep.part_slot + sub) * ep.part_ld + row] = v;
+  else atomicAdd(ep.row_acc + row, v);
+}
+#endif
 
 // ---- SIMT fp32 GEMM (usf_simt.cu) -------------------------------------------------------------
 // acc = A(MxK, lda) * W(NxK, ldw)^T with the epilogue above.  a_trans / w_trans select the
@@ -126,6 +139,8 @@ int launch_convert_rows(const float* x, int64_t ldx, uint16_t* y_bf16, float* y_
                         int64_t B, int64_t D, float* row_init, float init_value, cudaStream_t stream);
 int launch_copy_rows_bf16(const uint16_t* x, int64_t ldx, uint16_t* y, int64_t ldy, int64_t B, int64_t D, float* row_init,
                           float init_value, cudaStream_t stream);
+// out[r] += sum over slots (in slot order) of part[s * ld + r]: the end of a deterministic launch chain
+int launch_sum_row_parts(float* out, const float* part, int64_t ld, int slots, int64_t rows, cudaStream_t stream);
 int launch_bf16_to_f32(const uint16_t* x, int64_t ldx, float* y, int64_t ldy, int64_t B, int64_t D,
                        cudaStream_t stream);
 

@@ -227,7 +227,7 @@ usf_simt_gemm_kernel(const float* __restrict__ A, int64_t lda, int a_trans, cons
       }
       lsum = warp16_sum(lsum);
       if (tx == 0 && r < M && ep.row_acc != nullptr)
-        atomicAdd(ep.row_acc + r, mode == EPI_COUPLING_INV ? -lsum : lsum);
+        row_accumulate(ep, r, (int)blockIdx.y, mode == EPI_COUPLING_INV ? -lsum : lsum);
     }
   } else if (mode == EPI_ADD_INV || mode == EPI_ADD_FWD) {
 #pragma unroll
@@ -263,7 +263,7 @@ usf_simt_gemm_kernel(const float* __restrict__ A, int64_t lda, int a_trans, cons
         }
       }
       lsum = warp16_sum(lsum);
-      if (tx == 0 && r < M && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + r, lsum);
+      if (tx == 0 && r < M && ep.row_acc != nullptr && ep.loc != nullptr) row_accumulate(ep, r, (int)blockIdx.y, lsum);
     }
   }
 }
@@ -297,7 +297,7 @@ __global__ void usf_simt_epilogue_kernel(const float* __restrict__ acc, int64_t 
       lsum += ls;
     }
     lsum = warp_sum(lsum);
-    if (lane == 0 && ep.row_acc != nullptr) atomicAdd(ep.row_acc + r, mode == EPI_COUPLING_INV ? -lsum : lsum);
+    if (lane == 0 && ep.row_acc != nullptr) row_accumulate(ep, r, 0, mode == EPI_COUPLING_INV ? -lsum : lsum);
   } else if (mode == EPI_ADD_INV || mode == EPI_ADD_FWD) {
     for (int c = lane; c < ep.Db; c += 32) {
       const float t = a[c] + ep.bias[c];
@@ -316,8 +316,26 @@ __global__ void usf_simt_epilogue_kernel(const float* __restrict__ acc, int64_t 
       }
     }
     lsum = warp_sum(lsum);
-    if (lane == 0 && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + r, lsum);
+    if (lane == 0 && ep.row_acc != nullptr && ep.loc != nullptr) row_accumulate(ep, r, 0, lsum);
   }
+}
+
+// out[r] += part[0][r] + part[1][r] + ... in slot order (deterministic mode: the end of the launch chain)
+__global__ void usf_sum_row_parts_kernel(float* out, const float* __restrict__ part, int64_t ld, int slots, int64_t rows) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float v = out[r];
+    for (int s = 0; s < slots; ++s) v += part[(int64_t)s * ld + r];
+    out[r] = v;
+  }
+}
+
+int launch_sum_row_parts(float* out, const float* part, int64_t ld, int slots, int64_t rows, cudaStream_t stream) {
+  if (rows <= 0 || slots <= 0) return USF_OK;
+  int64_t blocks = (rows + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  usf_sum_row_parts_kernel<<<(unsigned)blocks, 256, 0, stream>>>(out, part, ld, slots, rows);
+  USF_LAUNCH_CHECK("usf_sum_row_parts_kernel");
+  return USF_OK;
 }
 
 const char* const kSimtGemmKernelName = "usf_simt_gemm_kernel";

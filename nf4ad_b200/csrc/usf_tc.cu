@@ -719,7 +719,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             cq1 = nq1;
           }
           if (is_cpl && rvalid && ep.row_acc != nullptr)
-            atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
+            row_accumulate(ep, row, nt * 2 + half, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
         } else {  // EPI_BASE_NORMAL / EPI_BASE_LAPLACE  (padded columns have inv_scale = 0 -> contribute 0)
           float lsum = 0.f;
           for (int c = half * 16; c < width; c += 32) {
@@ -737,7 +737,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
           }
-          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) row_accumulate(ep, row, nt * 2 + half, lsum);
         }
 
         // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -1129,8 +1129,8 @@ usf_tc_mlp_coupling_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           nt = nnt;
         }
       }
-      if (is_cpl && rvalid && ep.row_acc != nullptr)
-        atomicAdd(ep.row_acc + row, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
+      if (is_cpl && rvalid && ep.row_acc != nullptr)     // `half` = this warp's part (0 .. MLP_EPI_PARTS - 1)
+        row_accumulate(ep, row, half, (ep.mode == EPI_COUPLING_INV ? -ep.clamp : ep.clamp) * lsum);
     }
   }
 
@@ -1445,7 +1445,7 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (is_cpl && rvalid && ep.row_acc != nullptr)
-            atomicAdd(ep.row_acc + row, mode == EPI_COUPLING_INV ? -lsum : lsum);
+            row_accumulate(ep, row, nt * 2 + half, mode == EPI_COUPLING_INV ? -lsum : lsum);
         } else {   // base density
           float lsum = 0.f;
           const float* ev_loc = ev + TC_EPI_COLS;
@@ -1465,7 +1465,7 @@ usf_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) row_accumulate(ep, row, nt * 2 + half, lsum);
         }
         tc_fence_before();
         __syncwarp();
@@ -1752,7 +1752,7 @@ usf_tcb2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
           if (is_cpl && rvalid && ep.row_acc != nullptr)
-            atomicAdd(ep.row_acc + row, mode == EPI_COUPLING_INV ? -lsum : lsum);
+            row_accumulate(ep, row, nt * 2 + half, mode == EPI_COUPLING_INV ? -lsum : lsum);
         } else {   // base density
           float lsum = 0.f;
           const float* ev_loc = ev + TC_EPI_COLS;
@@ -1772,7 +1772,7 @@ usf_tcb2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
             }
           }
-          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) atomicAdd(ep.row_acc + row, lsum);
+          if (rvalid && ep.row_acc != nullptr && ep.loc != nullptr) row_accumulate(ep, row, nt * 2 + half, lsum);
         }
         tc_fence_before();
         __syncwarp();
@@ -2146,16 +2146,31 @@ int tcb2_gemm(const uint16_t* A, const uint16_t* Alo, int64_t lda, const uint16_
   return USF_OK;
 }
 
-// fp32 rows -> (hi, lo) bf16 pairs in the activation layout (pad columns zero), optional per-row accumulator seed
-__global__ void usf_split_rows_bf16x2_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* hi, __nv_bfloat16* lo,
+// fp32 rows -> (hi, lo) bf16 pairs in the activation layout (pad columns zero), optional per-row accumulator seed.
+// HBM-bound (4 D bytes read, 4 ldy written per row): 8 columns per thread, 16-byte loads when the source row allows,
+// one 16-byte store per output array.
+__global__ void usf_split_rows_bf16x2_kernel(const float* __restrict__ x, int64_t ldx, uint16_t* hi, uint16_t* lo,
                                              int64_t ldy, int64_t B, int64_t D, float* row_init, float init_value) {
-  const int64_t total = B * ldy;
+  const int64_t groups = ldy >> 3;
+  const int64_t total = B * groups;
+  const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / ldy, c = i - r * ldy;
-    const float v = c < D ? x[r * ldx + c] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int64_t r = i / groups, c = (i - r * groups) << 3;
+    float v[8];
+    const float* src = x + r * ldx + c;
+    if (vec_ok && c + 8 <= D) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c + j < D ? src[j] : 0.f;
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16x2_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    *reinterpret_cast<uint4*>(hi + r * ldy + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo + r * ldy + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     if (c == 0 && row_init != nullptr) row_init[r] = init_value;
   }
 }
@@ -2163,12 +2178,10 @@ __global__ void usf_split_rows_bf16x2_kernel(const float* __restrict__ x, int64_
 int launch_split_rows_bf16x2(const float* x, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldy, int64_t B, int64_t D,
                              float* row_init, float init_value, cudaStream_t stream) {
   if (B <= 0) return USF_OK;
-  const int64_t total = B * ldy;
+  const int64_t total = B * (ldy >> 3);          // ldy is a multiple of 16
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  usf_split_rows_bf16x2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                                    reinterpret_cast<__nv_bfloat16*>(lo), ldy, B, D, row_init,
-                                                                    init_value);
+  usf_split_rows_bf16x2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, hi, lo, ldy, B, D, row_init, init_value);
   USF_LAUNCH_CHECK("usf_split_rows_bf16x2_kernel");
   return USF_OK;
 }

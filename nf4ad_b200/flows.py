@@ -82,6 +82,9 @@ class Flow(torch.nn.Module):
         self.precision = _default_precision()   # "fp32" / "tf32x3" (<=1e-4 tier) or "bf16" (tcgen05, <=1e-2 tier, verified: _tier)
         self.effective_precision = self.precision
         self.bf16_calibration_err = None
+        # run-to-run bit-identical log_prob (the reference's eager CPU path is deterministic): per-row partial sums go to
+        # slots that are added in a fixed order instead of fp32 atomics (usf_set_deterministic).  Costs one small launch.
+        self.deterministic = os.environ.get("USF_DETERMINISTIC", "0") == "1"
         self.last_launches = 0                  # kernels enqueued by the last fused call
         self._compiled = {}
         self._key_slots = None
@@ -367,7 +370,7 @@ class Flow(torch.nn.Module):
         context = self._soft_context(x2, context)
         cs, xin = self._fused(x2, context, True)
         if cs is not None and cs.desc.base_kind >= 0:
-            lp, _, _, n = cs.run(xin, want_logprob=True)
+            lp, _, _, n = cs.run(xin, want_logprob=True, deterministic=self.deterministic)
             self.last_launches = n
             return lp.reshape(lead)
         # autograd (training) pass; "bf16" / "tf32x3" select the tensor-core forms of its GEMMs (ops.tc_training);

@@ -350,8 +350,9 @@ class CompiledStack:
         """True when usf_stack_run serves this stack with the one whole-stack kernel (small event shapes)."""
         return bool(lib().usf_stack_is_single_kernel(C.byref(self.desc), self.precision))
 
-    def run(self, x, want_logprob=False, want_y=False, want_ladj=False):
-        """x: (B, D) fp32 CUDA -- or bf16 rows for the bf16 tier (usf_stack_run_bf16in: bit-identical to fp32 rows that
+    def run(self, x, want_logprob=False, want_y=False, want_ladj=False, deterministic=False):
+        """`deterministic`: per-row sums without atomics (usf_set_deterministic): bit-identical results run to run.
+        x: (B, D) fp32 CUDA -- or bf16 rows for the bf16 tier (usf_stack_run_bf16in: bit-identical to fp32 rows that
         round to them).  Returns (logprob | None, y | None, ladj | None, n_launches)."""
         _lib.require_cuda(x)
         x_bf16 = x.dtype == torch.bfloat16 and self.precision == _lib.USF_PREC_BF16 and x.dim() == 2
@@ -372,6 +373,14 @@ class CompiledStack:
             return lp, y, ladj, 0
         if want_logprob and self.desc.base_kind < 0:
             raise _lib.USFError("this stack was compiled without a supported base distribution")
+        prev = lib().usf_set_deterministic(int(bool(deterministic)))
+        try:
+            return self._run(x, x_bf16, ldx, B, lp, y, ladj)
+        finally:
+            lib().usf_set_deterministic(prev)
+
+    def _run(self, x, x_bf16, ldx, B, lp, y, ladj):
+        dev = x.device
         nbytes = lib().usf_stack_workspace_bytes(C.byref(self.desc), B, self.precision)
         if nbytes == 0:
             raise _lib.USFError("usf_stack_workspace_bytes failed: " + lib().usf_last_error().decode())
