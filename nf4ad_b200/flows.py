@@ -211,10 +211,11 @@ class Flow(torch.nn.Module):
 
     def _small_ok(self, device, rows=None):
         """Does the one-kernel path take this stack (both directions share the shapes), and does it pay at this batch
-        size?  Measured against the 3xTF32 launch chain (scripts/bench_small.py, profiles/r2/small_stack.txt): one kernel
-        instead of 12 launches wins at every batch size while the layers are at most 32 wide (D = 6: 1.1-1.6x, D = 20:
-        1.0-1.7x) and up to ~8k rows for wider layers (D = 32 / 64 with 64-128 wide layers: 1.2-1.5x; at 65536 rows its
-        fp32 FFMA arithmetic, paced by shared-memory reads, loses 0.55-0.73x to the tensor-core chain)."""
+        size?  Measured against the split-operand tensor-core chain (scripts/bench_small.py, profiles/r2/small_stack.txt):
+        one kernel instead of 11 launches wins at every batch size while the layers are at most 32 wide (D = 6: 1.05-1.3x,
+        D = 20: 1.0-1.2x).  With 64-128 wide layers its fp32 FFMA arithmetic (paced by shared-memory reads) loses to
+        the tensor cores from a few thousand rows on (0.3-0.4x at 65536 rows), so it is kept for batches of up to 1024
+        rows, where a call is host-bound either way and one launch means the lowest latency and a deterministic sum."""
         if self.event_dim + self.context_dim() > self.SMALL_MAX_DIM or len(self.event_shape) != 1:
             return False
         key = self._weights_key()
@@ -233,7 +234,7 @@ class Flow(torch.nn.Module):
         _, eligible, widest = hit
         if not eligible:
             return False
-        return rows is None or self.SMALL_ALWAYS or rows <= 8192 or widest <= 32
+        return rows is None or self.SMALL_ALWAYS or rows <= 1024 or widest <= 32
 
     def _tier(self, x2=None, context_rows=None):
         want = self.precision
