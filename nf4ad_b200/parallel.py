@@ -399,6 +399,7 @@ class DataParallelTrainer:
         self._pending = [b[2] for b in self._buckets]
         self._sent = [False] * len(self._buckets)
         self._syncing = False
+        self._main_stream = None
         self._comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
         self._nccl = dev.type == "cuda" and dist.get_backend(self.group) == "nccl"
         if self.overlap:
@@ -433,8 +434,17 @@ class DataParallelTrainer:
         start, end, _ = self._buckets[b]
         chunk = self._flat[start:end]
         if self._comm_stream is not None:
-            cur = torch.cuda.current_stream(chunk.device)
-            self._comm_stream.wait_stream(cur)            # the gradients of this bucket are complete on `cur`
+            # the bucket's gradients were produced on the step's main stream, on the stream autograd runs this hook on,
+            # and -- LU inverses, weight gradients -- on the flow's side streams: wait for everything enqueued on any of
+            # them so far (the rest of the backward pass keeps running beside the collective)
+            from . import ops
+            dev = chunk.device
+            waits = {torch.cuda.current_stream(dev), self._main_stream}
+            waits.update(getattr(self.flow, "_side_streams", None) or [])
+            waits.update(st for i, st in ops._WGRAD_STREAMS.items() if i == dev.index)
+            for st in waits:
+                if st is not None:
+                    self._comm_stream.wait_stream(st)
             with torch.cuda.stream(self._comm_stream):
                 self._reduce(chunk)
         else:
@@ -455,6 +465,7 @@ class DataParallelTrainer:
                 p.grad = self._flat[s0:e0].view_as(p)      # someone set it to None / replaced it: re-attach the view
         self._pending = [b[2] for b in self._buckets]
         self._sent = [False] * len(self._buckets)
+        self._main_stream = torch.cuda.current_stream(self._flat.device) if self._flat.is_cuda else None
         self._syncing = True
 
     def _param_ranges(self):
