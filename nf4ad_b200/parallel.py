@@ -143,7 +143,7 @@ class ShardedScorer:
         self.flow, self.group = flow, group
         self.score_fn = score_fn or (lambda x: flow.log_prob(x))
         self.rank, self.world = _world(group)
-        self.chunk_rows = 16384         # rows per H2D / compute pipeline stage of predict_score_host
+        self.chunk_rows = int(os.environ.get("USF_HOST_CHUNK_ROWS", "16384"))   # rows per H2D / compute pipeline stage
         self._copy_stream = None
         # bf16 tier: narrow the rows to bf16 on the host cores before the PCIe copy (half the bytes; the tier rounds its
         # input to bf16 as its first device step, so the scores are bit-identical).  Only with the default score function.
