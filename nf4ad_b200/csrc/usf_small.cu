@@ -133,6 +133,133 @@ __device__ __forceinline__ void stage_x(const SsArgs& args, int64_t tile, float*
   }
 }
 
+struct SsLayerCtx {
+  const float* in; int ldi;
+  const float* wbuf; const float* bbuf; int ldw, K4, jn;
+  float* actc;        // current activation buffer (coupling: updated in place)
+  float* act_out;     // the other activation buffer (affine map output)
+  float* hid_out;     // hidden buffer this layer writes
+  int lda, ldh;
+  float* racc; const float* locs; const float* iscs;
+  int64_t row0; int nrows, tx, ty;
+};
+
+// One layer on this thread's 4 x (16 JN) register tile: GEMM against the staged weights, then the layer's epilogue.
+template <int JN>
+__device__ __forceinline__ void ss_layer(const SsArgs& args, const SsOp& op, const SsLayerCtx& cx) {
+  const int jn = cx.jn, tx = cx.tx, ty = cx.ty, lda = cx.lda;
+  const float* bbuf = cx.bbuf;
+  float acc[4][JN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < JN; ++j) acc[i][j] = 0.f;
+  const float* arow = cx.in + (ty * 4) * cx.ldi;
+  const float* wrow = cx.wbuf + tx * cx.ldw;
+  for (int k = 0; k < cx.K4; k += 4) {
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * cx.ldi + k);
+#pragma unroll
+    for (int j = 0; j < JN; ++j) {
+      if (JN <= 2 || j < jn) {
+        const float4 w = *reinterpret_cast<const float4*>(wrow + j * 16 * cx.ldw + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][j] = fmaf(a[i].x, w.x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, w.y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, w.z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, w.w, acc[i][j]);
+        }
+      }
+    }
+  }
+
+  if (op.kind == SS_AFFINE || op.kind == SS_HIDDEN) {
+    float* out = op.kind == SS_AFFINE ? cx.act_out : cx.hid_out;
+    const int ldo = op.kind == SS_AFFINE ? lda : cx.ldh;
+#pragma unroll
+    for (int j = 0; j < JN; ++j) {
+      if (j < jn) {
+        const int n = tx + 16 * j;
+        const float b = bbuf[n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[i][j] + b;
+          if (op.kind == SS_HIDDEN) v = fmaxf(v, 0.f);
+          out[(ty * 4 + i) * ldo + n] = v;
+        }
+      }
+    }
+  } else if (op.kind == SS_COUPLING) {
+    // staged columns: [s of coordinates 0..Db16) | t of the same] (affine) or [t] (additive); this thread's
+    // coordinates are c = tx + 16 j
+    float* u_base = cx.actc + op.b_off;
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const int jh = op.affine ? (jn >> 1) : jn;    // column groups of one parameter
+    constexpr int JH = JN > 4 ? 4 : JN;           // (at most 64 coordinates = 4 groups)
+#pragma unroll
+    for (int j = 0; j < JH; ++j) {
+      if (j < jh) {
+        const int c = tx + 16 * j;
+        if (c < op.Db) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float* up = u_base + (ty * 4 + i) * lda + c;
+            const float u = *up;
+            if (op.affine) {
+              // the shift of coordinate group j is accumulator group j + jh (jh = 1 .. 4); indices kept in range
+              const float tj = jh == 1 ? acc[i][(j + 1) % JN]
+                                       : (jh == 2 ? acc[i][(j + 2) % JN] : (jh == 3 ? acc[i][(j + 3) % JN] : acc[i][(j + 4) % JN]));
+              const float t = tj + bbuf[jh * 16 + c];
+              const float ls = op.clamp * tanhf(acc[i][j] + bbuf[c]);
+              lsum[i] += ls;
+              *up = args.inverse ? (u - t) * expf(-ls) : fmaf(u, expf(ls), t);
+            } else {
+              const float t = acc[i][j] + bbuf[c];
+              *up = args.inverse ? u - t : u + t;
+            }
+          }
+        }
+      }
+    }
+    if (op.affine) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float s = half_warp_sum(lsum[i]);
+        if (tx == 0) cx.racc[ty * 4 + i] += args.inverse ? -s : s;   // one writer per row, fixed order: deterministic
+      }
+    }
+  } else {  // SS_FINAL: natural column order, optional store, optional base log-density
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int JF = JN > 4 ? 4 : JN;           // D <= 64
+#pragma unroll
+    for (int j = 0; j < JF; ++j) {
+      if (j < jn) {
+        const int n = tx + 16 * j;
+        if (n < args.D) {
+          const float b = bbuf[n], lc = cx.locs[n], is = cx.iscs[n];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = ty * 4 + i;
+            const float z = acc[i][j] + b;
+            if (args.out_y != nullptr && r < cx.nrows) args.out_y[(cx.row0 + r) * args.ldy + n] = z;
+            const float d = (z - lc) * is;
+            lsum[i] += args.base_kind == 0 ? -0.5f * d * d : -fabsf(d);
+          }
+        }
+      }
+    }
+    if (args.base_kind >= 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float s = half_warp_sum(lsum[i]);
+        if (tx == 0) cx.racc[ty * 4 + i] += s;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SS_THREADS, 2) usf_small_stack_kernel(const __grid_constant__ SsArgs args) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
@@ -205,118 +332,18 @@ __global__ void __launch_bounds__(SS_THREADS, 2) usf_small_stack_kernel(const __
       if (oi == 0) { in = xsel ? xb1 : xb0; ldi = args.ldxs; }
       else if (op.kind == SS_AFFINE || op.kind == SS_FINAL || op.first) in = actc;
       else { in = hp ? hid1 : hid0; ldi = ldh; }
-      const int jn = N16 >> 4;   // 16-column groups of this layer (<= 8), uniform over the CTA
-      float acc[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-      const float* arow = in + (ty * 4) * ldi;
-      const float* wrow = wbuf + tx * ldw;
-      for (int k = 0; k < K4; k += 4) {
-        float4 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * ldi + k);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < jn) {
-            const float4 w = *reinterpret_cast<const float4*>(wrow + j * 16 * ldw + k);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              acc[i][j] = fmaf(a[i].x, w.x, acc[i][j]);
-              acc[i][j] = fmaf(a[i].y, w.y, acc[i][j]);
-              acc[i][j] = fmaf(a[i].z, w.z, acc[i][j]);
-              acc[i][j] = fmaf(a[i].w, w.w, acc[i][j]);
-            }
-          }
-        }
-      }
-
-      if (op.kind == SS_AFFINE || op.kind == SS_HIDDEN) {
-        // (the first layer of a stack without affine run would read the input buffer: the compiler always emits one)
-        float* out = op.kind == SS_AFFINE ? (cur ? act0 : act1) : ((op.first || hp) ? hid0 : hid1);
-        const int ldo = op.kind == SS_AFFINE ? lda : ldh;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < jn) {
-            const int n = tx + 16 * j;
-            const float b = bbuf[n];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float v = acc[i][j] + b;
-              if (op.kind == SS_HIDDEN) v = fmaxf(v, 0.f);
-              out[(ty * 4 + i) * ldo + n] = v;
-            }
-          }
-        }
-        if (op.kind == SS_AFFINE) cur ^= 1;
-        else hp = (op.first || hp) ? 0 : 1;
-      } else if (op.kind == SS_COUPLING) {
-        // staged columns: [s of coordinates 0..Db16) | t of the same] (affine) or [t] (additive); this thread's
-        // coordinates are c = tx + 16 j
-        float* u_base = actc + op.b_off;
-        float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-        const int jh = op.affine ? (jn >> 1) : jn;    // column groups of one parameter
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < jh) {
-            const int c = tx + 16 * j;
-            if (c < op.Db) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float* up = u_base + (ty * 4 + i) * lda + c;
-                const float u = *up;
-                if (op.affine) {
-                  // the shift of coordinate group j is accumulator group j + jh (jh = 1 .. 4)
-                  const float tj = jh == 1 ? acc[i][(j + 1) & 7]
-                                           : (jh == 2 ? acc[i][(j + 2) & 7] : (jh == 3 ? acc[i][(j + 3) & 7] : acc[i][(j + 4) & 7]));
-                  const float t = tj + bbuf[jh * 16 + c];
-                  const float ls = op.clamp * tanhf(acc[i][j] + bbuf[c]);
-                  lsum[i] += ls;
-                  *up = args.inverse ? (u - t) * expf(-ls) : fmaf(u, expf(ls), t);
-                } else {
-                  const float t = acc[i][j] + bbuf[c];
-                  *up = args.inverse ? u - t : u + t;
-                }
-              }
-            }
-          }
-        }
-        if (op.affine) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float s = half_warp_sum(lsum[i]);
-            if (tx == 0) racc[ty * 4 + i] += args.inverse ? -s : s;   // one writer per row, fixed order: deterministic
-          }
-        }
-        hp = 0;
-      } else {  // SS_FINAL: natural column order, optional store, optional base log-density
-        float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < jn) {
-            const int n = tx + 16 * j;
-            if (n < args.D) {
-              const float b = bbuf[n], lc = locs[n], is = iscs[n];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int r = ty * 4 + i;
-                const float z = acc[i][j] + b;
-                if (args.out_y != nullptr && r < nrows) args.out_y[(row0 + r) * args.ldy + n] = z;
-                const float d = (z - lc) * is;
-                lsum[i] += args.base_kind == 0 ? -0.5f * d * d : -fabsf(d);
-              }
-            }
-          }
-        }
-        if (args.base_kind >= 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float s = half_warp_sum(lsum[i]);
-            if (tx == 0) racc[ty * 4 + i] += s;
-          }
-        }
-      }
+      // the layer itself, compiled for 1 / 2 / 4 / 8 column groups of 16 (a 6-wide layer must not pay for the 128-wide
+      // register tile: with one body predicated over 8 groups the tiny stacks were instruction-bound)
+      const int jn = N16 >> 4;
+      SsLayerCtx cx{in, ldi, wbuf, bbuf, ldw, K4, jn, actc, cur ? act0 : act1, (op.first || hp) ? hid0 : hid1, lda, ldh,
+                    racc, locs, iscs, row0, nrows, tx, ty};
+      if (jn <= 1) ss_layer<1>(args, op, cx);
+      else if (jn == 2) ss_layer<2>(args, op, cx);
+      else if (jn <= 4) ss_layer<4>(args, op, cx);
+      else ss_layer<8>(args, op, cx);
+      if (op.kind == SS_AFFINE) cur ^= 1;
+      else if (op.kind == SS_HIDDEN) hp = (op.first || hp) ? 0 : 1;
+      else if (op.kind == SS_COUPLING) hp = 0;
       sbuf ^= 1;
     }
     xsel ^= 1;

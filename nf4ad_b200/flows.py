@@ -202,6 +202,7 @@ class Flow(torch.nn.Module):
     BF16_CALIBRATION_TOL = 5e-3
     BF16_MIN_DIM = 128
     SMALL_MAX_DIM = 64
+    SMALL_MAX_ROWS = 8192       # (for stacks with layers wider than 32; see _small_ok)
     # the tensor-core tier that stands in for fp32 ("auto", and where bf16 is not trusted): bf16 (hi, lo) operand pairs.
     # Measured on every BASELINE shape with D >= 128 (scripts/bf16x2_check.py, profiles/r2/bf16x2.txt): log_prob max-row
     # error 5e-6 .. 2.8e-5 (3xTF32: 5e-6 .. 5.6e-5) at 2.0-2.5x the 3xTF32 rate (C2: 3.39 vs 6.66 ms per 65536 rows).
@@ -212,10 +213,10 @@ class Flow(torch.nn.Module):
     def _small_ok(self, device, rows=None):
         """Does the one-kernel path take this stack (both directions share the shapes), and does it pay at this batch
         size?  Measured against the split-operand tensor-core chain (scripts/bench_small.py, profiles/r2/small_stack.txt):
-        one kernel instead of 11 launches wins at every batch size while the layers are at most 32 wide (D = 6: 1.05-1.3x,
-        D = 20: 1.0-1.2x).  With 64-128 wide layers its fp32 FFMA arithmetic (paced by shared-memory reads) loses to
-        the tensor cores from a few thousand rows on (0.3-0.4x at 65536 rows), so it is kept for batches of up to 1024
-        rows, where a call is host-bound either way and one launch means the lowest latency and a deterministic sum."""
+        one kernel instead of 11 launches wins at every batch size while the layers are at most 32 wide (D = 6: 1.6-1.8x,
+        D = 20: 1.5x from 65536 rows on).  With 64-128 wide layers its fp32 FFMA arithmetic (paced by shared-memory reads)
+        loses to the tensor cores beyond 8192 rows (0.4-0.6x at 65536 rows), so there it is kept for batches of up to
+        8192 rows, where it is 1.03-1.17x and one launch means the lowest latency and a deterministic sum."""
         if self.event_dim + self.context_dim() > self.SMALL_MAX_DIM or len(self.event_shape) != 1:
             return False
         key = self._weights_key()
@@ -234,7 +235,7 @@ class Flow(torch.nn.Module):
         _, eligible, widest = hit
         if not eligible:
             return False
-        return rows is None or self.SMALL_ALWAYS or rows <= 1024 or widest <= 32
+        return rows is None or self.SMALL_ALWAYS or rows <= self.SMALL_MAX_ROWS or widest <= 32
 
     def _tier(self, x2=None, context_rows=None):
         want = self.precision
