@@ -20,8 +20,8 @@ import torch
 
 from . import _lib, ops, stack
 from .transforms import (
-    BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform, MaskedAffineCoupling,
-    MaskedCoupling, ScaleTransform, SequentialAffineTransform, context_dim, coupling_apply,
+    BaseTransform, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform, MaskedAffineCoupling,
+    MaskedCoupling, ScaleTransform, SequentialAffineTransform, composing, context_dim, coupling_apply,
 )
 
 def _on_device(method):
@@ -85,6 +85,8 @@ class Flow(torch.nn.Module):
         # run-to-run bit-identical log_prob (the reference's eager CPU path is deterministic): per-row partial sums go to
         # slots that are added in a fixed order instead of fp32 atomics (usf_set_deterministic).  Costs one small launch.
         self.deterministic = os.environ.get("USF_DETERMINISTIC", "0") == "1"
+        # tensor-core training: compose the affine runs between couplings in weight space (`_compose_affine_runs`)
+        self.compose_affine = os.environ.get("USF_COMPOSE_AFFINE", "1") != "0"
         self.last_launches = 0                  # kernels enqueued by the last fused call
         self._compiled = {}
         self._key_slots = None
@@ -403,16 +405,7 @@ class Flow(torch.nn.Module):
         if not y.is_cuda or B < 8 or B % 8 or len(mods) < 2:
             return
         cur = torch.cuda.current_stream(y.device)
-        streams = self.__dict__.get("_side_streams")
-        if streams is None or streams[0].device != y.device:
-            streams = [torch.cuda.Stream(device=y.device) for _ in range(8)]
-            self.__dict__["_side_streams"] = streams
-            # the factor gradients are produced on the side streams on purpose; autograd syncs them with the
-            # accumulation stream, it only warns that this costs a synchronisation
-            warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-            if warn_off is not None:
-                warn_off(False)
-        used = streams[:min(len(streams), len(mods))]
+        used = self._side(y.device, len(mods))
         for s in used:
             s.wait_stream(cur)
         # in the order the pass will need them (it walks the layers backwards); each consumer joins only its own stream
@@ -423,22 +416,129 @@ class Flow(torch.nn.Module):
             A.record_stream(cur)
             lu.__dict__["_A_pre"] = (A, st)
 
+    _PROBES = {}                 # (device, D) -> (I_D, 8 zero rows): what an affine run is composed on
+
+    def _side(self, device, n):
+        """`n` (at most 16) side streams of this flow; the pool only ever holds streams a pass has forked into, so a
+        trainer that joins "all of the flow's side streams" never waits on one outside a capture."""
+        n = max(1, min(16, n))
+        streams = self.__dict__.get("_side_streams")
+        if streams is None or streams[0].device != device:
+            streams = self.__dict__["_side_streams"] = []
+            # the factor gradients are produced on the side streams on purpose; autograd syncs them with the
+            # accumulation stream, it only warns that this costs a synchronisation
+            warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if warn_off is not None:
+                warn_off(False)
+        while len(streams) < n:
+            streams.append(torch.cuda.Stream(device=device))
+        return streams[:n]
+
+    def _compose_affine_runs(self, y):
+        """Mixed-precision training: every maximal run of affine layers between two couplings (LU solve / product,
+        Householder reflections, scale -- with affine conjugation the tail of one block and the head of the next) is a
+        single map x -> x M^T + c that does not depend on the data.  Each run is evaluated ONCE per step in weight space:
+        its layers are applied, with autograd, to probe rows on a side stream (M^T = the identity through the linear parts,
+        c = the image of 0, the parameter-only log-dets summed there too), and the batch then sees ONE tensor-core GEMM per
+        run instead of a GEMM / reflection / scale kernel per layer.  The runs are independent of each other, so their
+        chains -- forward here, backward wherever autograd reaches them: a node's backward runs on its forward's
+        stream -- overlap each other and the batch-sized chain.  -> (plan, {id(run): (M^T, c, log-det, stream)})."""
+        plan, run = [], []
+        for layer in reversed(self.layers):
+            if isinstance(layer, BaseTransform) and getattr(layer, "is_affine", False) and not stack._is_coupling(layer):
+                run.append(layer)
+                continue
+            if run:
+                plan.append(run)
+                run = []
+            plan.append(layer)
+        if run:
+            plan.append(run)
+        B, D = y.shape[0], y.shape[-1]
+        composed = {}
+        if not (y.is_cuda and y.dim() == 2 and B >= 8 and B % 8 == 0 and D % 16 == 0 and getattr(self, "compose_affine", True)):
+            return plan, composed
+        runs = [r for r in plan if isinstance(r, list)
+                and any(isinstance(m, LUTransform) for layer in r for m in layer.modules())]
+        if not runs:
+            return plan, composed
+        dev = y.device
+        probes = Flow._PROBES.get((dev, D))
+        if probes is None:
+            probes = Flow._PROBES[(dev, D)] = (torch.eye(D, device=dev, dtype=torch.float32),
+                                               torch.zeros(8, D, device=dev, dtype=torch.float32))
+        cur = torch.cuda.current_stream(dev)
+        # A parameter's gradient accumulator runs on the stream that is current when the parameter first enters a graph,
+        # and autograd sums the contributions of different nodes there.  Every affine layer sits in TWO runs (tail of
+        # one, head of the next): were the accumulator created inside a run, the partial sums of the neighbouring
+        # run's gradients would be queued on this run's stream ahead of its own backward chain -- and the nine chains
+        # would execute one after the other (measured: a 2.1 ms tail).  So the accumulators are created here, on the
+        # calling stream; the graphs built below keep them alive.
+        pin = [p.view_as(p) for r in runs for layer in r for p in layer.parameters() if p.requires_grad]
+        used = self._side(dev, len(runs))
+        for st in used:
+            st.wait_stream(cur)
+        for i, r in enumerate(runs):
+            st = used[i % len(used)]
+            with torch.cuda.stream(st), composing() as comp:
+                # the matrix: the identity through the run's linear parts (shifts off -- taking them from the same rows
+                # and subtracting would make every shift gradient a difference of D bf16-rounded sums) ...
+                comp["linear_only"] = True
+                Mt = probes[0]
+                for layer in r:
+                    Mt = layer.backward(Mt)
+                # ... and the shift: the zero row through the full maps (8 rows: the GEMM's row granularity)
+                comp["linear_only"] = False
+                z, const = probes[1], None
+                for layer in r:
+                    nxt = layer.backward(z)
+                    l = layer.log_abs_det_jacobian(nxt, z)
+                    if torch.is_tensor(l) and l.dim() > 0:
+                        const = False                      # a data-dependent log-det: not an affine run after all
+                        break
+                    l = torch.as_tensor(l, device=dev, dtype=torch.float32)
+                    const = l if const is None else const + l
+                    z = nxt
+                if const is False:
+                    continue
+                c = z[0]
+            for t in (Mt, c, const):
+                t.record_stream(cur)
+            composed[id(r)] = (Mt, c, const, st)
+        del pin
+        return plan, composed
+
     def _inverse_layers(self, y, context=None):
         """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""
-        if ops.tc_train_enabled():
+        if ops.tc_train_enabled() and y.dim() == 2:
+            plan, composed = self._compose_affine_runs(y)
+        else:
+            plan, composed = list(reversed(self.layers)), {}
+        if ops.tc_train_enabled() and not composed:
             self._prefetch_lu_inverses(y)
         total = torch.zeros(y.shape[0], device=y.device, dtype=torch.float32)
-        for layer in reversed(self.layers):
-            if hasattr(layer, "inverse_and_ladj"):
-                x, ladj = layer.inverse_and_ladj(y, context)
-            elif stack._is_coupling(layer):
-                # a foreign coupling class (the reference's own MaskedAffineCoupling): same arithmetic, our kernels
-                x, ladj = coupling_apply(layer, y, True, context)
-            else:
-                x = layer.backward(y) if context is None else layer.backward(y, context)
-                ladj = layer.log_abs_det_jacobian(x, y)
-            total = total - ladj
-            y = x
+        consts = []
+        for item in plan:
+            hit = composed.get(id(item)) if isinstance(item, list) else None
+            if hit is not None:
+                Mt, c, const, st = hit
+                torch.cuda.current_stream(y.device).wait_stream(st)
+                y = ops.linear_fn(y, Mt, c, False, w_transposed=True)
+                consts.append(const)
+                continue
+            for layer in (item if isinstance(item, list) else (item,)):
+                if hasattr(layer, "inverse_and_ladj"):
+                    x, ladj = layer.inverse_and_ladj(y, context)
+                elif stack._is_coupling(layer):
+                    # a foreign coupling class (the reference's own MaskedAffineCoupling): same arithmetic, our kernels
+                    x, ladj = coupling_apply(layer, y, True, context)
+                else:
+                    x = layer.backward(y) if context is None else layer.backward(y, context)
+                    ladj = layer.log_abs_det_jacobian(x, y)
+                total = total - ladj
+                y = x
+        if consts:
+            total = total - torch.stack(consts).sum()
         return y, total
 
     def _forward_layers(self, z, context=None):

@@ -231,17 +231,19 @@ def tc_train_enabled():
     return _TC_TRAIN != 0
 
 
-def linear_fn(x, W, bias, relu=False):
+def linear_fn(x, W, bias, relu=False, w_transposed=False):
     """Autograd linear layer: tensor-core (bf16) GEMMs in mixed-precision training when the shapes allow TMA operands
-    (N, K multiples of 16, batch multiple of 8), else the fp32 kernels."""
+    (N, K multiples of 16, batch multiple of 8), else the fp32 kernels.  `w_transposed`: `W` holds the map's transpose
+    (K, N) -- y = x W + bias -- which is how a composed affine run arrives (`Flow._compose_affine_runs`); its gradient
+    comes back in the same layout."""
     if _TC_TRAIN and x.is_cuda and x.dim() == 2 and x.shape[0] % 8 == 0 and x.shape[0] >= 8 \
             and W.shape[0] % 16 == 0 and W.shape[1] % 16 == 0:
         if _TC_TRAIN == 2:
             if x.shape[0] >= 256:        # below that the fp32 split-K kernels are as fast
-                return LinearT3Fn.apply(x, W, bias, relu)
-            return LinearFn.apply(x, W, bias, relu)
-        return LinearTCFn.apply(x, W, bias, relu)
-    return LinearFn.apply(x, W, bias, relu)
+                return LinearT3Fn.apply(x, W, bias, relu, w_transposed)
+        else:
+            return LinearTCFn.apply(x, W, bias, relu, w_transposed)
+    return LinearFn.apply(x, W.t() if w_transposed else W, bias, relu)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -291,9 +293,12 @@ def _overlapped_wgrad(fn, operands):
         return fn()
     dev = operands[0].device
     cur = torch.cuda.current_stream(dev)
-    side = _WGRAD_STREAMS.get(dev.index)
+    # one partner stream per calling stream: the weight-space chains of different affine runs (each on its own side
+    # stream) must not meet on a shared one -- every fork / join there would order them after each other
+    key = (dev.index, cur.cuda_stream)
+    side = _WGRAD_STREAMS.get(key)
     if side is None:
-        side = _WGRAD_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        side = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         out = fn()
@@ -313,14 +318,17 @@ class LinearTCFn(torch.autograd.Function):
     gating and the bias gradient)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, relu):
+    def forward(ctx, x, W, bias, relu, wt=False):
         B, K = x.shape
-        N = W.shape[0]
+        N = W.shape[1] if wt else W.shape[0]
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         xb, xT, _ = to_bf16(x, want_rows=True, want_transposed=need_w)
-        Wb, WT, _ = to_bf16(W, want_rows=True, want_transposed=need_x)
+        if wt:       # W^T (K, N) given: its rows are the dgrad operand, its transpose the forward operand
+            WT, Wb, _ = to_bf16(W, want_rows=need_x, want_transposed=True)
+        else:
+            Wb, WT, _ = to_bf16(W, want_rows=True, want_transposed=need_x)
         y = gemm_bf16(xb, Wb, B, N, K, bias, relu)
-        ctx.relu, ctx.has_bias, ctx.shape = bool(relu), bias is not None, (B, N, K)
+        ctx.relu, ctx.has_bias, ctx.shape, ctx.wt = bool(relu), bias is not None, (B, N, K), bool(wt)
         ctx.save_for_backward(xT, WT, y if relu else None)
         return y
 
@@ -331,29 +339,34 @@ class LinearTCFn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         dyb, dyT, db = to_bf16(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
                                want_colsum=need_b)
+        # dW = dy^T x (N, K), or in the transposed layout d(W^T) = x^T dy (K, N)
+        wgrad = (lambda: gemm_bf16(xT, dyT, K, N, B)) if ctx.wt else (lambda: gemm_bf16(dyT, xT, N, K, B))
         join = None
         if need_w and need_x and _WGRAD_OVERLAP:
-            dW, join = _overlapped_wgrad(lambda: gemm_bf16(dyT, xT, N, K, B), (dyT, xT))
+            dW, join = _overlapped_wgrad(wgrad, (dyT, xT))
         else:
-            dW = gemm_bf16(dyT, xT, N, K, B) if need_w else None
+            dW = wgrad() if need_w else None
         dx = gemm_bf16(dyb, WT, B, K, N) if need_x else None
         if join is not None:
             torch.cuda.current_stream(dy.device).wait_stream(join)
-        return dx, dW, db, None
+        return dx, dW, db, None, None
 
 
 class LinearT3Fn(torch.autograd.Function):
     """LinearTCFn with 3xTF32 GEMMs: fp32-grade forward / dgrad / wgrad on the tensor cores."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, relu):
+    def forward(ctx, x, W, bias, relu, wt=False):
         B, K = x.shape
-        N = W.shape[0]
+        N = W.shape[1] if wt else W.shape[0]
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         xr, xT, _ = to_t3(x, want_rows=True, want_transposed=need_w)
-        Wr, WT, _ = to_t3(W, want_rows=True, want_transposed=need_x)
+        if wt:
+            WT, Wr, _ = to_t3(W, want_rows=need_x, want_transposed=True)
+        else:
+            Wr, WT, _ = to_t3(W, want_rows=True, want_transposed=need_x)
         y = gemm_t3(xr, Wr, B, N, K, bias, relu)
-        ctx.relu, ctx.has_bias, ctx.shape = bool(relu), bias is not None, (B, N, K)
+        ctx.relu, ctx.has_bias, ctx.shape, ctx.wt = bool(relu), bias is not None, (B, N, K), bool(wt)
         ctx.save_for_backward(xT[0], xT[1], WT[0], WT[1], y if relu else None)
         return y
 
@@ -364,15 +377,16 @@ class LinearT3Fn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         dyr, dyT, db = to_t3(dy, relu_mask=y if ctx.relu else None, want_rows=need_x, want_transposed=need_w,
                              want_colsum=need_b)
+        wgrad = (lambda: gemm_t3((xTh, xTl), dyT, K, N, B)) if ctx.wt else (lambda: gemm_t3(dyT, (xTh, xTl), N, K, B))
         join = None
         if need_w and need_x and _WGRAD_OVERLAP:
-            dW, join = _overlapped_wgrad(lambda: gemm_t3(dyT, (xTh, xTl), N, K, B), (dyT[0], dyT[1], xTh, xTl))
+            dW, join = _overlapped_wgrad(wgrad, (dyT[0], dyT[1], xTh, xTl))
         else:
-            dW = gemm_t3(dyT, (xTh, xTl), N, K, B) if need_w else None
+            dW = wgrad() if need_w else None
         dx = gemm_t3(dyr, (WTh, WTl), B, K, N) if need_x else None
         if join is not None:
             torch.cuda.current_stream(dy.device).wait_stream(join)
-        return dx, dW, db, None
+        return dx, dW, db, None, None
 
 
 class LUInverseFn(torch.autograd.Function):
@@ -581,6 +595,39 @@ class CouplingFn(torch.autograd.Function):
                                      ctx.clamp, int(ctx.inverse), ctx.act, ptr(dx), D, ptr(ds), D, ptr(dt), D, B, D, stream()),
               "usf_coupling_bwd")
         return dx, ds, dt, None, None, None, None
+
+
+class CouplingPackedFn(torch.autograd.Function):
+    """`CouplingFn` for a conditioner output that is ONE `[s | t]` tensor (B, 2 D): the kernels read the two halves in
+    place and the backward pass writes `d[s | t]` as one tensor -- no slice / zero-fill / copy / add nodes around it."""
+
+    @staticmethod
+    def forward(ctx, x, st, mask, clamp, inverse, act=0):
+        D = x.shape[1]
+        st, _ = _rows(st)
+        y, ladj = coupling(x, st[:, :D], st[:, D:], mask, clamp, inverse, act)
+        ctx.clamp, ctx.inverse, ctx.act = float(clamp), bool(inverse), int(act)
+        ctx.save_for_backward(x, st, mask)
+        return y, ladj
+
+    @staticmethod
+    def backward(ctx, dy, dladj):
+        x, st, mask = ctx.saved_tensors
+        B, D = x.shape
+        dev = x.device
+        dy = torch.zeros(B, D, device=dev, dtype=torch.float32) if dy is None else dy
+        dy, lddy = _rows(dy)
+        x, ldx = _rows(x)
+        ldst = st.stride(0) if B > 1 else 2 * D
+        s, t = st[:, :D], st[:, D:]
+        m = f32c(mask).reshape(-1).contiguous()
+        dl = f32c(dladj).contiguous() if dladj is not None else None
+        dx = torch.empty(B, D, device=dev, dtype=torch.float32)
+        dst = torch.empty(B, 2 * D, device=dev, dtype=torch.float32)
+        check(lib().usf_coupling_bwd(ptr(dy), lddy, ptr(dl), 1.0, ptr(x), ldx, ptr(s), ldst, ptr(t), ldst, ptr(m),
+                                     ctx.clamp, int(ctx.inverse), ctx.act, ptr(dx), D, ptr(dst[:, :D]), 2 * D,
+                                     ptr(dst[:, D:]), 2 * D, B, D, stream()), "usf_coupling_bwd")
+        return dx, dst, None, None, None, None
 
 
 class BaseLogProbFn(torch.autograd.Function):

@@ -441,7 +441,7 @@ class DataParallelTrainer:
             dev = chunk.device
             waits = {torch.cuda.current_stream(dev), self._main_stream}
             waits.update(getattr(self.flow, "_side_streams", None) or [])
-            waits.update(st for i, st in ops._WGRAD_STREAMS.items() if i == dev.index)
+            waits.update(st for (i, _), st in ops._WGRAD_STREAMS.items() if i == dev.index)
             for st in waits:
                 if st is not None:
                     self._comm_stream.wait_stream(st)
@@ -535,7 +535,10 @@ class DataParallelTrainer:
 
     def _capture(self, batch):
         static_x = batch.detach().clone()
-        graph = torch.cuda.CUDAGraph()
+        dot = os.environ.get("USF_GRAPH_DOT")        # debugging: dump the captured step's node / edge list (Graphviz)
+        graph = torch.cuda.CUDAGraph(keep_graph=True) if dot else torch.cuda.CUDAGraph()
+        if dot:
+            graph.enable_debug_mode()
         if self._flat is None:
             self.opt.zero_grad(set_to_none=True)
         # thread_local: NCCL's watchdog thread may query events while this thread captures
@@ -549,6 +552,8 @@ class DataParallelTrainer:
                 self._clip()
             self.opt.step()
             static_loss = loss.detach()
+        if dot:
+            graph.debug_dump(dot)
         return graph, static_x, static_loss
 
     def _hyper_sig(self):

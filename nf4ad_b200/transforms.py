@@ -109,6 +109,25 @@ class BaseTransform(TransformModule):
     is_affine = False
 
 
+# Set while `Flow._compose_affine_runs` evaluates an affine run on probe rows: "linear_only" drops the shifts (the probe
+# rows are the identity: the run's matrix), "A" / "W" share a layer's dense inverse / factor product between the
+# matrix pass and the shift pass of one composition.
+_COMPOSE = None
+
+
+class composing:
+    def __enter__(self):
+        global _COMPOSE
+        self.prev = _COMPOSE
+        _COMPOSE = {"linear_only": False, "A": {}, "W": {}}
+        return _COMPOSE
+
+    def __exit__(self, *exc):
+        global _COMPOSE
+        _COMPOSE = self.prev
+        return False
+
+
 class LUTransform(BaseTransform):
     """`LUTransform(dim, prior_scale)` (call sites `nf4ad/flows.py:85,110`).
 
@@ -141,11 +160,19 @@ class LUTransform(BaseTransform):
 
     @property
     def weight(self):
+        comp = _COMPOSE
+        if comp is not None:                                  # one product per layer per composition
+            W = comp["W"].get(id(self))
+            if W is None:
+                W = comp["W"][id(self)] = ops.LUPackFn.apply(self.L_raw, self.U_raw)
+            return W
         return ops.LUPackFn.apply(self.L_raw, self.U_raw)
 
     def forward(self, x, context=None):
         x2, squeeze = _as2d(x)
-        y = ops.linear_fn(x2, self.weight, self.bias, False)
+        comp = _COMPOSE
+        bias = None if (comp is not None and comp["linear_only"]) else self.bias
+        y = ops.linear_fn(x2, self.weight, bias, False)
         return _restore(y, squeeze)
 
     def backward(self, y, context=None):
@@ -153,12 +180,19 @@ class LUTransform(BaseTransform):
         if ops.tc_train_enabled() and y2.is_cuda and self.dim % 16 == 0 and y2.shape[0] % 8 == 0 and y2.shape[0] >= 8:
             # mixed-precision training: x = A (y - b) with the dense inverse A = (LU)^{-1} (one weight-space solve per
             # step) applied by a tensor-core GEMM; the shift -A b is a weight-space matrix-vector product
+            comp = _COMPOSE
             pre = self.__dict__.pop("_A_pre", None)      # issued up front by Flow._prefetch_lu_inverses
-            if pre is not None:
+            if comp is not None and id(self) in comp["A"]:
+                A = comp["A"][id(self)]
+            elif pre is not None:
                 A, side = pre
                 torch.cuda.current_stream(y2.device).wait_stream(side)
             else:
                 A = ops.LUInverseFn.apply(self.L_raw, self.U_raw)
+            if comp is not None:
+                comp["A"][id(self)] = A
+                if comp["linear_only"]:
+                    return _restore(ops.linear_fn(y2, A, None, False), squeeze)
             # the shift -A b through the library's own GEMM (a 1 x D x D product; no cuBLAS call on the training path)
             shift = ops.LinearFn.apply(self.bias.unsqueeze(0), A, None, False).squeeze(0)
             x = ops.linear_fn(y2, A, -shift, False)
@@ -472,6 +506,11 @@ def coupling_apply(layer, v, inverse, context=None, additive=False):
     else:                                   # image-shaped event: the conditioner sees (B, C, H, W)
         vmb = vm.reshape(vb.shape)
         params = layer.conditioner(vmb) if context is None else layer.conditioner(vmb, context)
+    if not additive and vb.dim() == 2 and torch.is_tensor(params) and params.dim() == 2 and v2.is_cuda \
+            and params.shape == (B, 2 * v2.shape[1]) and params.dtype == v2.dtype == torch.float32:
+        # ONE [s | t] tensor (`_parse_params`' 2C form on flat rows): read in place, gradient written as one tensor
+        out, ladj = ops.CouplingPackedFn.apply(v2, params, m, float(getattr(layer, "clamp", 5.0)), inverse, act)
+        return _restore(out.reshape(vb.shape), how), ladj
     if additive:
         t = params[-1] if isinstance(params, (tuple, list)) else params
         s, t = None, t.to(vb.dtype)
