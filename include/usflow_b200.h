@@ -51,6 +51,13 @@ int usf_version(void);
 const char* usf_last_error(void);
 /* 1 if a CUDA device with compute capability 10.x is usable by this process, else 0. */
 int usf_device_ok(void);
+/* A new non-blocking stream on the current device (and its release).  The host side forks the weight-space work of a
+ * training step (one chain per affine run, `Flow._compose_affine_runs`) onto ~20 streams that must be DISTINCT: a
+ * framework-level stream pool that hands the same stream out twice would order two chains after each other.
+ * priority: 0 = default, negative = more urgent (clamped to the device's range): the batch-sized chain of the step runs
+ * above the weight-space chains, and those in the order the batch will need them. */
+int usf_stream_create(int priority, usf_stream_t* out);
+int usf_stream_destroy(usf_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* Layer kernels (fp32).  One entry point per bijector of the BaseTransform   */
@@ -78,6 +85,15 @@ int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, const float* U
                  int transpose, float* x, int64_t ldx, int64_t B, int64_t D,
                  float* scratch /* usf_lu_solve_scratch_floats(D) floats, or NULL for the slow generic kernel */,
                  usf_stream_t stream);
+
+/* A = (L U)^{-1}, dense row-major D x D, from the raw factors (L = unit lower triangle of L_raw, U = upper triangle of
+ * U_raw): what mixed-precision training applies to the batch by a GEMM instead of solving per row
+ * (`LUTransform.backward`, nf4ad/flows.py:85,110 call sites).  The two triangular inverses run in one launch (identity
+ * right-hand sides, half the work of a solve each), the product on the fp32 GEMM -- or, with A == NULL, left to the
+ * caller: U^{-1} is then at scratch[0 .. D^2), L^{-1} at scratch[D^2 .. 2 D^2) (row-major).
+ * scratch: usf_lu_inverse_scratch_floats(D) floats (0 = D not supported: use usf_lu_solve on the identity). */
+int64_t usf_lu_inverse_scratch_floats(int64_t D);
+int usf_lu_inverse(const float* L_raw, const float* U_raw, int64_t D, float* A, float* scratch, usf_stream_t stream);
 int64_t usf_lu_solve_scratch_floats(int64_t D);
 
 /* Product of nvs Householder reflections H_v = I - 2 v v^T/|v|^2, applied in storage

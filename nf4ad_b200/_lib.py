@@ -41,8 +41,12 @@ _PROTOS = {
     "usf_version": (_int, []),
     "usf_last_error": (C.c_char_p, []),
     "usf_device_ok": (_int, []),
+    "usf_stream_create": (_int, [_int, C.POINTER(_vp)]),
+    "usf_stream_destroy": (_int, [_vp]),
     "usf_lu_pack": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "usf_linear": (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "usf_lu_inverse_scratch_floats": (_i64, [_i64]),
+    "usf_lu_inverse": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "usf_lu_solve": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _vp, _i64, _i64, _i64, _vp, _vp]),
     "usf_lu_solve_scratch_floats": (_i64, [_i64]),
     "usf_householder": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
@@ -146,6 +150,18 @@ def require_cuda(*tensors):
 
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def new_stream(device, priority=0):
+    """A stream of its own on `device` (torch's `Stream()` hands out a pool of 32 per device round-robin: the ~20 side
+    streams of a training step plus whatever else the process created would alias, and two aliased chains run one after
+    the other).  `priority`: 0 default, negative = more urgent.  Wrapped as an `ExternalStream`; lives as long as the
+    process."""
+    device = torch.device(device)
+    handle = _vp()
+    with torch.cuda.device(device):
+        check(lib().usf_stream_create(int(priority), C.byref(handle)), "usf_stream_create")
+    return torch.cuda.ExternalStream(handle.value, device=device)
 
 
 def stream():

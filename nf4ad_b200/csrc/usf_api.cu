@@ -142,6 +142,23 @@ int plan_stack(const usf_stack_desc* st, int64_t rows, int precision, StackPlan*
 using namespace usf;
 
 extern "C" int usf_version(void) { return USF_VERSION; }
+
+extern "C" int usf_stream_create(int priority, usf_stream_t* out) {
+  USF_CHECK_ARG(out != nullptr, "usf_stream_create: null output");
+  int least = 0, greatest = 0;          // numerically: greatest priority <= least priority
+  USF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  if (priority < greatest) priority = greatest;
+  if (priority > least) priority = least;
+  cudaStream_t s = nullptr;
+  USF_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority));
+  *out = reinterpret_cast<usf_stream_t>(s);
+  return USF_OK;
+}
+
+extern "C" int usf_stream_destroy(usf_stream_t stream) {
+  if (stream != nullptr) USF_CUDA(cudaStreamDestroy(reinterpret_cast<cudaStream_t>(stream)));
+  return USF_OK;
+}
 extern "C" const char* usf_last_error(void) { return g_err; }
 
 extern "C" int usf_device_ok(void) {

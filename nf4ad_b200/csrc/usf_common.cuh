@@ -124,6 +124,8 @@ int64_t trsm_fast_scratch_floats(int64_t D);
 bool trsm_fast_supported(int64_t D);
 int trsm_rows_fast(const float* T, int64_t D, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr,
                    const float* bias, float* X, int64_t ldx, int64_t B, float* scratch, cudaStream_t stream);
+int64_t lu_inverse_scratch_floats(int64_t D);
+int lu_inverse(const float* L_raw, const float* U_raw, int64_t D, float* A, float* scratch, cudaStream_t stream);
 int tc_timeout_flag(int* out, int reset);
 int tc_trace_ctl(int on, unsigned long long* out, int max_records);
 int trsm_rows(const float* T, int64_t D, bool lower, bool unit, bool trans, const float* rhs, int64_t ldr,

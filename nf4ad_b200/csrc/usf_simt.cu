@@ -1274,6 +1274,17 @@ extern "C" int usf_lu_solve(const float* y, int64_t ldy, const float* L_raw, con
   return solve(L_raw, false, true, true, x, ldx, nullptr);
 }
 
+extern "C" int64_t usf_lu_inverse_scratch_floats(int64_t D) {
+  return D > 0 && trsm_fast_supported(D) ? lu_inverse_scratch_floats(D) : 0;
+}
+
+extern "C" int usf_lu_inverse(const float* L_raw, const float* U_raw, int64_t D, float* A, float* scratch,
+                              usf_stream_t stream) {
+  USF_CHECK_ARG(L_raw && U_raw && scratch && D > 0, "usf_lu_inverse: null pointer or bad size");
+  USF_CHECK_ARG(trsm_fast_supported(D), "usf_lu_inverse: D too large for the resident solve (use usf_lu_solve)");
+  return lu_inverse(L_raw, U_raw, D, A, scratch, as_stream(stream));
+}
+
 extern "C" int usf_householder(const float* x, int64_t ldx, const float* V, int64_t nvs, int reverse, float* y,
                                int64_t ldy, int64_t B, int64_t D, usf_stream_t stream) {
   USF_CHECK_ARG(x && y && (V || nvs == 0) && D > 0 && B >= 0 && nvs >= 0, "usf_householder: bad arguments");

@@ -29,8 +29,7 @@ __device__ __forceinline__ float tri_elem(const float* __restrict__ T, int64_t D
 
 // Dinv[jb][r][c] = (E_jj)^{-1}[r][c] for every diagonal block jb (identity-padded past D).
 template <bool LOWER, bool UNIT, bool TRANS>
-__global__ void __launch_bounds__(NB)
-usf_tri_diag_inv_kernel(const float* __restrict__ T, int64_t D, float* __restrict__ Dinv) {
+__device__ __forceinline__ void tri_diag_inv_body(const float* __restrict__ T, int64_t D, float* __restrict__ Dinv) {
   __shared__ float Es[NB][NB + 1];
   __shared__ float Ys[NB][NB + 1];   // Ys[row][col] = inverse
   const int jb = blockIdx.x, c = threadIdx.x;
@@ -64,14 +63,31 @@ usf_tri_diag_inv_kernel(const float* __restrict__ T, int64_t D, float* __restric
   for (int r = 0; r < NB; ++r) Dinv[((int64_t)jb * NB + r) * NB + c] = Ys[r][c];
 }
 
+template <bool LOWER, bool UNIT, bool TRANS>
+__global__ void __launch_bounds__(NB)
+usf_tri_diag_inv_kernel(const float* __restrict__ T, int64_t D, float* __restrict__ Dinv) {
+  tri_diag_inv_body<LOWER, UNIT, TRANS>(T, D, Dinv);
+}
+
+// Both factors of an LU pair at once (usf_lu_inverse): y = 0 -> U^T (lower, non-unit), y = 1 -> L^T (upper, unit).
+__global__ void __launch_bounds__(NB)
+usf_lu_diag_inv_kernel(const float* __restrict__ L_raw, const float* __restrict__ U_raw, int64_t D,
+                       float* __restrict__ DinvU, float* __restrict__ DinvL) {
+  if (blockIdx.y == 0) tri_diag_inv_body<true, false, true>(U_raw, D, DinvU);
+  else tri_diag_inv_body<false, true, true>(L_raw, D, DinvL);
+}
+
 constexpr int KC = 128;         // k-chunk streamed per iteration (4 column blocks): amortises the L2 latency of E tiles
 constexpr int KP = KC + 4;      // smem pitch of the E chunk (plain: 16-byte aligned rows for float4 reads)
 constexpr int KPT = KC + 5;     // transposed source: odd pitch keeps the transposing stores conflict-free (scalar reads)
 
-template <bool LOWER, bool TRANS>
-__global__ void __launch_bounds__(THREADS)
-usf_trsm_fast_kernel(const float* __restrict__ T, int64_t D, int Dp, const float* __restrict__ Dinv,
-                     const float* rhs, int64_t ldr, const float* __restrict__ bias, float* X, int64_t ldx, int64_t B) {
+// IDENT: the right-hand sides are the rows of the identity (X = E^{-T} row by row, i.e. the inverse of a triangular
+// matrix).  Row r of the solution then vanishes before (LOWER) / after (upper) column r, so a CTA skips the column
+// blocks on that side of its own rows and starts every accumulation at them: half the work of a dense solve.
+template <bool LOWER, bool TRANS, bool IDENT>
+__device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int64_t D, int Dp,
+                                               const float* __restrict__ Dinv, const float* rhs, int64_t ldr,
+                                               const float* __restrict__ bias, float* X, int64_t ldx, int64_t B) {
   extern __shared__ __align__(16) float sm[];
   float* Xs = sm;                                                                       // [ROWS][Dp]
   constexpr int PITCH = TRANS ? KPT : KP;
@@ -90,7 +106,9 @@ usf_trsm_fast_kernel(const float* __restrict__ T, int64_t D, int Dp, const float
     const int r = e / Dp, k = e - r * Dp;
     const int64_t gr = r0 + r;
     float v = 0.f;
-    if (gr < B && k < D) {
+    if (IDENT) {
+      v = (gr < B && gr == k) ? 1.f : 0.f;
+    } else if (gr < B && k < D) {
       v = rhs[gr * ldr + k];
       if (bias != nullptr) v -= bias[k];
     }
@@ -120,11 +138,13 @@ usf_trsm_fast_kernel(const float* __restrict__ T, int64_t D, int Dp, const float
     }
   };
 
+  const int own = (int)blockIdx.x;                 // (ROWS == NB: the column block of this CTA's own rows)
   for (int step = 0; step < nblk; ++step) {
     const int jb = LOWER ? step : nblk - 1 - step;
+    if (IDENT && (LOWER ? jb < own : jb > own)) continue;      // still zero there (uniform over the CTA)
     // solved column range feeding block jb
-    const int lo = LOWER ? 0 : (jb + 1) * NB;
-    const int hi = LOWER ? jb * NB : Dp;
+    const int lo = LOWER ? (IDENT ? own * NB : 0) : (jb + 1) * NB;
+    const int hi = LOWER ? jb * NB : (IDENT ? (own + 1) * NB : Dp);
     const int nchunk = (hi - lo + KC - 1) / KC;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float reg[16];
@@ -204,6 +224,21 @@ usf_trsm_fast_kernel(const float* __restrict__ T, int64_t D, int Dp, const float
   }
 }
 
+template <bool LOWER, bool TRANS>
+__global__ void __launch_bounds__(THREADS)
+usf_trsm_fast_kernel(const float* __restrict__ T, int64_t D, int Dp, const float* __restrict__ Dinv,
+                     const float* rhs, int64_t ldr, const float* __restrict__ bias, float* X, int64_t ldx, int64_t B) {
+  trsm_fast_body<LOWER, TRANS, false>(T, D, Dp, Dinv, rhs, ldr, bias, X, ldx, B);
+}
+
+// Z = U^{-1} (y = 0) and W = L^{-1} (y = 1), row by row, in one launch (usf_lu_inverse).
+__global__ void __launch_bounds__(THREADS, 1)
+usf_lu_tri_inverse_kernel(const float* __restrict__ L_raw, const float* __restrict__ U_raw, int64_t D, int Dp,
+                          const float* __restrict__ DinvU, const float* __restrict__ DinvL, float* Z, float* W) {
+  if (blockIdx.y == 0) trsm_fast_body<true, true, true>(U_raw, D, Dp, DinvU, nullptr, 0, nullptr, Z, D, D);
+  else trsm_fast_body<false, true, true>(L_raw, D, Dp, DinvL, nullptr, 0, nullptr, W, D, D);
+}
+
 size_t fast_smem_bytes(int Dp) { return sizeof(float) * ((size_t)ROWS * Dp + NB * KPT + (2 * ROWS + NB) * EP); }
 
 }  // namespace
@@ -240,6 +275,32 @@ int trsm_rows_fast(const float* T, int64_t D, bool lower, bool unit, bool trans,
 #undef USF_FAST
   USF_LAUNCH_CHECK("usf_trsm_fast_kernel");
   return USF_OK;
+}
+
+// A = (L U)^{-1} (row-major, dense), L = unit lower / U = upper triangle of the raw factors: the two triangular
+// inverses in ONE launch (identity right-hand sides: half the work of a solve each, and the two run side by side),
+// then A = U^{-1} L^{-1} by the fp32 GEMM.  scratch: 2 D^2 + 2 round_up(D, 32) * 32 floats.
+int64_t lu_inverse_scratch_floats(int64_t D) { return 2 * D * D + 2 * round_up(D, NB) * NB; }
+
+int lu_inverse(const float* L_raw, const float* U_raw, int64_t D, float* A, float* scratch, cudaStream_t stream) {
+  // A == nullptr: the factors' inverses only (Z = U^{-1} at scratch, W = L^{-1} at scratch + D^2): the caller
+  // multiplies them (the host side uses the 3xTF32 tensor-core GEMM where its shapes allow)
+  if (D <= 0) return USF_OK;
+  const int Dp = (int)round_up(D, NB);
+  const int nblk = Dp / NB;
+  float* Z = scratch;
+  float* W = Z + D * D;
+  float* DinvU = W + D * D;
+  float* DinvL = DinvU + (int64_t)Dp * NB;
+  usf_lu_diag_inv_kernel<<<dim3(nblk, 2), NB, 0, stream>>>(L_raw, U_raw, D, DinvU, DinvL);
+  USF_LAUNCH_CHECK("usf_lu_diag_inv_kernel");
+  const size_t smem = fast_smem_bytes(Dp);
+  USF_CUDA(cudaFuncSetAttribute(usf_lu_tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  usf_lu_tri_inverse_kernel<<<dim3(nblk, 2), THREADS, smem, stream>>>(L_raw, U_raw, D, Dp, DinvU, DinvL, Z, W);
+  USF_LAUNCH_CHECK("usf_lu_tri_inverse_kernel");
+  if (A == nullptr) return USF_OK;
+  // A[i][j] = sum_k Z[i][k] W[k][j]
+  return simt_gemm_plain(Z, D, 0, W, D, 1, D, D, D, A, D, 0, stream);
 }
 
 }  // namespace usf

@@ -419,9 +419,9 @@ class Flow(torch.nn.Module):
     _PROBES = {}                 # (device, D) -> (I_D, 8 zero rows): what an affine run is composed on
 
     def _side(self, device, n):
-        """`n` (at most 16) side streams of this flow; the pool only ever holds streams a pass has forked into, so a
+        """`n` (at most 32) side streams of this flow; the pool only ever holds streams a pass has forked into, so a
         trainer that joins "all of the flow's side streams" never waits on one outside a capture."""
-        n = max(1, min(16, n))
+        n = max(1, min(32, n))
         streams = self.__dict__.get("_side_streams")
         if streams is None or streams[0].device != device:
             streams = self.__dict__["_side_streams"] = []
@@ -431,7 +431,9 @@ class Flow(torch.nn.Module):
             if warn_off is not None:
                 warn_off(False)
         while len(streams) < n:
-            streams.append(torch.cuda.Stream(device=device))
+            # two streams per affine run, in the order the batch-sized chain consumes the runs: the earlier a run is
+            # needed, the more urgent its stream (the chain itself runs above all of them: DataParallelTrainer)
+            streams.append(_lib.new_stream(device, priority=min(0, -4 + len(streams) // 2)))
         return streams[:n]
 
     def _compose_affine_runs(self, y):
@@ -475,43 +477,86 @@ class Flow(torch.nn.Module):
         # would execute one after the other (measured: a 2.1 ms tail).  So the accumulators are created here, on the
         # calling stream; the graphs built below keep them alive.
         pin = [p.view_as(p) for r in runs for layer in r for p in layer.parameters() if p.requires_grad]
-        used = self._side(dev, len(runs))
+        used = self._side(dev, 2 * len(runs))
         for st in used:
             st.wait_stream(cur)
         for i, r in enumerate(runs):
-            st = used[i % len(used)]
-            with torch.cuda.stream(st), composing() as comp:
+            st = used[(2 * i) % len(used)]              # the matrix pass
+            st_c = used[(2 * i + 1) % len(used)]        # the shift pass (waits for the factors the first one inverts)
+            with composing() as comp:
                 # the matrix: the identity through the run's linear parts (shifts off -- taking them from the same rows
                 # and subtracting would make every shift gradient a difference of D bf16-rounded sums) ...
-                comp["linear_only"] = True
-                Mt = probes[0]
-                for layer in r:
-                    Mt = layer.backward(Mt)
+                with torch.cuda.stream(st):
+                    comp["linear_only"] = True
+                    Mt = probes[0]
+                    for layer in r:
+                        Mt = layer.backward(Mt)
                 # ... and the shift: the zero row through the full maps (8 rows: the GEMM's row granularity)
-                comp["linear_only"] = False
-                z, const = probes[1], None
-                for layer in r:
-                    nxt = layer.backward(z)
-                    l = layer.log_abs_det_jacobian(nxt, z)
-                    if torch.is_tensor(l) and l.dim() > 0:
-                        const = False                      # a data-dependent log-det: not an affine run after all
-                        break
-                    l = torch.as_tensor(l, device=dev, dtype=torch.float32)
-                    const = l if const is None else const + l
-                    z = nxt
-                if const is False:
-                    continue
-                c = z[0]
+                with torch.cuda.stream(st_c):
+                    comp["linear_only"] = False
+                    z, const = probes[1], None
+                    for layer in r:
+                        nxt = layer.backward(z)
+                        l = layer.log_abs_det_jacobian(nxt, z)
+                        if torch.is_tensor(l) and l.dim() > 0:
+                            const = False                  # a data-dependent log-det: not an affine run after all
+                            break
+                        l = torch.as_tensor(l, device=dev, dtype=torch.float32)
+                        const = l if const is None else const + l
+                        z = nxt
+                    c = None if const is False else z[0]
+            if const is False:
+                cur.wait_stream(st)
+                cur.wait_stream(st_c)
+                continue
             for t in (Mt, c, const):
                 t.record_stream(cur)
-            composed[id(r)] = (Mt, c, const, st)
+            composed[id(r)] = (Mt, c, const, (st, st_c))
         del pin
         return plan, composed
+
+    def _prefetch_conditioners(self, y):
+        """Tensor-core training: the bf16 operand forms of the conditioner weights (first layer with the coupling mask
+        folded in) do not depend on the batch: converted up front on one side stream instead of in front of every GEMM
+        of the batch-sized chain.  Single use: `run_conditioner` pops `_usf_pre`."""
+        from .transforms import conditioner_weights
+        if ops._TC_TRAIN != 1 or not y.is_cuda or y.dim() != 2 or y.shape[0] < 8 or y.shape[0] % 8:
+            return
+        todo = []
+        for layer in self.layers:
+            cond = getattr(layer, "conditioner", None)
+            if stack._is_coupling(layer) and isinstance(cond, torch.nn.Module):
+                cond.__dict__.pop("_usf_pre", None)
+                if layer.mask.numel() == y.shape[1] and all(p.is_cuda for p in cond.parameters()):
+                    todo.append((layer, cond))
+        if not todo:
+            return
+        cur = torch.cuda.current_stream(y.device)
+        st = self.__dict__.get("_cond_stream")
+        if st is None or st.device != y.device:
+            self._side(y.device, 1)                                  # (the pool, on this device)
+            st = self.__dict__["_cond_stream"] = _lib.new_stream(y.device, priority=-8)   # short and needed first
+            self.__dict__["_side_streams"].append(st)                # joined by the trainer with the others
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            for layer, cond in todo:
+                ws = conditioner_weights(cond, layer.mask)
+                if ws is None or any(W.shape[0] % 16 or W.shape[1] % 16 for W, _ in ws):
+                    continue
+                pre = []
+                for W, b in ws:
+                    Wb, WT = ops.weight_operands(W)
+                    for t in (W, Wb, WT):
+                        t.record_stream(cur)
+                    pre.append((W, b, (Wb, WT)))
+                cond.__dict__["_usf_pre"] = (pre, st)
+        self.__dict__["_cond_pending"] = st
 
     def _inverse_layers(self, y, context=None):
         """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""
         if ops.tc_train_enabled() and y.dim() == 2:
             plan, composed = self._compose_affine_runs(y)
+            self._prefetch_conditioners(y)
         else:
             plan, composed = list(reversed(self.layers)), {}
         if ops.tc_train_enabled() and not composed:
@@ -521,8 +566,9 @@ class Flow(torch.nn.Module):
         for item in plan:
             hit = composed.get(id(item)) if isinstance(item, list) else None
             if hit is not None:
-                Mt, c, const, st = hit
-                torch.cuda.current_stream(y.device).wait_stream(st)
+                Mt, c, const, sts = hit
+                for st in sts:
+                    torch.cuda.current_stream(y.device).wait_stream(st)
                 y = ops.linear_fn(y, Mt, c, False, w_transposed=True)
                 consts.append(const)
                 continue
@@ -539,6 +585,9 @@ class Flow(torch.nn.Module):
                 y = x
         if consts:
             total = total - torch.stack(consts).sum()
+        pending = self.__dict__.pop("_cond_pending", None)
+        if pending is not None:              # (joined even if no conditioner picked its operands up)
+            torch.cuda.current_stream(y.device).wait_stream(pending)
         return y, total
 
     def _forward_layers(self, z, context=None):

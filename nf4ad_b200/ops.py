@@ -63,6 +63,27 @@ def lu_solve(y, L_raw, U_raw, bias=None, transpose=False):
     return x
 
 
+def lu_inverse(L_raw, U_raw):
+    """A = (L U)^{-1} as a dense matrix (usf_lu_inverse: both triangular inverses in one launch + one fp32 GEMM)."""
+    require_cuda(L_raw, U_raw)
+    D = L_raw.shape[0]
+    Lc, Uc = f32c(L_raw).contiguous(), f32c(U_raw).contiguous()
+    n = int(lib().usf_lu_inverse_scratch_floats(D))
+    if n == 0:          # too large for the resident triangular solve: the blocked solve on the identity
+        return lu_solve(torch.eye(D, device=Lc.device, dtype=torch.float32), Lc, Uc, None, transpose=True)
+    scratch = torch.empty(n, device=Lc.device, dtype=torch.float32)
+    if D % 16 == 0 and D >= 256:
+        # the product U^{-1} L^{-1} on the 3xTF32 tensor-core GEMM (fp32-grade; the FFMA GEMM takes 4x as long)
+        check(lib().usf_lu_inverse(ptr(Lc), ptr(Uc), D, None, ptr(scratch), stream()), "usf_lu_inverse")
+        Z, W = scratch[:D * D].view(D, D), scratch[D * D:2 * D * D].view(D, D)
+        Zr, _, _ = to_t3(Z, want_rows=True)
+        _, Wt, _ = to_t3(W, want_rows=False, want_transposed=True)
+        return gemm_t3(Zr, Wt, D, D, D)
+    A = torch.empty(D, D, device=Lc.device, dtype=torch.float32)
+    check(lib().usf_lu_inverse(ptr(Lc), ptr(Uc), D, ptr(A), ptr(scratch), stream()), "usf_lu_inverse")
+    return A
+
+
 def householder(x, V, reverse=False):
     require_cuda(x, V)
     x, ldx = _rows(x)
@@ -231,18 +252,20 @@ def tc_train_enabled():
     return _TC_TRAIN != 0
 
 
-def linear_fn(x, W, bias, relu=False, w_transposed=False):
+def linear_fn(x, W, bias, relu=False, w_transposed=False, operands=None):
     """Autograd linear layer: tensor-core (bf16) GEMMs in mixed-precision training when the shapes allow TMA operands
     (N, K multiples of 16, batch multiple of 8), else the fp32 kernels.  `w_transposed`: `W` holds the map's transpose
     (K, N) -- y = x W + bias -- which is how a composed affine run arrives (`Flow._compose_affine_runs`); its gradient
-    comes back in the same layout."""
+    comes back in the same layout.  `operands`: the bf16 forms `(W rows, W^T rows)` of `W` if the caller converted them
+    ahead of time (`weight_operands`, off the batch-sized chain)."""
     if _TC_TRAIN and x.is_cuda and x.dim() == 2 and x.shape[0] % 8 == 0 and x.shape[0] >= 8 \
             and W.shape[0] % 16 == 0 and W.shape[1] % 16 == 0:
         if _TC_TRAIN == 2:
             if x.shape[0] >= 256:        # below that the fp32 split-K kernels are as fast
                 return LinearT3Fn.apply(x, W, bias, relu, w_transposed)
         else:
-            return LinearTCFn.apply(x, W, bias, relu, w_transposed)
+            W, defer = wgrad_deferred(x, W)
+            return LinearTCFn.apply(x, W, bias, relu, w_transposed, operands, defer)
     return LinearFn.apply(x, W.t() if w_transposed else W, bias, relu)
 
 
@@ -282,23 +305,30 @@ class LinearFn(torch.autograd.Function):
 
 _WGRAD_STREAMS = {}
 _WGRAD_OVERLAP = os.environ.get("USF_WGRAD_OVERLAP", "1") != "0"
+_WGRAD_DEFER = os.environ.get("USF_WGRAD_DEFER", "1") != "0"
+_WGRAD_OVERLAP_MIN_ROWS = 1024     # weight-space products (D or 8 rows) are too short to be worth a fork / join
+
+
+def _wgrad_stream(dev):
+    """The partner stream of the current stream of `dev` for weight-gradient GEMMs.  One per calling stream: the
+    weight-space chains of different affine runs (each on its own side stream) must not meet on a shared one -- every
+    fork / join there would order them after each other."""
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, cur.cuda_stream)
+    side = _WGRAD_STREAMS.get(key)
+    if side is None:
+        side = _WGRAD_STREAMS[key] = _lib.new_stream(dev)
+    return cur, side
 
 
 def _overlapped_wgrad(fn, operands):
     """The weight-gradient GEMM of a linear layer reduces over the batch into a small (N, K) output -- 16-64 tiles, a
     fraction of the GPU -- and nothing downstream in the backward chain needs it.  It is issued on a side stream while
-    the input-gradient GEMM runs on the current one (fork after the operands are ready, join before returning, so
-    autograd's stream bookkeeping is untouched); both GEMMs then share the SMs.  Survives CUDA-graph capture."""
-    if not _WGRAD_OVERLAP:
-        return fn()
+    the input-gradient GEMM runs on the current one (fork after the operands are ready); both GEMMs then share the SMs.
+    -> (dW, side stream): the caller joins the stream before returning -- or, if the weight went through
+    `_WgradSide`, not at all.  Survives CUDA-graph capture."""
     dev = operands[0].device
-    cur = torch.cuda.current_stream(dev)
-    # one partner stream per calling stream: the weight-space chains of different affine runs (each on its own side
-    # stream) must not meet on a shared one -- every fork / join there would order them after each other
-    key = (dev.index, cur.cuda_stream)
-    side = _WGRAD_STREAMS.get(key)
-    if side is None:
-        side = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    cur, side = _wgrad_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         out = fn()
@@ -307,6 +337,33 @@ def _overlapped_wgrad(fn, operands):
             t.record_stream(side)
     out.record_stream(cur)
     return out, side
+
+
+class _WgradSide(torch.autograd.Function):
+    """Identity on a weight, applied with the weight-gradient partner stream current.  Autograd runs a node's backward
+    on the stream its forward ran on and synchronises the CONSUMERS of its result with that stream: with this node
+    between a weight and `LinearTCFn`, the weight gradient that `LinearTCFn.backward` leaves running on the partner
+    stream is handed on from that very stream -- ordered behind the GEMM -- and the batch-sized backward chain never
+    waits for a weight-gradient GEMM (28 us against the 10-17 us of the input-gradient GEMM it ran beside)."""
+
+    @staticmethod
+    def forward(ctx, W):
+        return W.view_as(W)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def wgrad_deferred(x, W):
+    """-> (W routed through `_WgradSide`, True) if this layer's weight-gradient GEMM may trail behind the backward chain,
+    else (W, False)."""
+    if not (_WGRAD_OVERLAP and _WGRAD_DEFER and x.is_cuda and x.shape[0] >= _WGRAD_OVERLAP_MIN_ROWS
+            and torch.is_grad_enabled() and W.requires_grad and x.requires_grad):
+        return W, False
+    _, side = _wgrad_stream(x.device)
+    with torch.cuda.stream(side):
+        return _WgradSide.apply(W), True
 
 
 class LinearTCFn(torch.autograd.Function):
@@ -318,17 +375,21 @@ class LinearTCFn(torch.autograd.Function):
     gating and the bias gradient)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, relu, wt=False):
+    def forward(ctx, x, W, bias, relu, wt=False, operands=None, defer=False):
         B, K = x.shape
         N = W.shape[1] if wt else W.shape[0]
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ctx.defer = bool(defer)          # W came through _WgradSide: its gradient is handed on from the partner stream
         xb, xT, _ = to_bf16(x, want_rows=True, want_transposed=need_w)
-        if wt:       # W^T (K, N) given: its rows are the dgrad operand, its transpose the forward operand
+        if operands is not None:
+            Wb, WT = operands
+        elif wt:     # W^T (K, N) given: its rows are the dgrad operand, its transpose the forward operand
             WT, Wb, _ = to_bf16(W, want_rows=need_x, want_transposed=True)
         else:
             Wb, WT, _ = to_bf16(W, want_rows=True, want_transposed=need_x)
         y = gemm_bf16(xb, Wb, B, N, K, bias, relu)
         ctx.relu, ctx.has_bias, ctx.shape, ctx.wt = bool(relu), bias is not None, (B, N, K), bool(wt)
+        ctx.overlap = _WGRAD_OVERLAP and B >= _WGRAD_OVERLAP_MIN_ROWS
         ctx.save_for_backward(xT, WT, y if relu else None)
         return y
 
@@ -342,14 +403,37 @@ class LinearTCFn(torch.autograd.Function):
         # dW = dy^T x (N, K), or in the transposed layout d(W^T) = x^T dy (K, N)
         wgrad = (lambda: gemm_bf16(xT, dyT, K, N, B)) if ctx.wt else (lambda: gemm_bf16(dyT, xT, N, K, B))
         join = None
-        if need_w and need_x and _WGRAD_OVERLAP:
+        if need_w and need_x and ctx.overlap:
             dW, join = _overlapped_wgrad(wgrad, (dyT, xT))
         else:
             dW = wgrad() if need_w else None
         dx = gemm_bf16(dyb, WT, B, K, N) if need_x else None
-        if join is not None:
+        if join is not None and not ctx.defer:
             torch.cuda.current_stream(dy.device).wait_stream(join)
-        return dx, dW, db, None, None
+        return dx, dW, db, None, None, None, None
+
+
+def weight_operands(W, w_transposed=False):
+    """The bf16 operand pair `LinearTCFn` builds from a weight: (W rows (N, K), W^T rows (K, N))."""
+    if w_transposed:
+        WT, Wb, _ = to_bf16(W, want_rows=True, want_transposed=True)
+    else:
+        Wb, WT, _ = to_bf16(W, want_rows=True, want_transposed=True)
+    return Wb, WT
+
+
+class MaskFn(torch.autograd.Function):
+    """x * mask for a constant 0/1 mask: the same element-wise kernel forward and backward (no parameter gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return scale(x, mask, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        mask, = ctx.saved_tensors
+        return scale(dy, mask, False), None
 
 
 class LinearT3Fn(torch.autograd.Function):
@@ -379,7 +463,7 @@ class LinearT3Fn(torch.autograd.Function):
                              want_colsum=need_b)
         wgrad = (lambda: gemm_t3((xTh, xTl), dyT, K, N, B)) if ctx.wt else (lambda: gemm_t3(dyT, (xTh, xTl), N, K, B))
         join = None
-        if need_w and need_x and _WGRAD_OVERLAP:
+        if need_w and need_x and _WGRAD_OVERLAP and B >= _WGRAD_OVERLAP_MIN_ROWS:
             dW, join = _overlapped_wgrad(wgrad, (dyT[0], dyT[1], xTh, xTl))
         else:
             dW = wgrad() if need_w else None
@@ -396,8 +480,7 @@ class LUInverseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, L_raw, U_raw):
         D = L_raw.shape[0]
-        eye = torch.eye(D, device=L_raw.device, dtype=torch.float32)
-        A = lu_solve(eye, L_raw, U_raw, None, transpose=True)      # row i = e_i^T (LU)^{-1}
+        A = lu_inverse(L_raw, U_raw)
         ctx.tc = bool(_TC_TRAIN == 1 and _TC_WEIGHT_SPACE)
         ctx.save_for_backward(A, L_raw, U_raw)
         return A

@@ -370,6 +370,7 @@ class DataParallelTrainer:
             nccl = False
         self.use_graph = bool(use_graph) and nccl and capturable and on_cuda
         self.graph_warmup = int(graph_warmup)
+        self._capture_stream = None
         self._graphs = {}      # batch shape -> [seen, CUDAGraph | None, static input, static loss, hyper-parameter signature]
         self.graph_replays = 0
         self.graph_error = None     # the exception that switched graph replay off, if any
@@ -541,8 +542,14 @@ class DataParallelTrainer:
             graph.enable_debug_mode()
         if self._flat is None:
             self.opt.zero_grad(set_to_none=True)
+        # The step is captured on a stream of the highest priority: graph kernel nodes inherit the priority of the stream
+        # they were captured on, and the batch-sized chain (the step's critical path) must not queue behind the
+        # weight-space chains the flow forks beside it (`Flow._compose_affine_runs`, lower priorities).
+        from . import _lib
+        if self._capture_stream is None or self._capture_stream.device != static_x.device:
+            self._capture_stream = _lib.new_stream(static_x.device, priority=-8)
         # thread_local: NCCL's watchdog thread may query events while this thread captures
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
             if self._flat is not None:
                 self._begin_sync()          # the memset of the flat gradient buffer is part of the replayed step
             loss = self.loss_fn(static_x)

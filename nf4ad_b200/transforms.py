@@ -115,6 +115,28 @@ class BaseTransform(TransformModule):
 _COMPOSE = None
 
 
+def _mark(t):
+    """(stream, event) after the work enqueued so far on the current stream of `t`'s device (None on the CPU)."""
+    if not t.is_cuda:
+        return None
+    ev = torch.cuda.Event()
+    st = torch.cuda.current_stream(t.device)
+    ev.record(st)
+    return st, ev
+
+
+def _shared(hit):
+    """A tensor cached by a composition, made safe to read on the current stream (the matrix pass and the shift pass
+    of a run are enqueued on two streams)."""
+    t, mark = hit
+    if mark is not None:
+        cur = torch.cuda.current_stream(t.device)
+        if cur != mark[0]:
+            cur.wait_event(mark[1])
+            t.record_stream(cur)
+    return t
+
+
 class composing:
     def __enter__(self):
         global _COMPOSE
@@ -162,10 +184,10 @@ class LUTransform(BaseTransform):
     def weight(self):
         comp = _COMPOSE
         if comp is not None:                                  # one product per layer per composition
-            W = comp["W"].get(id(self))
-            if W is None:
-                W = comp["W"][id(self)] = ops.LUPackFn.apply(self.L_raw, self.U_raw)
-            return W
+            hit = comp["W"].get(id(self))
+            if hit is None:
+                hit = comp["W"][id(self)] = (ops.LUPackFn.apply(self.L_raw, self.U_raw), _mark(self.L_raw))
+            return _shared(hit)
         return ops.LUPackFn.apply(self.L_raw, self.U_raw)
 
     def forward(self, x, context=None):
@@ -183,14 +205,15 @@ class LUTransform(BaseTransform):
             comp = _COMPOSE
             pre = self.__dict__.pop("_A_pre", None)      # issued up front by Flow._prefetch_lu_inverses
             if comp is not None and id(self) in comp["A"]:
-                A = comp["A"][id(self)]
+                A = _shared(comp["A"][id(self)])
             elif pre is not None:
                 A, side = pre
                 torch.cuda.current_stream(y2.device).wait_stream(side)
             else:
                 A = ops.LUInverseFn.apply(self.L_raw, self.U_raw)
             if comp is not None:
-                comp["A"][id(self)] = A
+                if id(self) not in comp["A"]:
+                    comp["A"][id(self)] = (A, _mark(A))
                 if comp["linear_only"]:
                     return _restore(ops.linear_fn(y2, A, None, False), squeeze)
             # the shift -A b through the library's own GEMM (a 1 x D x D product; no cuBLAS call on the training path)
@@ -434,21 +457,60 @@ def mlp_layers(module):
     return linears
 
 
-def run_conditioner(cond, xm, context=None):
+def conditioner_weights(cond, mask=None):
+    """The (weight, bias) pairs of a recognised Linear/ReLU conditioner as the training GEMMs take them, or None.  With
+    `mask` (the coupling's 0/1 mask over the event) the masking of the conditioner's input is folded into the first
+    layer -- `(x m) W^T = x (W m)^T`, a weight-sized product whose autograd node also masks the weight gradient -- so
+    that no batch-sized masking pass runs."""
+    linears = mlp_layers(cond)
+    if linears is None:
+        return None
+    out = []
+    for i, lin in enumerate(linears):
+        W = lin.weight
+        if i == 0 and mask is not None:
+            cd = context_dim(cond)
+            m = mask.reshape(-1).to(W.dtype)
+            if cd:
+                m = torch.cat([torch.ones(cd, device=m.device, dtype=m.dtype), m])
+            if m.numel() != W.shape[1]:
+                return None
+            W = W * m
+        out.append((W, lin.bias))
+    return out
+
+
+def run_conditioner(cond, xm, context=None, mask=None):
     """Evaluates the conditioner on flat rows `xm` (B, D).  Recognised Linear/ReLU chains run on usf_linear (our GEMM +
     bias/ReLU epilogue) -- a conditional one on `cat([context, xm])`; anything else is an opaque user module evaluated
-    as given (`conditioner(x_masked)` / `conditioner(x_masked, context)`, `nf4ad/transforms.py:71-74`)."""
+    as given (`conditioner(x_masked)` / `conditioner(x_masked, context)`, `nf4ad/transforms.py:71-74`).  `mask`: `xm` is
+    the UNMASKED input and the mask is to be applied here (tensor-core training: folded into the first layer's weight,
+    `conditioner_weights`; the layers' bf16 operands may have been prepared ahead by `Flow._prefetch_conditioners`)."""
     linears = mlp_layers(cond) if xm.is_cuda and xm.dim() == 2 else None
     cd = context_dim(cond)
-    if linears is None or (context is not None) != (cd > 0) or linears[0].in_features != xm.shape[1] + cd:
+    fast = not (linears is None or (context is not None) != (cd > 0) or linears[0].in_features != xm.shape[1] + cd)
+    pre = cond.__dict__.pop("_usf_pre", None) if isinstance(cond, torch.nn.Module) else None
+    weights = None
+    if fast and mask is not None:
+        if pre is not None:
+            weights, side = pre
+            torch.cuda.current_stream(xm.device).wait_stream(side)
+        else:
+            weights = conditioner_weights(cond, mask)
+            weights = None if weights is None else [(W, b, None) for W, b in weights]
+    if mask is not None and weights is None:
+        xm = ops.MaskFn.apply(xm, mask.reshape(-1))
+    if not fast:
         return cond(xm) if context is None else cond(xm, context)
     h = xm
     if cd:
         ctx = context.to(xm.dtype)
         ctx = ctx.reshape(-1, cd) if ctx.dim() != 2 else ctx
         h = torch.cat([ctx.expand(xm.shape[0], cd), xm], dim=-1)
-    for i, lin in enumerate(linears):
-        h = ops.linear_fn(h, lin.weight, lin.bias, i + 1 < len(linears))
+    if weights is None:
+        weights = [(lin.weight, lin.bias, None) for lin in linears]
+    for i, (W, b, operands) in enumerate(weights):
+        h = ops.linear_fn(h, W, b, i + 1 < len(weights), operands=operands)
     pd = getattr(cond, "param_dims", None)
     if pd is not None and len(pd) > 1:           # DenseNN tuple output
         outs, o = [], 0
@@ -500,10 +562,13 @@ def coupling_apply(layer, v, inverse, context=None, additive=False):
     B = vb.shape[0]
     v2 = vb.reshape(B, -1)
     m = mask.reshape(-1)
-    vm = ops.ScaleFn.apply(v2, m, False)
-    if vb.dim() == 2:
-        params = run_conditioner(layer.conditioner, vm, context)
+    if vb.dim() == 2 and ops.tc_train_enabled() and v2.is_cuda:
+        # tensor-core training: the mask goes into the conditioner's first layer (no batch-sized masking pass)
+        params = run_conditioner(layer.conditioner, v2, context, mask=m)
+    elif vb.dim() == 2:
+        params = run_conditioner(layer.conditioner, ops.ScaleFn.apply(v2, m, False), context)
     else:                                   # image-shaped event: the conditioner sees (B, C, H, W)
+        vm = ops.ScaleFn.apply(v2, m, False)
         vmb = vm.reshape(vb.shape)
         params = layer.conditioner(vmb) if context is None else layer.conditioner(vmb, context)
     if not additive and vb.dim() == 2 and torch.is_tensor(params) and params.dim() == 2 and v2.is_cuda \

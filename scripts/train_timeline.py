@@ -30,7 +30,8 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     if eager:
         tr._eager_step(x)
     else:
-        tr.step(x)
+        for _ in range(int(os.environ.get("TIMELINE_REPLAYS", "4"))):      # back to back: the last one is steady state
+            tr.step(x)
     torch.cuda.synchronize()
 if eager:
     print("side streams:", [s.cuda_stream for s in flow.__dict__.get("_side_streams", [])])
@@ -42,6 +43,11 @@ def short(n):
     return n.split("(")[0][:70]
 for e in ev: e["name"] = short(e["name"])
 ev.sort(key=lambda e: e["ts"])
+if not eager:                       # keep the last replay: from its input copy (the step's first device op) on
+    starts = [i for i, e in enumerate(ev) if e["name"].startswith("Memcpy DtoD") and e["args"].get("bytes", 0) >= x.numel() * 4]
+    if len(starts) > 1:
+        print(f"replay starts at {[round(ev[i]['ts'] - ev[0]['ts']) for i in starts]} us")
+        ev = ev[starts[-1]:]
 t0, t1 = ev[0]["ts"], max(e["ts"] + e["dur"] for e in ev)
 print(f"one replay: {len(ev)} device ops, span {(t1 - t0) / 1e3:.3f} ms")
 tot = collections.defaultdict(lambda: [0, 0.0])
