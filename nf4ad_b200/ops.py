@@ -496,8 +496,7 @@ class LUInverseFn(torch.autograd.Function):
         # P = A^T dA ;  dW = -(P A^T)
         if ctx.tc and D % 16 == 0:
             # mixed precision: the two D^3 products on the tensor cores as well (bf16 operands, fp32 accumulate)
-            _, At, _ = to_bf16(A, want_rows=False, want_transposed=True)      # A^T rows
-            Ab, _, _ = to_bf16(A, want_rows=True)
+            Ab, At, _ = to_bf16(A, want_rows=True, want_transposed=True)      # A rows, A^T rows: one pass
             _, dAt, _ = to_bf16(dA, want_rows=False, want_transposed=True)    # dA^T rows: operand [n, k] = dA[k, n]
             P = gemm_bf16(At, dAt, D, D, D)
             Pb, _, _ = to_bf16(P, want_rows=True)

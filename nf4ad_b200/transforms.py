@@ -193,8 +193,11 @@ class LUTransform(BaseTransform):
     def forward(self, x, context=None):
         x2, squeeze = _as2d(x)
         comp = _COMPOSE
-        bias = None if (comp is not None and comp["linear_only"]) else self.bias
-        y = ops.linear_fn(x2, self.weight, bias, False)
+        if comp is not None and comp["linear_only"]:
+            if x2 is comp.get("eye"):                    # the identity probe: I W^T, no product needed
+                return _restore(self.weight.t().contiguous(), squeeze)
+            return _restore(ops.linear_fn(x2, self.weight, None, False), squeeze)
+        y = ops.linear_fn(x2, self.weight, self.bias, False)
         return _restore(y, squeeze)
 
     def backward(self, y, context=None):
@@ -215,6 +218,8 @@ class LUTransform(BaseTransform):
                 if id(self) not in comp["A"]:
                     comp["A"][id(self)] = (A, _mark(A))
                 if comp["linear_only"]:
+                    if y2 is comp.get("eye"):            # the identity probe: I A^T, no product needed
+                        return _restore(A.t().contiguous(), squeeze)
                     return _restore(ops.linear_fn(y2, A, None, False), squeeze)
             # the shift -A b through the library's own GEMM (a 1 x D x D product; no cuBLAS call on the training path)
             shift = ops.LinearFn.apply(self.bias.unsqueeze(0), A, None, False).squeeze(0)
