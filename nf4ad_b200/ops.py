@@ -63,6 +63,9 @@ def lu_solve(y, L_raw, U_raw, bias=None, transpose=False):
     return x
 
 
+_LU_T3_PRODUCT = os.environ.get("USF_LU_T3", "1") != "0"
+
+
 def lu_inverse(L_raw, U_raw):
     """A = (L U)^{-1} as a dense matrix (usf_lu_inverse: both triangular inverses in one launch + one fp32 GEMM)."""
     require_cuda(L_raw, U_raw)
@@ -72,7 +75,7 @@ def lu_inverse(L_raw, U_raw):
     if n == 0:          # too large for the resident triangular solve: the blocked solve on the identity
         return lu_solve(torch.eye(D, device=Lc.device, dtype=torch.float32), Lc, Uc, None, transpose=True)
     scratch = torch.empty(n, device=Lc.device, dtype=torch.float32)
-    if D % 16 == 0 and D >= 256:
+    if D % 16 == 0 and D >= 256 and _LU_T3_PRODUCT:
         # the product U^{-1} L^{-1} on the 3xTF32 tensor-core GEMM (fp32-grade; the FFMA GEMM takes 4x as long)
         check(lib().usf_lu_inverse(ptr(Lc), ptr(Uc), D, None, ptr(scratch), stream()), "usf_lu_inverse")
         Z, W = scratch[:D * D].view(D, D), scratch[D * D:2 * D * D].view(D, D)

@@ -68,36 +68,58 @@ def _grads(flow, x, **attrs):
 
 
 @pytest.mark.parametrize("D,K,hidden,B", [(64, 3, [128, 128], 256), (784, 2, [256], 1024)])
-def test_composed_affine_runs_match_the_layerwise_pass(P, D, K, hidden, B):
-    """`Flow._compose_affine_runs` (one GEMM per affine run on the batch, the run's matrix / shift / log-det evaluated in
-    weight space on side streams) against the layer-wise pass of the same tier: same loss, same gradients for every
-    parameter -- the 3xTF32 tier to 2e-3 of each gradient's norm (1e-2 for the reflection vectors), the bf16 tier in direction and norm -- and both
-    against the fp32 kernels (the reference's arithmetic, nf4ad/flows.py:160-169 + adbench_wrapper.py:383-391)."""
+def test_composed_affine_runs_match_the_layerwise_pass(O, P, D, K, hidden, B):
+    """`Flow._compose_affine_runs` (one GEMM per affine run on the batch; the run's matrix / shift / log-det evaluated in
+    weight space on side streams) against the layer-wise pass of the same tier and against the fp64 oracle's loss and
+    gradients (the reference's arithmetic: nf4ad/flows.py:160-169 + adbench_wrapper.py:383-391).  Every gradient of the
+    3xTF32 tier within 1e-2 of fp64 in norm, every gradient of the bf16 tier with the right direction and norm, and the
+    composed pass never further from fp64 than 1.5x the layer-wise pass of its tier."""
     torch.manual_seed(0)
+    fo = build_flow(O, "NonUSFlow", D, K, ("mlp", hidden), affine_conjugation=True, prior_scale=1.0)
+    tame(fo, 0.25)
+    randomize_constants(fo, 3)
     flow = build_flow(P, "NonUSFlow", D, K, ("mlp", hidden), affine_conjugation=True, prior_scale=1.0)
-    tame(flow, 0.25)
-    randomize_constants(flow, 3)
+    flow.load_state_dict(fo.state_dict())
     flow = flow.to("cuda").train()
-    x = torch.randn(B, D, generator=torch.Generator().manual_seed(5)).cuda()
+    xc = torch.randn(B, D, generator=torch.Generator().manual_seed(5))
+    x = xc.cuda()
+    fo = fo.double()
+    l64 = -fo.log_prob(xc.double()).mean()
+    l64.backward()
+    g64 = {n: p.grad.detach() for n, p in fo.named_parameters() if p.grad is not None}
+    l64 = float(l64.detach())
+
+    def dist(g):
+        out = {}
+        for n, ref in g64.items():
+            if float(ref.norm()) > 1e-9:
+                out[n] = float((g[n].double().cpu() - ref).norm() / ref.norm())
+        return out
+
     l32, g32 = _grads(flow, x, precision="fp32")
+    assert set(g32) == set(g64) and abs(l32 - l64) <= 1e-5 * max(1.0, abs(l64))
+    e32 = dist(g32)
+    assert max(e32.values()) < 1e-2, max(e32.values())
     for prec, ltol in (("tf32x3", 1e-4), ("bf16", 1e-2)):
-        lc, gc = _grads(flow, x, precision=prec, compose_affine=True)
-        ll, gl = _grads(flow, x, precision=prec, compose_affine=False)
-        assert abs(lc - l32) <= ltol * max(1.0, abs(l32)) and abs(ll - l32) <= ltol * max(1.0, abs(l32)), (prec, lc, ll, l32)
-        assert set(gc) == set(gl) == set(g32)
-        for n, ref in g32.items():
-            if float(ref.norm()) < 1e-6:
-                continue
-            for which, got in (("composed", gc[n]), ("layer-wise", gl[n])):
-                assert torch.isfinite(got).all(), (prec, which, n)
-                cos = float((ref * got).sum() / (ref.norm() * got.norm()).clamp_min(1e-30))
+        errs = {}
+        for which, composed in (("composed", True), ("layer-wise", False)):
+            loss, g = _grads(flow, x, precision=prec, compose_affine=composed)
+            assert abs(loss - l64) <= ltol * max(1.0, abs(l64)), (prec, which, loss, l64)
+            assert set(g) == set(g64)
+            errs[which] = dist(g)
+            for n, e in errs[which].items():
+                assert torch.isfinite(g[n]).all(), (prec, which, n)
                 if prec == "tf32x3":
-                    # (the reflection vectors' gradients are differences of near-equal terms: 5e-3 at D = 784 in BOTH
-                    # passes; everything else is below 1e-3)
-                    rel = float((got - ref).norm() / ref.norm())
-                    assert rel <= (1e-2 if "householder" in n else 2e-3), (prec, which, n, rel)
+                    # the tier's gradients sit 3e-3 .. 5e-3 from fp64 at D = 784 in either pass (the tensor cores'
+                    # fp32 accumulation over K = 784 .. 1024; the fp32 FFMA kernels: 7e-5)
+                    assert e <= 1e-2, (prec, which, n, e, e32[n])
                 else:
+                    ref, got = g64[n], g[n].double().cpu()
+                    cos = float((ref * got).sum() / (ref.norm() * got.norm()).clamp_min(1e-30))
                     assert cos > 0.98 and 0.9 < float(got.norm() / ref.norm()) < 1.1, (prec, which, n, cos)
+        # composing in weight space does not cost accuracy: no gradient further from fp64 than 1.5x the layer-wise one
+        for n, e in errs["composed"].items():
+            assert e <= 1.5 * errs["layer-wise"][n] + (1e-3 if prec == "tf32x3" else 2e-2), (prec, n, e, errs["layer-wise"][n])
     flow.compose_affine = True
 
 
