@@ -331,6 +331,11 @@ class ShardedScorer:
         return self.gather(local, sizes).cpu()
 
 
+def _is_capturing(st):
+    with torch.cuda.stream(st):
+        return torch.cuda.is_current_stream_capturing()
+
+
 class DataParallelTrainer:
     """Data-parallel NLL training step (`adbench_wrapper.py:375-392`): per-rank micro-batch, gradients averaged over the
     ranks (loss is a per-rank mean), global-norm clipping after the reduction, identical optimizer step on every rank.
@@ -443,8 +448,11 @@ class DataParallelTrainer:
             waits = {torch.cuda.current_stream(dev), self._main_stream}
             waits.update(getattr(self.flow, "_side_streams", None) or [])
             waits.update(st for (i, _), st in ops._WGRAD_STREAMS.items() if i == dev.index)
+            # only streams in the same capture state as this hook's: a capturing stream must not wait for one outside
+            # its capture (the weight-gradient partner of the eager warm-up steps' stream, say), and the other way round
+            capturing = torch.cuda.is_current_stream_capturing()
             for st in waits:
-                if st is not None:
+                if st is not None and _is_capturing(st) == capturing:
                     self._comm_stream.wait_stream(st)
             with torch.cuda.stream(self._comm_stream):
                 self._reduce(chunk)
