@@ -24,6 +24,35 @@ from .transforms import (
     MaskedCoupling, ScaleTransform, SequentialAffineTransform, composing, context_dim, coupling_apply,
 )
 
+class _RunComposer:
+    """Composes the affine runs of one training pass (`Flow._compose_affine_runs`), each chain forked from the step's
+    start event.  `AHEAD` = how many runs are composed in advance of the one the batch-sized chain takes next.  Two
+    orders follow the order in which this code runs on the host: a replayed CUDA graph dispatches its nodes roughly in
+    capture order (~0.6 us per node; a step has ~1400), and autograd's backward pass visits nodes newest first -- so
+    with a small `AHEAD` weight-space and batch-sized work alternate in both passes, with a large one (default: every
+    run up front) all weight-space chains are dispatched first and visited last.  Measured on C2 / B = 4096
+    (USF_COMPOSE_AHEAD = 1, 2, 3, all): 3.43 / 3.44 / 3.37 / 3.42 ms per step -- no difference: the step ends ~0.6 ms
+    after the batch chain either way, which is the latency of ONE weight-space backward chain (~100 short kernels), not
+    the order they are visited in.  Kept as a switch for other shapes."""
+
+    AHEAD = int(os.environ.get("USF_COMPOSE_AHEAD", "99"))
+
+    def __init__(self, flow, runs, probes, cur, start, pin):
+        self.flow, self.runs, self.probes, self.cur, self.start, self.pin = flow, runs, probes, cur, start, pin
+        self.done = []                       # per run, in order: the composed tuple or None
+
+    def take(self, item):
+        """The composed form of plan item `item` (None: not one of the composed runs), composing ahead first."""
+        idx = next((i for i, r in enumerate(self.runs) if r is item), None)
+        if idx is None:
+            return None
+        upto = min(len(self.runs), idx + 1 + max(0, self.AHEAD))
+        while len(self.done) < upto:
+            i = len(self.done)
+            self.done.append(self.flow._compose_run(self.runs[i], i, self.probes, self.cur, self.start))
+        return self.done[idx]
+
+
 def _on_device(method):
     """Runs a `Flow` method with the CUDA device of its first tensor argument current: the C library launches on the
     current device's current stream (`_lib.stream`), so a flow living on cuda:1 must not be driven through cuda:0."""
@@ -419,12 +448,16 @@ class Flow(torch.nn.Module):
     _PROBES = {}                 # (device, D) -> (I_D, 8 zero rows): what an affine run is composed on
 
     def _side(self, device, n):
-        """`n` (at most 32) side streams of this flow; the pool only ever holds streams a pass has forked into, so a
-        trainer that joins "all of the flow's side streams" never waits on one outside a capture."""
+        """`n` (at most 32) side streams of this flow for the weight-space chains.  Every stream the flow creates is
+        also listed in `_side_streams`, which a trainer joins; the lists only ever hold streams a pass has forked into,
+        so joining "all of the flow's side streams" never waits on one outside a capture."""
         n = max(1, min(32, n))
-        streams = self.__dict__.get("_side_streams")
-        if streams is None or streams[0].device != device:
-            streams = self.__dict__["_side_streams"] = []
+        streams = self.__dict__.get("_run_streams")
+        if streams is None or (streams and streams[0].device != device):
+            streams = self.__dict__["_run_streams"] = []
+            self.__dict__["_side_streams"] = []
+            for k in ("_cond_stream", "_acc_stream"):
+                self.__dict__.pop(k, None)
             # the factor gradients are produced on the side streams on purpose; autograd syncs them with the
             # accumulation stream, it only warns that this costs a synchronisation
             warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
@@ -433,8 +466,19 @@ class Flow(torch.nn.Module):
         while len(streams) < n:
             # two streams per affine run, in the order the batch-sized chain consumes the runs: the earlier a run is
             # needed, the more urgent its stream (the chain itself runs above all of them: DataParallelTrainer)
-            streams.append(_lib.new_stream(device, priority=min(0, -4 + len(streams) // 2)))
+            st = _lib.new_stream(device, priority=min(0, -4 + len(streams) // 2))
+            streams.append(st)
+            self.__dict__["_side_streams"].append(st)
         return streams[:n]
+
+    def _extra_stream(self, key, device, priority):
+        """A further stream of the flow's own (conditioner operands, gradient accumulation), created once per device."""
+        self._side(device, 1)                                        # (resets everything on a device change)
+        st = self.__dict__.get(key)
+        if st is None:
+            st = self.__dict__[key] = _lib.new_stream(device, priority=priority)
+            self.__dict__["_side_streams"].append(st)
+        return st
 
     def _compose_affine_runs(self, y):
         """Mixed-precision training: every maximal run of affine layers between two couplings (LU solve / product,
@@ -444,7 +488,8 @@ class Flow(torch.nn.Module):
         c = the image of 0, the parameter-only log-dets summed there too), and the batch then sees ONE tensor-core GEMM per
         run instead of a GEMM / reflection / scale kernel per layer.  The runs are independent of each other, so their
         chains -- forward here, backward wherever autograd reaches them: a node's backward runs on its forward's
-        stream -- overlap each other and the batch-sized chain.  -> (plan, {id(run): (M^T, c, log-det, stream)})."""
+        stream -- overlap each other and the batch-sized chain.  -> (plan, composer | None): the runs are composed by
+        `_RunComposer.take`, a few ahead of the batch-sized chain."""
         plan, run = [], []
         for layer in reversed(self.layers):
             if isinstance(layer, BaseTransform) and getattr(layer, "is_affine", False) and not stack._is_coupling(layer):
@@ -457,13 +502,12 @@ class Flow(torch.nn.Module):
         if run:
             plan.append(run)
         B, D = y.shape[0], y.shape[-1]
-        composed = {}
         if not (y.is_cuda and y.dim() == 2 and B >= 8 and B % 8 == 0 and D % 16 == 0 and getattr(self, "compose_affine", True)):
-            return plan, composed
+            return plan, None
         runs = [r for r in plan if isinstance(r, list)
                 and any(isinstance(m, LUTransform) for layer in r for m in layer.modules())]
         if not runs:
-            return plan, composed
+            return plan, None
         dev = y.device
         probes = Flow._PROBES.get((dev, D))
         if probes is None:
@@ -474,50 +518,59 @@ class Flow(torch.nn.Module):
         # and autograd sums the contributions of different nodes there.  Every affine layer sits in TWO runs (tail of
         # one, head of the next): were the accumulator created inside a run, the partial sums of the neighbouring
         # run's gradients would be queued on this run's stream ahead of its own backward chain -- and the nine chains
-        # would execute one after the other (measured: a 2.1 ms tail).  So the accumulators are created here, on the
-        # calling stream; the graphs built below keep them alive.
-        pin = [p.view_as(p) for r in runs for layer in r for p in layer.parameters() if p.requires_grad]
-        used = self._side(dev, 2 * len(runs))
-        for st in used:
-            st.wait_stream(cur)
-        for i, r in enumerate(runs):
-            st = used[(2 * i) % len(used)]              # the matrix pass
-            st_c = used[(2 * i + 1) % len(used)]        # the shift pass (waits for the factors the first one inverts)
-            with composing() as comp:
-                comp["eye"] = probes[0]
-                # the matrix: the identity through the run's linear parts (shifts off -- taking them from the same rows
-                # and subtracting would make every shift gradient a difference of D bf16-rounded sums) ...
-                with torch.cuda.stream(st):
-                    comp["linear_only"] = True
-                    Mt = probes[0]
-                    for layer in r:
-                        Mt = layer.backward(Mt)
-                # ... and the shift: the zero row through the full maps (8 rows: the GEMM's row granularity).
-                # (Issuing this pass first would put the LU factor nodes and their long backward on its stream, beside
-                # the matrix pass's backward chain -- measured: the tail shrinks by 90 us, but the replayed graph then
-                # starts the nine inversions three at a time instead of together: +500 us before the first coupling.)
-                with torch.cuda.stream(st_c):
-                    comp["linear_only"] = False
-                    z, const = probes[1], None
-                    for layer in r:
-                        nxt = layer.backward(z)
-                        l = layer.log_abs_det_jacobian(nxt, z)
-                        if torch.is_tensor(l) and l.dim() > 0:
-                            const = False                  # a data-dependent log-det: not an affine run after all
-                            break
-                        l = torch.as_tensor(l, device=dev, dtype=torch.float32)
-                        const = l if const is None else const + l
-                        z = nxt
-                    c = None if const is False else z[0]
-            if const is False:
-                cur.wait_stream(st)
-                cur.wait_stream(st_c)
-                continue
-            for t in (Mt, c, const):
-                t.record_stream(cur)
-            composed[id(r)] = (Mt, c, const, (st, st_c))
-        del pin
-        return plan, composed
+        # would execute one after the other (measured: a 2.1 ms tail).  So the accumulators are created here, on a stream
+        # of their own -- not the calling one either: with the runs composed a few ahead, their backward chains are
+        # visited BETWEEN the blocks of the batch-sized chain, and an accumulation queued on the batch chain's stream
+        # would hold it up until that weight-space chain has finished.  The graphs built later keep the accumulators
+        # alive (`pin` lives as long as the composer).
+        start = torch.cuda.Event()
+        start.record(cur)
+        acc = self._extra_stream("_acc_stream", dev, -8)
+        acc.wait_event(start)
+        with torch.cuda.stream(acc):
+            pin = [p.view_as(p) for r in runs for layer in r for p in layer.parameters() if p.requires_grad]
+        return plan, _RunComposer(self, runs, probes, cur, start, pin)
+
+    def _compose_run(self, r, i, probes, cur, start):
+        """One affine run -> (M^T, c, log-det, streams) or None, on the run's own two streams, forked from `start`."""
+        dev = probes[0].device
+        used = self._side(dev, 2 * (i + 1))
+        st, st_c = used[2 * i], used[2 * i + 1]     # the matrix pass / the shift pass (waits for the factors of the first)
+        st.wait_event(start)
+        st_c.wait_event(start)
+        with composing() as comp:
+            comp["eye"], comp["aux"] = probes[0], st_c
+            # the matrix: the identity through the run's linear parts (shifts off -- taking them from the same rows
+            # and subtracting would make every shift gradient a difference of D bf16-rounded sums) ...
+            with torch.cuda.stream(st):
+                comp["linear_only"] = True
+                Mt = probes[0]
+                for layer in r:
+                    Mt = layer.backward(Mt)
+            # ... and the shift: the zero row through the full maps (8 rows: the GEMM's row granularity).
+            # (Issuing this pass first would put the LU factor nodes and their long backward on its stream, beside
+            # the matrix pass's backward chain -- measured: the tail shrinks by 90 us, but the replayed graph then
+            # starts the nine inversions three at a time instead of together: +500 us before the first coupling.)
+            with torch.cuda.stream(st_c):
+                comp["linear_only"] = False
+                z, const = probes[1], None
+                for layer in r:
+                    nxt = layer.backward(z)
+                    l = layer.log_abs_det_jacobian(nxt, z)
+                    if torch.is_tensor(l) and l.dim() > 0:
+                        const = False                  # a data-dependent log-det: not an affine run after all
+                        break
+                    l = torch.as_tensor(l, device=dev, dtype=torch.float32)
+                    const = l if const is None else const + l
+                    z = nxt
+                c = None if const is False else z[0]
+        if const is False:
+            cur.wait_stream(st)
+            cur.wait_stream(st_c)
+            return None
+        for t in (Mt, c, const):
+            t.record_stream(cur)
+        return Mt, c, const, (st, st_c)
 
     def _prefetch_conditioners(self, y):
         """Tensor-core training: the bf16 operand forms of the conditioner weights (first layer with the coupling mask
@@ -536,11 +589,7 @@ class Flow(torch.nn.Module):
         if not todo:
             return
         cur = torch.cuda.current_stream(y.device)
-        st = self.__dict__.get("_cond_stream")
-        if st is None or st.device != y.device:
-            self._side(y.device, 1)                                  # (the pool, on this device)
-            st = self.__dict__["_cond_stream"] = _lib.new_stream(y.device, priority=-8)   # short and needed first
-            self.__dict__["_side_streams"].append(st)                # joined by the trainer with the others
+        st = self._extra_stream("_cond_stream", y.device, -8)       # short and needed first
         st.wait_stream(cur)
         with torch.cuda.stream(st):
             for layer, cond in todo:
@@ -559,16 +608,16 @@ class Flow(torch.nn.Module):
     def _inverse_layers(self, y, context=None):
         """Layer-wise data -> latent with the accumulated -sum(ladj) (autograd-capable)."""
         if ops.tc_train_enabled() and y.dim() == 2:
-            plan, composed = self._compose_affine_runs(y)
+            plan, composer = self._compose_affine_runs(y)
             self._prefetch_conditioners(y)
         else:
-            plan, composed = list(reversed(self.layers)), {}
-        if ops.tc_train_enabled() and not composed:
+            plan, composer = list(reversed(self.layers)), None
+        if ops.tc_train_enabled() and composer is None:
             self._prefetch_lu_inverses(y)
         total = torch.zeros(y.shape[0], device=y.device, dtype=torch.float32)
         consts = []
         for item in plan:
-            hit = composed.get(id(item)) if isinstance(item, list) else None
+            hit = composer.take(item) if (composer is not None and isinstance(item, list)) else None
             if hit is not None:
                 Mt, c, const, sts = hit
                 for st in sts:

@@ -186,7 +186,16 @@ class LUTransform(BaseTransform):
         if comp is not None:                                  # one product per layer per composition
             hit = comp["W"].get(id(self))
             if hit is None:
-                hit = comp["W"][id(self)] = (ops.LUPackFn.apply(self.L_raw, self.U_raw), _mark(self.L_raw))
+                # on the composition's auxiliary stream: the product (and, in the backward pass, its factor gradients --
+                # three D^3 products) runs beside the chain that consumes it instead of inside it
+                aux = comp.get("aux")
+                if aux is not None and self.L_raw.is_cuda:
+                    aux.wait_stream(torch.cuda.current_stream(self.L_raw.device))
+                    with torch.cuda.stream(aux):
+                        hit = (ops.LUPackFn.apply(self.L_raw, self.U_raw), _mark(self.L_raw))
+                else:
+                    hit = (ops.LUPackFn.apply(self.L_raw, self.U_raw), _mark(self.L_raw))
+                comp["W"][id(self)] = hit
             return _shared(hit)
         return ops.LUPackFn.apply(self.L_raw, self.U_raw)
 
