@@ -119,6 +119,18 @@ __device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity,
   }
 }
 
+// TMA store of one box (shared -> global, bulk async-group completion); coordinates in elements: c0 = column, c1 = row.
+// Rows / columns outside the tensor are not written.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the staging tile may be overwritten once the stores issued so far have READ it
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -376,6 +388,7 @@ struct TcArgs {
   uint32_t stage_bytes;       // bytes per stage (A tile + this CTA's W rows), multiple of 1024
   uint32_t backoff_ns;        // sleep between polls of the epilogue / producer waits (0 = spin)
   int dbg;                    // debug experiments (env USF_TC_DBG): 1 = copy-out without the global store, 2 = no copy-out
+  uint32_t out_stage_bytes;   // > 0: bf16 outputs leave through a staging tile in shared memory and TMA stores (see tmO)
   unsigned long long* trace;  // debug: per-role timestamp records of CTA 0/1 (NULL = off), see usf_debug_tc_trace
   EpiParams ep;
 };
@@ -396,14 +409,17 @@ __device__ __forceinline__ void tc_trace(unsigned long long* buf, int& n, int ti
 // producer / MMA loops carry no instrumentation at all (their instruction count is what bounds the MMA issue rate).
 template <int CG, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs args) {
+usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmO, TcArgs args) {
   // runtime ring geometry: a stage holds 128 rows of A and bn/CG rows of W (1 KB granularity), as many stages as fit
   const int TC_STAGES = args.stages;
   const uint32_t TC_STAGE_BYTES = args.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the chain may start its prologue
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // [ring][output staging tile: 128 rows x 64-column blocks of bf16, 16 KB each, 128B-swizzled like an operand tile][barriers]
+  const uint32_t ostage_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t bar_base = ostage_base + args.out_stage_bytes;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent work unit (CTA / CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -430,6 +446,7 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    if (args.out_stage_bytes != 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
   }
   if (warp == 1) {
     if (CG == 1) {
@@ -639,9 +656,65 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (ok) {
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)a * TC_MAX_BN;
+        bool released = false;
 
         if (dbg & 2) {
           // ablation: accumulator handed straight back
+        } else if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16 && args.out_stage_bytes != 0) {
+          // bf16 activations through shared memory and TMA stores: every full 64-column block of the tile is written
+          // into a staging tile in the swizzled K-major layout (row-per-thread 16-byte pieces, conflict-free) and
+          // leaves as ONE bulk tensor store of 128 rows x 128 bytes; rows past M and columns past N are clipped by
+          // the tensor map.  The remainder of a tile that is not a multiple of 64 columns wide is stored directly.
+          const int nfull = width >> 6;
+          const int rloc = lane_grp * 32 + lane;
+          uint4* ost = reinterpret_cast<uint4*>(smem_raw + (ostage_base - smem_u32(smem_raw)));
+          // the previous tile's stores must have read the staging tile before it is overwritten
+          if (et == 0) tma_store_wait_read();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int c = half * 16; c < width; c += 32) {
+            float v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            const float4* bv = reinterpret_cast<const float4*>(ev + c);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = bv[j4];
+              v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+            }
+            if (ep.mode == EPI_BIAS_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            const int blk = c >> 6;
+            if (blk < nfull) {
+              const int p = (c & 63) >> 3;    // 16-byte piece within the 128-byte row of block `blk`
+              uint4* rowp = ost + (size_t)blk * (TC_A_BYTES / 16) + rloc * 8;
+              rowp[p ^ (rloc & 7)] = q0;
+              rowp[(p + 1) ^ (rloc & 7)] = q1;
+            } else if (rvalid) {
+              st_global_256(reinterpret_cast<uint16_t*>(ep.out) + row * ep.ldo + n0 + c, q0, q1);
+            }
+          }
+          // the accumulator is drained: hand the TMEM buffer back before the staging tile is synchronised and stored
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1 || cta_rank == 0) mbar_arrive(tempty_bar(a));
+            else mbar_arrive_cluster(tempty_bar(a), 0);
+          }
+          released = true;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            const int r0 = (mt * CG + (int)cta_rank) * TC_BM;
+            for (int b = 0; b < nfull; ++b) tma_store_2d(&tmO, ostage_base + (uint32_t)b * TC_A_BYTES, (int)n0 + b * 64, r0);
+            tma_store_commit();
+          }
         } else if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16) {
           for (int c = half * 16; c < width; c += 32) {
             float v[16];
@@ -741,17 +814,20 @@ usf_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
 
         // accumulator drained: hand the TMEM buffer back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 1 || cta_rank == 0) mbar_arrive(tempty_bar(a));
-          else mbar_arrive_cluster(tempty_bar(a), 0);
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1 || cta_rank == 0) mbar_arrive(tempty_bar(a));
+            else mbar_arrive_cluster(tempty_bar(a), 0);
+          }
         }
         tc_trace<DBG>(trb, trn, t, 3);
       }
       a ^= 1;
       if (a == 0) aph ^= 1u;
     }
+    if (args.out_stage_bytes != 0 && et == 0) tma_store_wait_all();   // the last tile's bulk stores complete before exit
   }
 
   tc_fence_before();
@@ -1904,6 +1980,15 @@ static uint32_t tc_backoff_ns() {
   return (uint32_t)v;
 }
 
+// USF_TC_TMA_STORE=1: bf16 outputs of the plain GEMM through a shared-memory staging tile and TMA stores (UTMASTG).
+// Default off: measured on the affine GEMM of C2 (65536 x 784 x 784, profiles/r2/ab_tma_store.txt) 72.3 us against
+// 68.4 us with direct 256-bit stores -- the 48 KB staging tile costs two of the seven ring stages (5 stages alone:
+// 70.7 us) and the two block-wide barriers per tile the rest; the stores themselves were never the bound.
+static bool tc_tma_store() {
+  const char* e = getenv("USF_TC_TMA_STORE");      // read per launch: a test switches it within one process
+  return e != nullptr && e[0] == '1';
+}
+
 // USF_PDL=0 disables programmatic dependent launch of the tensor-core kernels.
 static bool tc_pdl() {
   static int v = -1;
@@ -1974,7 +2059,18 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   args.ep = ep;
   args.reverse = g_tile_reverse;
   args.stage_bytes = TC_A_BYTES + (uint32_t)round_up((int64_t)(bn / cg) * TC_BK * 2, 1024);
-  args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES) / args.stage_bytes);
+  // bf16 activations leave through a staging tile + TMA stores when the ring keeps >= 4 stages beside it (ring depth
+  // >= 4 is flat, profiles/r1_run9) and the output qualifies as a tensor map (USF_TC_TMA_STORE=0: direct 256-bit stores)
+  args.out_stage_bytes = 0;
+  CUtensorMap tmO;
+  memset(&tmO, 0, sizeof(tmO));
+  if ((ep.mode == EPI_BIAS || ep.mode == EPI_BIAS_RELU) && ep.out_bf16 && bn >= 64 && tc_tma_store() && cg == 2) {
+    const uint32_t want = (uint32_t)(bn / 64) * TC_A_BYTES;
+    if ((TC_SMEM_BYTES - TC_FIXED_BYTES - want) / args.stage_bytes >= 4) {
+      if (make_tmap(&tmO, ep.out, M, N, ep.ldo, TC_BM) == USF_OK) args.out_stage_bytes = want;
+    }
+  }
+  args.stages = (int)((TC_SMEM_BYTES - TC_FIXED_BYTES - args.out_stage_bytes) / args.stage_bytes);
   if (args.stages > TC_MAX_STAGES) args.stages = TC_MAX_STAGES;
   {
     static int cap = -1;   // tuning knob: USF_TC_MAX_STAGES caps the ring depth
@@ -1996,7 +2092,7 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   if (cg == 1) {
     int grid = num_sms();
     if (grid > total) grid = (int)total;
-    usf_tc_gemm_kernel<1, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, args);
+    usf_tc_gemm_kernel<1, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmW, tmO, args);
     USF_LAUNCH_CHECK("usf_tc_gemm_kernel<1>");
     return USF_OK;
   }
@@ -2016,8 +2112,8 @@ int tc_gemm(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int6
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl() ? 2 : 1;
-  if (args.trace != nullptr || (args.dbg != 0 && !(args.dbg & 0x200))) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, args));
-  else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, args));
+  if (args.trace != nullptr || (args.dbg != 0 && !(args.dbg & 0x200))) USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, true>, tmA, tmW, tmO, args));
+  else USF_CUDA(cudaLaunchKernelEx(&cfg, usf_tc_gemm_kernel<2, false>, tmA, tmW, tmO, args));
   return USF_OK;
 }
 

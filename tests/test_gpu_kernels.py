@@ -136,6 +136,42 @@ def test_tcgen05_linear_bf16(ops, B, N, K, relu, f32out):
     assert relerr(y.float(), ref) < tol
 
 
+@pytest.mark.parametrize("B,N,K,relu", [(300, 208, 104, True), (1000, 784, 784, False), (4096, 1568, 256, True),
+                                        (20000, 256, 392, True), (130, 64, 64, False), (513, 48, 128, False)])
+def test_tcgen05_linear_bf16_tma_store(ops, B, N, K, relu, monkeypatch):
+    """`USF_TC_TMA_STORE=1`: the bf16 output of the tcgen05 GEMM through a shared-memory staging tile and TMA stores
+    (`cp.async.bulk.tensor ... global.shared::cta`, UTMASTG) is bit-identical to the direct stores, for ragged row
+    counts (rows past M are clipped by the tensor map), tiles that are not a multiple of 64 columns wide (the remainder is
+    stored directly) and tiles narrower than one block (N = 48: the direct path)."""
+    from nf4ad_b200 import _lib
+    from nf4ad_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(B + N + K)
+    ld = (K + 7) // 8 * 8
+    x = torch.zeros(B, ld)
+    x[:, :K] = torch.randn(B, K, generator=g)
+    W = torch.zeros(N, ld)
+    W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g).cuda()
+    xb, Wb = x.cuda().bfloat16(), W.cuda().bfloat16()
+    outs = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("USF_TC_TMA_STORE", on)
+        # (leading dimension wider than N and a sentinel around the tile: nothing outside [B, N] may be touched)
+        y = torch.full((B + 3, N + 16), 7.0, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib().usf_linear_bf16(ptr(xb), ld, ptr(Wb), ld, ptr(b), int(relu), ptr(y), N + 16, 1, B, N, K, stream()),
+                   "usf_linear_bf16")
+        torch.cuda.synchronize()
+        flag = C.c_int(0)
+        _lib.check(lib().usf_debug_tc_timeout(C.byref(flag), 1))
+        assert flag.value == 0
+        assert bool((y[B:] == 7.0).all()) and bool((y[:, N:] == 7.0).all())
+        outs.append(y[:B, :N].clone())
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    ref = xb.float().double().cpu()[:, :K] @ Wb.float().double().cpu()[:, :K].t() + b.double().cpu()
+    ref = ref.clamp_min(0) if relu else ref
+    assert relerr(outs[1].float(), ref) < 6e-3
+
+
 @pytest.mark.parametrize("B,N,relu", [(8, 16, False), (64, 784, True), (257, 100, True), (4096, 256, False)])
 def test_to_bf16_operand_pass(ops, B, N, relu):
     """usf_to_bf16: bf16 row-major copy, bf16 transposed copy (both zero padded to a multiple of 8 columns) and
