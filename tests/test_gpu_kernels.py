@@ -172,13 +172,21 @@ def test_tcgen05_linear_bf16_tma_store(ops, B, N, K, relu, monkeypatch):
     assert relerr(outs[1].float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("B,N,relu", [(8, 16, False), (64, 784, True), (257, 100, True), (4096, 256, False)])
-def test_to_bf16_operand_pass(ops, B, N, relu):
+@pytest.mark.parametrize("B,N,relu,ld", [(8, 16, False, 0), (64, 784, True, 0), (257, 100, True, 0), (4096, 256, False, 0),
+                                         (4096, 1568, True, 0), (130, 99, True, 0), (131, 99, True, 104), (70, 5, False, 8),
+                                         (1000, 784, False, 800)])
+def test_to_bf16_operand_pass(ops, B, N, relu, ld):
     """usf_to_bf16: bf16 row-major copy, bf16 transposed copy (both zero padded to a multiple of 8 columns) and
-    fp32 column sums of the (ReLU-gated) input, in one pass -- bit-exact against torch's round-to-nearest-even."""
+    fp32 column sums of the (ReLU-gated) input, in one pass -- bit-exact against torch's round-to-nearest-even.
+    16-byte aligned rows take the vectorised kernel (64 x 64 tiles; `ld` > 0: a strided view whose width is not a multiple
+    of 4), anything else the element-wise one."""
     g = torch.Generator().manual_seed(B + N)
-    x = torch.randn(B, N, generator=g).cuda()
-    mask = torch.randn(B, N, generator=g).cuda() if relu else None
+    if ld:
+        x = torch.randn(B, ld, generator=g).cuda()[:, :N]
+        mask = torch.randn(B, ld, generator=g).cuda()[:, :N] if relu else None
+    else:
+        x = torch.randn(B, N, generator=g).cuda()
+        mask = torch.randn(B, N, generator=g).cuda() if relu else None
     rows, tr, cs = ops.to_bf16(x, relu_mask=mask, want_rows=True, want_transposed=True, want_colsum=True)
     v = torch.where(mask > 0, x, torch.zeros_like(x)) if relu else x
     ref = v.to(torch.bfloat16)
