@@ -53,7 +53,8 @@ const char* usf_last_error(void);
 int usf_device_ok(void);
 /* A new non-blocking stream on the current device (and its release).  The host side forks the weight-space work of a
  * training step (one chain per affine run, `Flow._compose_affine_runs`) onto ~20 streams that must be DISTINCT: a
- * framework-level stream pool that hands the same stream out twice would order two chains after each other.
+ * framework-level stream pool that hands the same stream out twice would order two chains after each other.  (The
+ * host side keeps ONE such set per device for the whole process, `_lib.pooled_stream`: flows and trainers come and go.)
  * priority: 0 = default, negative = more urgent (clamped to the device's range): the batch-sized chain of the step runs
  * above the weight-space chains, and those in the order the batch will need them. */
 int usf_stream_create(int priority, usf_stream_t* out);

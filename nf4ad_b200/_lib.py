@@ -164,6 +164,21 @@ def new_stream(device, priority=0):
     return torch.cuda.ExternalStream(handle.value, device=device)
 
 
+_STREAM_POOL = {}
+
+
+def pooled_stream(device, name, priority=0):
+    """The process-wide stream `name` of `device`, created on first use.  Flows and trainers come and go (one per
+    hyper-parameter trial); the streams they fork their weight-space work onto are shared per device instead of being
+    created per object, so a long sweep does not accumulate thousands of CUDA streams."""
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+    st = _STREAM_POOL.get(key)
+    if st is None:
+        st = _STREAM_POOL[key] = new_stream(device, priority)
+    return st
+
+
 def stream():
     """torch's current stream of the current device (`require_cuda` has checked that the operands live there)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -466,7 +466,7 @@ class Flow(torch.nn.Module):
         while len(streams) < n:
             # two streams per affine run, in the order the batch-sized chain consumes the runs: the earlier a run is
             # needed, the more urgent its stream (the chain itself runs above all of them: DataParallelTrainer)
-            st = _lib.new_stream(device, priority=min(0, -4 + len(streams) // 2))
+            st = _lib.pooled_stream(device, ("run", len(streams)), priority=min(0, -4 + len(streams) // 2))
             streams.append(st)
             self.__dict__["_side_streams"].append(st)
         return streams[:n]
@@ -476,7 +476,7 @@ class Flow(torch.nn.Module):
         self._side(device, 1)                                        # (resets everything on a device change)
         st = self.__dict__.get(key)
         if st is None:
-            st = self.__dict__[key] = _lib.new_stream(device, priority=priority)
+            st = self.__dict__[key] = _lib.pooled_stream(device, key, priority=priority)
             self.__dict__["_side_streams"].append(st)
         return st
 

@@ -555,7 +555,7 @@ class DataParallelTrainer:
         # weight-space chains the flow forks beside it (`Flow._compose_affine_runs`, lower priorities).
         from . import _lib
         if self._capture_stream is None or self._capture_stream.device != static_x.device:
-            self._capture_stream = _lib.new_stream(static_x.device, priority=-8)
+            self._capture_stream = _lib.pooled_stream(static_x.device, "capture", priority=-8)
         # thread_local: NCCL's watchdog thread may query events while this thread captures
         with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
             if self._flat is not None:
