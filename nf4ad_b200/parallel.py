@@ -534,7 +534,28 @@ class DataParallelTrainer:
         else:
             self.opt.zero_grad(set_to_none=True)
 
+    def _step_stream(self, device):
+        from . import _lib
+        if self._capture_stream is None or self._capture_stream.device != device:
+            self._capture_stream = _lib.pooled_stream(device, "capture", priority=-8)
+        return self._capture_stream
+
     def _eager_step(self, batch):
+        if batch.is_cuda and self.use_graph:
+            # The warm-up steps run on the stream the step will be captured on, not on the caller's: a parameter's
+            # gradient accumulator keeps the stream of its first use for as long as anything references the graph, and
+            # one left on the legacy default stream makes a later capture fail ("would make the legacy stream depend on
+            # a capturing stream").
+            st, cur = self._step_stream(batch.device), torch.cuda.current_stream(batch.device)
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out = self._eager_step_on_current(batch)
+            batch.record_stream(st)
+            cur.wait_stream(st)
+            return out
+        return self._eager_step_on_current(batch)
+
+    def _eager_step_on_current(self, batch):
         self._zero_grad()
         loss = self.loss_fn(batch)
         loss.backward()
@@ -555,11 +576,8 @@ class DataParallelTrainer:
         # The step is captured on a stream of the highest priority: graph kernel nodes inherit the priority of the stream
         # they were captured on, and the batch-sized chain (the step's critical path) must not queue behind the
         # weight-space chains the flow forks beside it (`Flow._compose_affine_runs`, lower priorities).
-        from . import _lib
-        if self._capture_stream is None or self._capture_stream.device != static_x.device:
-            self._capture_stream = _lib.pooled_stream(static_x.device, "capture", priority=-8)
         # thread_local: NCCL's watchdog thread may query events while this thread captures
-        with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
+        with torch.cuda.graph(graph, stream=self._step_stream(static_x.device), capture_error_mode="thread_local"):
             if self._flat is not None:
                 self._begin_sync()          # the memset of the flat gradient buffer is part of the replayed step
             loss = self.loss_fn(static_x)
@@ -606,7 +624,7 @@ class DataParallelTrainer:
             except Exception as e:                     # e.g. a conditioner that is not capture-safe
                 import warnings
                 self.use_graph = False
-                self.graph_error = e
+                self.graph_error = e.with_traceback(None)      # (no frames: they would keep the failed step's graph alive)
                 warnings.warn(f"nf4ad_b200: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
                               "continuing with eager steps", RuntimeWarning)
                 self._abandon_capture(batch.device)
@@ -622,7 +640,18 @@ class DataParallelTrainer:
         from . import ops
         for m in self.flow.modules():
             m.__dict__.pop("_A_pre", None)
+            m.__dict__.pop("_usf_pre", None)
+        self.flow.__dict__.pop("_cond_pending", None)
         torch.cuda.synchronize(device)
         for st in list(getattr(self.flow, "_side_streams", None) or []) + list(ops._WGRAD_STREAMS.values()):
             st.synchronize()
         self.opt.zero_grad(set_to_none=True)
+        # A capture that dies half way leaves the device's default generator in its "capturing" state (capture_end never
+        # reached the generator's epilogue): the next random draw outside a graph -- the soft-training noise of the eager
+        # fallback -- then raises "Offset increment outside graph capture".  An empty capture runs prologue and epilogue.
+        try:
+            with torch.cuda.device(device):
+                with torch.cuda.graph(torch.cuda.CUDAGraph(), capture_error_mode="thread_local"):
+                    pass
+        except Exception:
+            pass

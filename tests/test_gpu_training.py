@@ -220,3 +220,71 @@ def test_own_streams_are_distinct_and_prioritised():
     assert float(x[0]) == 2.0
     for s in streams:
         _lib.check(_lib.lib().usf_stream_destroy(_lib.C.c_void_p(s.cuda_stream)), "usf_stream_destroy")
+
+
+def test_conditional_flow_trains_in_the_tensor_core_tier(O, P):
+    """A conditional flow (soft training: `ConditionalDenseNN` conditioners on `cat([context, x])`, nf4ad/flows.py:56-57,
+    transforms.py:71-74) in the bf16 training tier: the coupling mask is folded into the first conditioner layer with
+    the context columns left alone, the affine runs are composed.  Loss within the tier of the fp64 oracle's, gradients
+    in its direction, and `Flow.fit` runs on the graph trainer."""
+    import numpy as np
+    D, B = 32, 256
+    torch.manual_seed(2)
+    prior = lambda ns, dev: ns.dist.Uniform(torch.tensor(0.0, device=dev), torch.tensor(0.2, device=dev))
+    kw = dict(affine_conjugation=True, prior_scale=1.0, soft_training=True)
+    fo = build_flow(O, "NonUSFlow", D, 3, ("cond2", [64]), training_noise_prior=prior(O, "cpu"), **kw)
+    tame(fo, 0.25)
+    fp = build_flow(P, "NonUSFlow", D, 3, ("cond2", [64]), training_noise_prior=prior(P, "cpu"), **kw)
+    fp.load_state_dict(fo.state_dict())
+    fo, fp = fo.double(), fp.to("cuda").train()
+    g = torch.Generator().manual_seed(3)
+    x, ctx = torch.randn(B, D, generator=g), 0.2 * torch.rand(B, 1, generator=g)
+    l64 = -fo.log_prob(x.double(), ctx.double()).mean()
+    l64.backward()
+    g64 = {n: p.grad for n, p in fo.named_parameters() if p.grad is not None}
+    fp.precision = "bf16"
+    loss = -fp.log_prob(x.cuda(), ctx.cuda()).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(l64)) <= 1e-2 * max(1.0, abs(float(l64)))
+    for n, p in fp.named_parameters():
+        if n in g64 and float(g64[n].norm()) > 1e-6:
+            got, ref = p.grad.double().cpu(), g64[n]
+            cos = float((ref * got).sum() / (ref.norm() * got.norm()).clamp_min(1e-30))
+            assert cos > 0.97, (n, cos)
+    fp.zero_grad(set_to_none=True)
+    data = torch.randn(512, D, generator=g) * 0.5 + 0.3
+    # (a) While `loss` -- and with it the autograd graph of that step on the DEFAULT stream -- is alive, so are its
+    # gradient accumulators; a captured step that reaches them would make the legacy stream wait for a capturing one.
+    # The trainer must notice, warn, recover (streams joined, the generator out of its capture state: the soft-training
+    # noise draws random numbers) and go on with eager steps.
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        losses = fp.fit(data, torch.optim.Adam, {"lr": 1e-3}, batch_size=64, epochs=2)
+    assert len(losses) == 2 and np.all(np.isfinite(losses))
+    if fp.fit_graph_replays == 0:
+        assert any("capture of the training step failed" in str(w.message) for w in caught)
+    # (b) the normal case: nothing of an earlier step is kept -> graph replay
+    del loss
+    import gc
+    gc.collect()
+    losses = fp.fit(data, torch.optim.Adam, {"lr": 1e-3}, batch_size=64, epochs=4)
+    assert len(losses) == 4 and np.all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert fp.fit_graph_replays >= 8 * 4 - 4
+
+
+def test_many_flows_share_one_set_of_streams(P):
+    """A sweep builds and trains many flows in one process (hyperopt): the side streams are per device, not per flow."""
+    from nf4ad_b200 import _lib
+    x = torch.randn(64, 32, device="cuda")
+    seen = None
+    for i in range(4):
+        torch.manual_seed(i)
+        flow = build_flow(P, "NonUSFlow", 32, 2, ("mlp", [32]), affine_conjugation=True).to("cuda").train()
+        flow.precision = "bf16"
+        (-flow.log_prob(x).mean()).backward()
+        torch.cuda.synchronize()
+        n = len(_lib._STREAM_POOL)
+        assert seen is None or n == seen, (seen, n)
+        seen = n
