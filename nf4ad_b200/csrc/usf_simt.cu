@@ -1097,6 +1097,10 @@ __global__ void usf_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, con
                                    __nv_bfloat16* rows, int64_t ldr, __nv_bfloat16* tr, int64_t ldt, float* colsum,
                                    int64_t B, int64_t N, int64_t Bp, int64_t Np) {
   __shared__ float tile[32][33];
+  // the tensor-core GEMM that consumes this pass is launched with programmatic stream serialization: let it run its
+  // prologue (barrier init, TMEM allocation, tensor-map prefetch, cluster sync: 3-4 us) beside this kernel; it waits
+  // (griddepcontrol.wait) for this grid to complete before it touches the operands
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   float cs = 0.f;
@@ -1143,6 +1147,7 @@ usf_to_bf16_v4_kernel(const float* __restrict__ x, int64_t ldx, const float* __r
                       int64_t N, int64_t Bp, int64_t Np) {
   __shared__ float tile[64][65];
   __shared__ float part[16][64];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (see usf_to_bf16_kernel)
   const int t = threadIdx.x;
   const int q = t & 15, g = t >> 4;                  // 16 threads x 4 columns across a row, 16 rows per pass
   const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
