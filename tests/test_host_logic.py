@@ -146,3 +146,40 @@ def test_dropin_import_names_resolve_to_the_product():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300,
                        env=dict(os.environ, PYTHONPATH=ROOT))
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_affine_run_plan_groups_the_layers_between_couplings():
+    """`Flow._compose_affine_runs` (host logic, no CUDA): the layers of the data -> latent pass grouped into maximal runs
+    of affine layers between couplings -- with affine conjugation K + 1 runs for K blocks, each run but the last the affine
+    layer of one block followed by the inverse of the previous block's -- and on the CPU (or for a batch the tensor-core GEMMs do not take) nothing is
+    composed.  `conditioner_weights` folds the coupling mask into the first layer only."""
+    import nf4ad_b200
+    from _cases import build_flow
+    from nf4ad_b200 import stack
+    from nf4ad_b200.transforms import InverseTransform, LUTransform, conditioner_weights
+    ns = nf4ad_b200.namespace()
+    K, D = 3, 16
+    flow = build_flow(ns, "NonUSFlow", D, K, ("mlp", [32]), affine_conjugation=True, prior_scale=1.0)
+    plan, composer = flow._compose_affine_runs(torch.zeros(8, D))
+    assert composer is None                                           # CPU tensor: layer-wise
+    runs = [item for item in plan if isinstance(item, list)]
+    couplings = [item for item in plan if not isinstance(item, list)]
+    assert len(couplings) == K and all(stack._is_coupling(c) for c in couplings)
+    assert len(runs) == K + 1
+    # reversed layer list: [scale, final affine, inverse of block K's], coupling K, [block K's affine, inverse of block
+    # K-1's], ..., coupling 1, [block 1's affine]
+    assert [len(r) for r in runs] == [3] + [2] * (K - 1) + [1]
+    for r in runs[:-1]:                            # head of one block (its inverse direction) after the tail of the next
+        assert isinstance(r[-1], InverseTransform) and not isinstance(r[-2], InverseTransform)
+    assert all(any(isinstance(m, LUTransform) for layer in r for m in layer.modules()) for r in runs)
+    flat = [layer for item in plan for layer in (item if isinstance(item, list) else [item])]
+    assert flat == list(reversed(list(flow.layers)))                  # nothing lost, order kept
+    # mask folding: (x * m) W^T == x (W * m)^T for the first layer, the others untouched
+    cpl = couplings[0]
+    ws = conditioner_weights(cpl.conditioner, cpl.mask)
+    lin = [m for m in cpl.conditioner.modules() if isinstance(m, torch.nn.Linear)]
+    assert len(ws) == len(lin) and ws[1][0] is lin[1].weight and ws[0][1] is lin[0].bias
+    x = torch.randn(5, D)
+    m = cpl.mask.reshape(-1)
+    assert torch.allclose((x * m) @ lin[0].weight.t(), x @ ws[0][0].t(), atol=1e-6)
+    assert conditioner_weights(torch.nn.Sequential(torch.nn.Tanh()), cpl.mask) is None      # opaque conditioner
