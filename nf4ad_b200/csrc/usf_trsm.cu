@@ -78,26 +78,33 @@ usf_lu_diag_inv_kernel(const float* __restrict__ L_raw, const float* __restrict_
 }
 
 constexpr int KC = 128;         // k-chunk streamed per iteration (4 column blocks): amortises the L2 latency of E tiles
-constexpr int KP = KC + 4;      // smem pitch of the E chunk (plain: 16-byte aligned rows for float4 reads)
-constexpr int KPT = KC + 5;     // transposed source: odd pitch keeps the transposing stores conflict-free (scalar reads)
+constexpr int EKP = NB + 4;     // pitch of the k-major E chunk  Es[kk][c]  (16-byte aligned rows: one float4 = 4 columns)
+constexpr int XPAD = 4;         // Xs row pitch = Dp + 4: four different rows read by one warp fall into different banks
+constexpr int KSPLIT = 4;       // k-splits of a chunk (32 k each): 64 threads x (4 rows x 4 columns) per split
 
 // IDENT: the right-hand sides are the rows of the identity (X = E^{-T} row by row, i.e. the inverse of a triangular
 // matrix).  Row r of the solution then vanishes before (LOWER) / after (upper) column r, so a CTA skips the column
 // blocks on that side of its own rows and starts every accumulation at them: half the work of a dense solve.
+//
+// Accumulation: thread (ks, rq, cq) owns rows rq + 8 i (a warp's four row values are neighbours: with the row pitch
+// Dp + 4 their float4 reads fall into different banks) x columns 4 cq .. +3 of the 32 x 32 block over the k-quarter
+// ks of every chunk: per 4 k it reads 4 float4 of X (4 k of one row each, warp-broadcast) and 4 float4 of E (4 columns
+// at one k each) for 64 FMAs -- 8 shared-memory reads per 64 FMAs; the first form of this kernel (8 rows x 1 column per
+// thread) needed 9 per 32 and was bound by them.
 template <bool LOWER, bool TRANS, bool IDENT>
 __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int64_t D, int Dp,
                                                const float* __restrict__ Dinv, const float* rhs, int64_t ldr,
                                                const float* __restrict__ bias, float* X, int64_t ldx, int64_t B) {
   extern __shared__ __align__(16) float sm[];
-  float* Xs = sm;                                                                       // [ROWS][Dp]
-  constexpr int PITCH = TRANS ? KPT : KP;
-  float* Es = sm + (size_t)ROWS * Dp;                                                    // [NB][PITCH]   Es[c][kk]
-  float(*Ts)[EP] = reinterpret_cast<float(*)[EP]>(sm + (size_t)ROWS * Dp + NB * KPT);    // [ROWS][EP] (16B aligned)
-  float(*Ds)[EP] = reinterpret_cast<float(*)[EP]>(sm + (size_t)ROWS * Dp + NB * KPT + ROWS * EP);   // [NB][EP]
-  float(*Ps)[EP] = reinterpret_cast<float(*)[EP]>(sm + (size_t)ROWS * Dp + NB * KPT + (ROWS + NB) * EP);  // partial sums
+  const int XP = Dp + XPAD;
+  float* Xs = sm;                                                                       // [ROWS][XP]
+  float* Es = sm + (size_t)ROWS * XP;                                                    // [KC][EKP]   Es[kk][c]
+  float(*Ts)[EP] = reinterpret_cast<float(*)[EP]>(Es + KC * EKP);                        // [ROWS][EP] (16B aligned)
+  float(*Ds)[EP] = reinterpret_cast<float(*)[EP]>(Es + KC * EKP + ROWS * EP);            // [NB][EP]
+  float(*Ps)[ROWS][EP] = reinterpret_cast<float(*)[ROWS][EP]>(Es + KC * EKP + (ROWS + NB) * EP);   // [KSPLIT] partial sums
   const int tid = threadIdx.x;
-  const int kh = tid >> 7;                          // which half of every k-chunk this thread accumulates
-  const int c = tid & 31, rg = (tid & 127) >> 5;    // column c of the block, rows rg*8 .. rg*8+7
+  const int ks = tid >> 6, rq = (tid & 63) >> 3, cq = tid & 7;      // accumulation: k-split, row quad, column quad
+  const int kh = tid >> 7, c = tid & 31, rg = (tid & 127) >> 5;      // diagonal-block stage: column c, rows rg*8 + kh*4 .. +3
   const int64_t r0 = (int64_t)blockIdx.x * ROWS;
   const int nblk = Dp / NB;
 
@@ -112,7 +119,7 @@ __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int6
       v = rhs[gr * ldr + k];
       if (bias != nullptr) v -= bias[k];
     }
-    Xs[e] = v;
+    Xs[(size_t)r * XP + k] = v;
   }
   __syncthreads();
 
@@ -134,7 +141,7 @@ __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int6
       const int e = tid + i * THREADS;
       int cc, kk;
       if (TRANS) { kk = e >> 5; cc = e & 31; } else { cc = e >> 7; kk = e & 127; }
-      Es[cc * PITCH + kk] = reg[i];
+      Es[kk * EKP + cc] = reg[i];
     }
   };
 
@@ -146,7 +153,11 @@ __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int6
     const int lo = LOWER ? (IDENT ? own * NB : 0) : (jb + 1) * NB;
     const int hi = LOWER ? jb * NB : (IDENT ? (own + 1) * NB : Dp);
     const int nchunk = (hi - lo + KC - 1) / KC;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float reg[16];
     if (nchunk > 0) load_chunk(jb, lo, lo, hi, reg);
     // the inverse of the diagonal block is independent of the accumulation: fetch it early
@@ -160,41 +171,43 @@ __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int6
       __syncthreads();
       if (q + 1 < nchunk) load_chunk(jb, k0 + KC, lo, hi, reg);   // prefetch the next chunk (overlaps the FMAs below)
       const int kw = hi - k0 < KC ? hi - k0 : KC;                  // multiple of 32
-      const float* xrow = Xs + (size_t)(rg * 8) * Dp + k0;
-      const int kend = kw < (kh + 1) * (KC / 2) ? kw : (kh + 1) * (KC / 2);
-      for (int kk = kh * (KC / 2); kk < kend; kk += 4) {
-        float4 ev;
-        if (TRANS) {
-          const float* ep = Es + c * PITCH + kk;
-          ev = make_float4(ep[0], ep[1], ep[2], ep[3]);
-        } else {
-          ev = *reinterpret_cast<const float4*>(Es + c * PITCH + kk);
-        }
+      if (ks * 32 < kw) {                                          // this split's k-quarter is part of the chunk
+        const float* xrow = Xs + (size_t)rq * XP + k0 + ks * 32;        // rows rq, rq + 8, rq + 16, rq + 24
+        const float* erow = Es + (ks * 32) * EKP + cq * 4;
+#pragma unroll 2
+        for (int kk = 0; kk < 32; kk += 4) {
+          float4 xv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 xv = *reinterpret_cast<const float4*>(xrow + (size_t)i * Dp + kk);   // warp-broadcast
-          acc[i] = fmaf(xv.x, ev.x, acc[i]);
-          acc[i] = fmaf(xv.y, ev.y, acc[i]);
-          acc[i] = fmaf(xv.z, ev.z, acc[i]);
-          acc[i] = fmaf(xv.w, ev.w, acc[i]);
+          for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + (size_t)(8 * i) * XP + kk);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 ev = *reinterpret_cast<const float4*>(erow + (kk + u) * EKP);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xs = u == 0 ? xv[i].x : (u == 1 ? xv[i].y : (u == 2 ? xv[i].z : xv[i].w));
+              acc[i][0] = fmaf(xs, ev.x, acc[i][0]);
+              acc[i][1] = fmaf(xs, ev.y, acc[i][1]);
+              acc[i][2] = fmaf(xs, ev.z, acc[i][2]);
+              acc[i][3] = fmaf(xs, ev.w, acc[i][3]);
+            }
+          }
         }
       }
     }
-    // combine the two k-halves, then Ts = R_j - acc ; Ds = inverse of the diagonal block
-    if (kh == 1) {
+    // partial sums of the k-splits, then Ts = R_j - sum ; Ds = inverse of the diagonal block
 #pragma unroll
-      for (int i = 0; i < 8; ++i) Ps[rg * 8 + i][c] = acc[i];
-    }
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(&Ps[ks][rq + 8 * i][cq * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * THREADS;
       Ds[e >> 5][e & 31] = dreg[i];
     }
     __syncthreads();
-    if (kh == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        Ts[rg * 8 + i][c] = Xs[(size_t)(rg * 8 + i) * Dp + jb * NB + c] - acc[i] - Ps[rg * 8 + i][c];
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * THREADS, r = e >> 5, cc = e & 31;
+      Ts[r][cc] = Xs[(size_t)r * XP + jb * NB + cc] - (Ps[0][r][cc] + Ps[1][r][cc]) - (Ps[2][r][cc] + Ps[3][r][cc]);
     }
     __syncthreads();
     // x[r][c] = sum_c' Dinv[c][c'] * t[r][c']   (each k-half group takes 4 of the thread's 8 rows)
@@ -213,14 +226,14 @@ __device__ __forceinline__ void trsm_fast_body(const float* __restrict__ T, int6
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) Xs[(size_t)(rb + i) * Dp + jb * NB + c] = xo[i];
+    for (int i = 0; i < 4; ++i) Xs[(size_t)(rb + i) * XP + jb * NB + c] = xo[i];
     __syncthreads();
   }
 
   for (int e = tid; e < ROWS * Dp; e += THREADS) {
     const int r = e / Dp, k = e - r * Dp;
     const int64_t gr = r0 + r;
-    if (gr < B && k < D) X[gr * ldx + k] = Xs[e];
+    if (gr < B && k < D) X[gr * ldx + k] = Xs[(size_t)r * XP + k];
   }
 }
 
@@ -239,7 +252,9 @@ usf_lu_tri_inverse_kernel(const float* __restrict__ L_raw, const float* __restri
   else trsm_fast_body<false, true, true>(L_raw, D, Dp, DinvL, nullptr, 0, nullptr, W, D, D);
 }
 
-size_t fast_smem_bytes(int Dp) { return sizeof(float) * ((size_t)ROWS * Dp + NB * KPT + (2 * ROWS + NB) * EP); }
+size_t fast_smem_bytes(int Dp) {
+  return sizeof(float) * ((size_t)ROWS * (Dp + XPAD) + KC * EKP + (ROWS + NB) * EP + (size_t)KSPLIT * ROWS * EP);
+}
 
 }  // namespace
 
