@@ -553,16 +553,20 @@ class Flow(torch.nn.Module):
             # starts the nine inversions three at a time instead of together: +500 us before the first coupling.)
             with torch.cuda.stream(st_c):
                 comp["linear_only"] = False
+                # the parameter-only log-dets first: created before the shift chain, their backward nodes are visited
+                # after it, so the ~15 tiny kernels of their gradients do not sit between the chain's backward and the
+                # factor gradients that wait for it (an affine layer's log-det does not look at its arguments)
                 z, const = probes[1], None
                 for layer in r:
-                    nxt = layer.backward(z)
-                    l = layer.log_abs_det_jacobian(nxt, z)
+                    l = layer.log_abs_det_jacobian(z, z)
                     if torch.is_tensor(l) and l.dim() > 0:
                         const = False                  # a data-dependent log-det: not an affine run after all
                         break
                     l = torch.as_tensor(l, device=dev, dtype=torch.float32)
                     const = l if const is None else const + l
-                    z = nxt
+                if const is not False:
+                    for layer in r:
+                        z = layer.backward(z)
                 c = None if const is False else z[0]
         if const is False:
             cur.wait_stream(st)
