@@ -532,7 +532,7 @@ class Flow(torch.nn.Module):
         return plan, _RunComposer(self, runs, probes, cur, start, pin)
 
     def _compose_run(self, r, i, probes, cur, start):
-        """One affine run -> (M^T, c, log-det, streams) or None, on the run's own two streams, forked from `start`."""
+        """One affine run -> (M^T, c, log-det, streams, bf16 operands of M | None) or None, on the run's own two streams, forked from `start`."""
         dev = probes[0].device
         used = self._side(dev, 2 * (i + 1))
         st, st_c = used[2 * i], used[2 * i + 1]     # the matrix pass / the shift pass (waits for the factors of the first)
@@ -572,9 +572,16 @@ class Flow(torch.nn.Module):
             cur.wait_stream(st)
             cur.wait_stream(st_c)
             return None
+        operands = None
+        if ops._TC_TRAIN == 1:
+            # the bf16 operand forms of the composed matrix, on the run's stream rather than in front of the batch's GEMM
+            with torch.cuda.stream(st):
+                operands = ops.weight_operands(Mt.detach(), w_transposed=True)
+            for t in operands:
+                t.record_stream(cur)
         for t in (Mt, c, const):
             t.record_stream(cur)
-        return Mt, c, const, (st, st_c)
+        return Mt, c, const, (st, st_c), operands
 
     def _prefetch_conditioners(self, y):
         """Tensor-core training: the bf16 operand forms of the conditioner weights (first layer with the coupling mask
@@ -626,10 +633,10 @@ class Flow(torch.nn.Module):
         for item in plan:
             hit = composer.take(item) if (composer is not None and isinstance(item, list)) else None
             if hit is not None:
-                Mt, c, const, sts = hit
+                Mt, c, const, sts, operands = hit
                 for st in sts:
                     torch.cuda.current_stream(y.device).wait_stream(st)
-                y = ops.linear_fn(y, Mt, c, False, w_transposed=True)
+                y = ops.linear_fn(y, Mt, c, False, w_transposed=True, operands=operands)
                 consts.append(const)
                 continue
             for layer in (item if isinstance(item, list) else (item,)):
