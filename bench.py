@@ -32,6 +32,7 @@ ALG_BYTES_PER_SAMPLE = 4 * D + 4
 LAST_LAYER_GAIN = 0.25             # trained-flow-like activations (see DESIGN.md "Synthetic weights")
 CPU_ROWS = 65536                   # the CPU arm scores B = 65536 (and B = 32) like the GPU arm
 CPU_SMALL_ROWS = 32
+TRAIN_SMALL_ROWS = 64              # training B per GPU = 64 (the reference's regime) and 4096
 # DRAM bytes per launch at 65536 rows from the committed ncu capture (profiles/): {kind: bytes}; filled from
 # profiles/r2/ncu_dram_bytes.json when present (written by scripts/ncu_summary.py), else the round-1 capture
 NCU_DRAM_BYTES = {"affine_gemm": 174.4e6, "conditioner+coupling": 120.3e6, "final_gemm+base": 174.4e6}
@@ -301,6 +302,50 @@ def cpu_reference_run(steps, warmup, rows, config=DEFAULT_CONFIG):
     ts.sort()
     med = ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2])
     return rows / med, cores, med * 1e3, kind
+
+
+def torch_eager_gpu_run(steps, warmup, rows, dev, config=DEFAULT_CONFIG):
+    """"also record torch-eager ON THE B200 (cuBLAS / ATen) as the existing GPU kernels to beat".  The same
+    classes as `cpu_reference_run` (the reference's own NonUSFlow + MaskedAffineCoupling on the oracle's src.usflows / pyro
+    shim), moved to the GPU with `.to(device)` and scored exactly as `adbench_wrapper.py:419-424` does: fp32, eval(),
+    no_grad(), one call on the whole batch -- every layer an ATen op, the GEMMs cuBLAS SGEMM (torch's default
+    `allow_tf32 = False`) and, second, cuBLAS TF32 (`allow_tf32 = True`: the tensor-core form of the stock path).
+    None of this repo's kernels run here.  Part of the cpu_baseline leg (a baseline, never the product path).
+    -> dict, or {"error": ...} if the shim does not run on this device."""
+    import oracle
+    out = {"api": "reference NonUSFlow.log_prob on cuda through torch eager (ATen + cuBLAS), fp32, eval()+no_grad()",
+           "rows": rows, "steps": steps, "warmup": warmup}
+    try:
+        kind = "reference" if oracle.ref_available() else "port"
+        ns = oracle.load_ref() if kind == "reference" else oracle.load()
+        out["kind"] = kind
+        flow = build_config_flow(ns, config, dev)
+        d = CONFIGS[config][1]
+        x = torch.randn(rows, d, generator=torch.Generator().manual_seed(42)).to(dev)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        try:
+            for tag, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                with torch.no_grad():
+                    for _ in range(warmup):
+                        flow.log_prob(x)
+                    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                    for a, b in evs:
+                        a.record()
+                        lp = flow.log_prob(x)
+                        b.record()
+                torch.cuda.synchronize(dev)
+                ts = sorted(a.elapsed_time(b) for a, b in evs)
+                med = ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2])
+                out[tag] = {"value": rows / (med * 1e-3), "unit": "samples/s", "ms_per_step": med,
+                            "finite": bool(torch.isfinite(lp).all())}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        del flow, x
+        torch.cuda.empty_cache()
+    except Exception as e:                      # a baseline must never take the bench line down with it
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
 
 
 def main():
@@ -606,7 +651,7 @@ def main():
 
     # ---- training step (second BASELINE metric): fwd + hand-written backward kernels + (DP all-reduce) + Adam
     train_ms, train_B, train_steps, train_graph = float("nan"), args.train_rows, args.train_steps, False
-    train32_ms = train3_ms = float("nan")
+    train32_ms = train3_ms = train_small_ms = float("nan")
     if train_steps > 0:
         from nf4ad_b200.parallel import DataParallelTrainer
         from nf4ad_b200.optim import FusedAdam
@@ -638,10 +683,35 @@ def main():
                 train32_ms = g0.elapsed_time(g1)
             assert bool(torch.isfinite(loss))
             del tflow, opt, trainer
-    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms], device=dev, dtype=torch.float64)
+        # the reference's own batch size (training B per GPU = 64 and 4096; `adbench_wrapper.py:310`): the step
+        # is launch / dependency-latency bound there, which is what the one-graph replay is for
+        # (single-GPU line only: the multi-rank runs report the B = 4096 step above)
+        if world == 1:
+            try:
+                xs = x[:TRAIN_SMALL_ROWS]
+                tflow = build_config_flow(P, args.config, dev).train()
+                tflow.precision = "bf16"
+                opt = FusedAdam(tflow.parameters(), lr=1e-4)
+                trainer = DataParallelTrainer(tflow, opt)
+                for _ in range(5):
+                    trainer.step(xs)
+                torch.cuda.synchronize(dev)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(train_steps):
+                    loss = trainer.step(xs)
+                g1.record()
+                torch.cuda.synchronize(dev)
+                if bool(torch.isfinite(loss)):
+                    train_small_ms = g0.elapsed_time(g1)
+                del tflow, opt, trainer
+            except Exception as e:              # an extra line must not take the headline down
+                print(f"bench: small-batch training line skipped ({type(e).__name__}: {e})", file=sys.stderr, flush=True)
+    t = torch.tensor([ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms, train_small_ms],
+                     device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms = (float(v) for v in t)
+    ms_total, e2e_ms, train_ms, train32_ms, train3_ms, pageable_ms, h2d_only_ms, train_small_ms = (float(v) for v in t)
 
     if rank == 0:
         steps_prof = 3
@@ -767,6 +837,12 @@ def main():
                                              "ms_per_step": train3_ms / train_steps},
                              "fp32_path": {"value": train_B * world * train_steps / (train32_ms * 1e-3),
                                            "ms_per_step": train32_ms / train_steps}}
+            if train_small_ms == train_small_ms:          # (not NaN: measured on this run)
+                line["train"]["small_batch"] = {
+                    "batch_per_gpu": TRAIN_SMALL_ROWS,
+                    "value": TRAIN_SMALL_ROWS * world * train_steps / (train_small_ms * 1e-3),
+                    "ms_per_step": train_small_ms / train_steps,
+                    "note": "the reference's own batch size (adbench_wrapper.py:310), bf16 tier, one CUDA-graph replay per step"}
         if world == 1 and not args.no_cpu_baseline:
             # B = 65536 (and 32), 3 warm-ups, median of 10 -- about 30 s of host work
             v, cores, cms, kind = cpu_reference_run(10, 3, CPU_ROWS, args.config)
@@ -783,6 +859,9 @@ def main():
                 ref = fo.log_prob(x_host[:256].double())
                 got = flow.log_prob(x[:256]).double().cpu()
             line["cpu_baseline"]["gpu_vs_oracle_fp64_max_rel_err"] = float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max())
+            # ... and records the stock GPU path beside the CPU one: the same reference classes in torch eager on
+            # this B200 (ATen + cuBLAS), none of our kernels
+            line["cpu_baseline"]["torch_eager_b200"] = torch_eager_gpu_run(10, 3, CPU_ROWS, dev, args.config)
         print(json.dumps(line), flush=True)
     if world > 1:
         # every rank has contributed to the line above (the max-over-ranks all_reduce); leave together, and leave through
