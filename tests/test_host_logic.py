@@ -183,3 +183,28 @@ def test_affine_run_plan_groups_the_layers_between_couplings():
     m = cpl.mask.reshape(-1)
     assert torch.allclose((x * m) @ lin[0].weight.t(), x @ ws[0][0].t(), atol=1e-6)
     assert conditioner_weights(torch.nn.Sequential(torch.nn.Tanh()), cpl.mask) is None      # opaque conditioner
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): rank 0 prints ONE JSON line with the contract's keys --
+    `impl`, BASELINE.json's metric / unit, a `cpu_baseline` describing this very run (`kind` "reference" when the
+    `oracle/_ref` snapshot exists, else "port"), an `e2e` that moves no bytes -- and every other rank exits 0 silently."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3",
+           "--rows", "1024", "--config", "C4-adbench-D64"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="4")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "log_prob samples/sec" and j["unit"] == "samples/s"
+    assert j["higher_is_better"] is True and j["n_gpus"] == 2 and j["steps"] == 2 and j["warmup"] == 3
+    assert j["value"] > 0 and abs(j["value"] - 1024 / (j["ms_per_step"] * 1e-3)) < 1e-6 * j["value"]
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and "1024 rows" in cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "C4-adbench-D64" in j["config"]["workload"] and "model" not in j["config"]
+    # the other ranks of a torchrun launch: no work, no output, exit 0
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", LOCAL_RANK="1"), cwd=ROOT)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
