@@ -304,6 +304,40 @@ def cpu_reference_run(steps, warmup, rows, config=DEFAULT_CONFIG):
     return rows / med, cores, med * 1e3, kind
 
 
+def reference_train_run(device, rows, steps, warmup, config=DEFAULT_CONFIG):
+    """BASELINE.md section 3, training baseline: the `ADBenchFlow.fit`-equivalent step of the reference
+    (`adbench_wrapper.py:375-392`: zero_grad, loss = -log_prob(batch).mean(), backward, torch.optim.Adam step, the loss
+    read back on the host) with the reference's own classes on the oracle's src.usflows / pyro shim, in torch eager --
+    on the host cores (`device` "cpu") or on the B200 (ATen + cuBLAS; none of this repo's kernels).  Host wall clock
+    around whole steps (each ends with the reference's own host read of the loss, i.e. a device sync), median.
+    -> dict, or {"error": ...}."""
+    import oracle
+    out = {"batch": rows, "steps": steps, "warmup": warmup}
+    try:
+        ns = oracle.load_ref() if oracle.ref_available() else oracle.load()
+        flow = build_config_flow(ns, config, device).train()
+        opt = torch.optim.Adam(flow.parameters(), lr=1e-4)
+        d = CONFIGS[config][1]
+        x = torch.randn(rows, d, generator=torch.Generator().manual_seed(42)).to(device)
+        ts, last = [], float("nan")
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            loss = -flow.log_prob(x).mean()
+            loss.backward()
+            opt.step()
+            last = float(loss.detach().cpu())
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+        ts.sort()
+        med = ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2])
+        out.update({"value": rows / med, "unit": "samples/s", "ms_per_step": med * 1e3, "finite": last == last})
+        del flow, opt, x
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
 def torch_eager_gpu_run(steps, warmup, rows, dev, config=DEFAULT_CONFIG):
     """"also record torch-eager ON THE B200 (cuBLAS / ATen) as the existing GPU kernels to beat".  The same
     classes as `cpu_reference_run` (the reference's own NonUSFlow + MaskedAffineCoupling on the oracle's src.usflows / pyro
@@ -862,6 +896,15 @@ def main():
             # ... and records the stock GPU path beside the CPU one: the same reference classes in torch eager on
             # this B200 (ATen + cuBLAS), none of our kernels
             line["cpu_baseline"]["torch_eager_b200"] = torch_eager_gpu_run(10, 3, CPU_ROWS, dev, args.config)
+            # the second BASELINE metric's baselines: the reference's training step at B = 64 and
+            # 4096, on the host cores and in torch eager on this B200
+            if train_steps > 0:
+                line["cpu_baseline"]["train"] = {
+                    "unit": "samples/s", "cores": cores,
+                    "what": "reference classes, zero_grad + -log_prob.mean() + backward + torch.optim.Adam step + host read "
+                            "of the loss (adbench_wrapper.py:375-392), torch eager, fp32, median of whole-step wall times",
+                    "cpu": {f"B{b}": reference_train_run("cpu", b, n, 1, args.config) for b, n in ((TRAIN_SMALL_ROWS, 10), (train_B, 3))},
+                    "torch_eager_b200": {f"B{b}": reference_train_run(dev, b, 10, 3, args.config) for b in (TRAIN_SMALL_ROWS, train_B)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         # every rank has contributed to the line above (the max-over-ranks all_reduce); leave together, and leave through
