@@ -170,3 +170,105 @@ def test_fused_adam_has_no_cpu_path():
     p.grad = torch.ones(4)
     with pytest.raises(_lib.USFError):
         opt.step()
+
+
+def _header_prototypes():
+    """name -> (return class, [argument classes]) parsed from include/usflow_b200.h.  Classes: 'p' pointer (incl. the
+    stream handle), 'i64', 'i32', 'f32', 'f64', 'sz', 'str' (const char* return)."""
+    src = open(os.path.join(ROOT, "include", "usflow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+
+    def cls(decl, is_return=False):
+        d = " ".join(decl.replace("const", " ").split())
+        if "*" in d:
+            return "str" if (is_return and d.startswith("char")) else "p"
+        base = d.split(" ")[0] if not d.startswith("unsigned") else " ".join(d.split(" ")[:2])
+        table = {"int64_t": "i64", "int": "i32", "int32_t": "i32", "float": "f32", "double": "f64", "size_t": "sz",
+                 "usf_stream_t": "p", "long": "i64"}
+        assert base in table, f"unclassified C type in the header: {decl!r}"
+        return table[base]
+
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(usf_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if ret.startswith("typedef") or not ret:
+            continue
+        arglist = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[name] = (cls(ret, True), [cls(a) for a in arglist])
+    return protos
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every entry point's ctypes prototype in `nf4ad_b200/_lib.py` agrees with its C declaration argument by argument
+    (count and class: pointer / int64 / int / float / size_t) -- a float passed where the C side reads an int64, or a
+    missing argument, would not fail loudly at the call."""
+    from nf4ad_b200 import _lib
+    hdr = _header_prototypes()
+    assert set(hdr) == set(_declared())
+
+    def cls(t):
+        if t is None:
+            return "void"
+        if t is ctypes.c_char_p:
+            return "str"
+        if t is ctypes.c_void_p or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "p"
+        return {ctypes.c_int64: "i64", ctypes.c_longlong: "i64", ctypes.c_int32: "i32", ctypes.c_int: "i32",
+                ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_size_t: "sz"}[t]
+
+    bad = {}
+    for name, (ret, args) in hdr.items():
+        pres, pargs = _lib._PROTOS[name]
+        got = (cls(pres), [cls(a) for a in pargs])
+        want = (ret, args)
+        if got[0] == "str" and want[0] in ("str", "p"):
+            got = (want[0], got[1])
+        # a `const char*` ARGUMENT (c_char_p) is a pointer
+        got = (got[0], ["p" if a == "str" else a for a in got[1]])
+        if got != want:
+            bad[name] = {"header": want, "ctypes": got}
+    assert not bad, bad
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The descriptor structs `_lib.py` / `optim.py` hand to the library have the C compiler's own layout: a tiny C program
+    including include/usflow_b200.h (plain C: the header must stay C-compatible) prints sizeof / offsetof of every field."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    from nf4ad_b200 import _lib
+    from nf4ad_b200.optim import _AdamTensor
+    structs = {"usf_linear_desc": (_lib.LinearDesc, ["W", "Wb", "bias", "N", "K", "ldw"]),
+               "usf_block_desc": (_lib.BlockDesc, ["G", "b_off", "n_mlp", "mlp", "Da", "Db", "C", "affine", "clamp"]),
+               "usf_stack_desc": (_lib.StackDesc, ["D", "n_blocks", "blocks", "G_final", "inverse", "base_kind", "loc",
+                                                   "inv_scale", "const_term", "ctx_dim"]),
+               "usf_adam_tensor": (_AdamTensor, ["p", "g", "m", "v", "n"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "usflow_b200.h"', "int main(void) {"]
+    for cname, (_, fields) in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  printf("USF_MAX_MLP %d\\n", USF_MAX_MLP);', "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = {}
+    for line in out.splitlines():
+        parts = line.split()
+        if parts[0] == "USF_MAX_MLP":
+            assert int(parts[1]) == _lib.USF_MAX_MLP
+            continue
+        seen[(parts[0], parts[1])] = int(parts[2])
+    for cname, (ctype, fields) in structs.items():
+        assert seen[(cname, "size")] == ctypes.sizeof(ctype), cname
+        declared = [f for f, _ in ctype._fields_]
+        assert declared == fields, (cname, declared)          # same fields, same order
+        for f in fields:
+            assert seen[(cname, f)] == getattr(ctype, f).offset, (cname, f)
