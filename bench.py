@@ -871,7 +871,7 @@ def main():
                                              "ms_per_step": train3_ms / train_steps},
                              "fp32_path": {"value": train_B * world * train_steps / (train32_ms * 1e-3),
                                            "ms_per_step": train32_ms / train_steps}}
-            if train_small_ms == train_small_ms:          # (not NaN: measured on this run)
+            if world == 1 and train_small_ms == train_small_ms:          # (single-GPU line; not NaN: measured on this run)
                 line["train"]["small_batch"] = {
                     "batch_per_gpu": TRAIN_SMALL_ROWS,
                     "value": TRAIN_SMALL_ROWS * world * train_steps / (train_small_ms * 1e-3),
