@@ -893,6 +893,23 @@ def main():
                 ref = fo.log_prob(x_host[:256].double())
                 got = flow.log_prob(x[:256]).double().cpu()
             line["cpu_baseline"]["gpu_vs_oracle_fp64_max_rel_err"] = float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max())
+            # north star: "inverse(forward(x)) round-trip error reported" -- data -> latent -> data through both fused
+            # directions of the timed flow, worst coordinate relative to its row's largest magnitude, per tier
+            try:
+                rt = {}
+                keep = flow.precision
+                with torch.no_grad():
+                    xs = x[:256].float()
+                    scale_ = xs.abs().amax(dim=1, keepdim=True).clamp_min(1.0)
+                    for tier_ in dict.fromkeys((keep, "auto")):
+                        flow.precision = tier_
+                        back = flow.latent_to_data(flow.backward(xs))
+                        rt[f"{tier_}->{flow.effective_precision}"] = float(((back - xs).abs() / scale_).max())
+                flow.precision = keep
+                line["cpu_baseline"]["round_trip_max_err"] = rt
+            except Exception as e:
+                flow.precision = keep
+                line["cpu_baseline"]["round_trip_max_err"] = {"error": f"{type(e).__name__}: {e}"[:200]}
             # ... and records the stock GPU path beside the CPU one: the same reference classes in torch eager on
             # this B200 (ATen + cuBLAS), none of our kernels
             line["cpu_baseline"]["torch_eager_b200"] = torch_eager_gpu_run(10, 3, CPU_ROWS, dev, args.config)
