@@ -2,8 +2,9 @@
 
 Scoring shards by rows: every op of the density path is per-row, weights are
 replicated, so there is NO collective on the data path -- only one all-gather of the (rows,) fp32
-scores.  Training is data parallel: one flat all-reduce (sum) of the gradients per step, then the same
-optimizer step on every rank.
+scores.  Training is data parallel: every `.grad` is a view into one flat fp32 buffer that NCCL averages in place, in
+buckets handed over while the backward pass is still running, then the same optimizer step on every rank -- all inside the
+step's CUDA graph (`DataParallelTrainer`).
 """
 import os
 import time
