@@ -6,9 +6,11 @@
 (torch `transformed_distribution.py:143-190`), but execute as:
 
   * inference (no autograd): ONE fused launch chain over a packed layer-descriptor array
-    (`nf4ad_b200.stack` -> `usf_stack_run`), fp32 SIMT or bf16 tcgen05 GEMMs (`flow.precision`);
-  * training (autograd): the layer-wise fp32 kernels with their hand-written backward kernels
-    (`nf4ad_b200.ops` autograd Functions).
+    (`nf4ad_b200.stack` -> `usf_stack_run`) -- bf16 / bf16x2 / 3xTF32 tcgen05 GEMMs or fp32 FFMA kernels
+    (`flow.precision`, resolved per weight version by `Flow._tier`), one whole-stack kernel for small event shapes;
+  * training (autograd): the layer-wise kernels with their hand-written backward kernels (`nf4ad_b200.ops` autograd
+    Functions); in the tensor-core tiers the affine runs between couplings are composed in weight space
+    (`Flow._compose_affine_runs`) so the batch sees one GEMM per run.
 
 CUDA tensors only -- a CPU tensor raises (`USFError`); the CPU restatement lives in `oracle/`.
 """
@@ -108,7 +110,7 @@ class Flow(torch.nn.Module):
             [l for l in self.layers if isinstance(l, torch.nn.Module)])
         self.base_distribution = base_distribution
         self.device = device
-        self.precision = _default_precision()   # "fp32" / "tf32x3" (<=1e-4 tier) or "bf16" (tcgen05, <=1e-2 tier, verified: _tier)
+        self.precision = _default_precision()   # "auto" (default) / "fp32" / "bf16x2" / "tf32x3" (<= 1e-4 tiers) or "bf16" (<= 1e-2, verified: _tier)
         self.effective_precision = self.precision
         self.bf16_calibration_err = None
         # run-to-run bit-identical log_prob (the reference's eager CPU path is deterministic): per-row partial sums go to
